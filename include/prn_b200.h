@@ -1,0 +1,101 @@
+/* prn_b200.h — C ABI of libprn_b200.so: the sm_100a kernels behind PlaneRecNet's dense hot path.
+ *
+ * The reference (EryiXie/PlaneRecNet) has no FFI of its own: its hot path is Python calling
+ * torch/torchvision operators.  Each entry point below therefore replaces one *operator call site*
+ * of the reference (cited per function as file:line under /root/reference) and takes what that
+ * operator takes, flattened to plain pointers and sizes: raw device pointers, int32 dims, a
+ * cudaStream_t passed as void*.  No torch types cross this boundary.
+ *
+ * Conventions
+ *   - activations are NHWC ("pixel-major"), 16-bit (PRN_BF16 or PRN_F16), channel counts padded to
+ *     a multiple of 64 where they feed a tensor-core contraction;
+ *   - every function is asynchronous on `stream`, never allocates, never synchronises, keeps no
+ *     global state besides a cached driver entry point, and returns PRN_OK or a negative PrnStatus;
+ *   - prn_last_error() returns a thread-local human readable string for the last failure.
+ */
+#ifndef PRN_B200_H_
+#define PRN_B200_H_
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum PrnStatus {
+  PRN_OK = 0,
+  PRN_ERR_INVALID = -1,   /* bad argument (shape/alignment/NULL) */
+  PRN_ERR_CUDA = -2,      /* a CUDA runtime/driver call failed    */
+  PRN_ERR_UNSUPPORTED = -3
+} PrnStatus;
+
+typedef enum PrnDtype { PRN_F16 = 0, PRN_BF16 = 1 } PrnDtype;
+
+typedef enum PrnAct {
+  PRN_ACT_NONE = 0,
+  PRN_ACT_RELU = 1,
+  PRN_ACT_SIGMOID = 2,
+  PRN_ACT_SOFTPLUS = 3,      /* beta 1, threshold 20: planerecnet.py:572 */
+  PRN_ACT_DCN_OFFMASK = 4,   /* cols [0,18): clamp(+-act_param); cols [18,27): 2*sigmoid: models/dcn.py:56-57 */
+  PRN_ACT_SIGMOID_AVG4 = 5   /* sigmoid, then mean over 4 consecutive rows; output has M/4 rows */
+} PrnAct;
+
+typedef enum PrnPadMode { PRN_PAD_ZERO = 0, PRN_PAD_REFLECT = 1 } PrnPadMode;
+
+/* One convolution-like contraction  out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] ),
+ * m = (image, ho, wo) flattened, k = (ky, kx, c) with c running over src0's then src1's channels.
+ * Replaces F.conv2d / nn.Conv2d call sites: models/backbone.py:56-66, models/fpn.py:55,61,
+ * planerecnet.py:386-391, 478-495, 592-605, and (with `dcn_offmask` set) the
+ * torchvision.ops.deform_conv2d call at models/dcn.py:59-66. */
+typedef struct PrnConv {
+  /* ---- A operand: NHWC 16-bit sources, channel-concatenated (torch.cat(dim=1) in the reference) */
+  const void* src0;
+  const void* src1;        /* NULL when c1 == 0 */
+  int32_t c0, c1;          /* channels, each a multiple of 64 (c1 may be 0) */
+  int32_t batch, h_in, w_in;
+  int32_t upsample;        /* 1, or 2 = nearest x2 applied before padding (planerecnet.py:541) */
+  int32_t ksize, stride, pad;
+  int32_t pad_mode;        /* PrnPadMode; reflect = nn.ReflectionPad2d (planerecnet.py:516) */
+  int32_t h_out, w_out;
+  /* ---- deformable sampling (NULL for a plain conv): fp32 [M][32] rows = 18 offsets (dy,dx per tap),
+   *      9 modulators, 5 pad, as written by a PRN_ACT_DCN_OFFMASK conv. */
+  const float* dcn_offmask;
+  /* ---- B operand: packed weights [n_rows][ksize*ksize*(c0+c1)], 16-bit, K contiguous.
+   *      w_group_rows != 0: per-image weights, image g uses rows [g*w_group_rows, +n_pad). */
+  const void* weight;
+  int32_t n_pad;           /* output columns computed per group, multiple of 16 */
+  int32_t w_rows_total;    /* rows of the weight matrix in memory */
+  int32_t w_group_rows;
+  const float* bias;       /* fp32 [n_pad] (shared by all groups) or NULL */
+  /* ---- epilogue */
+  const void* residual;    /* 16-bit [M][ld_res] added before the activation, or NULL */
+  int32_t ld_res;
+  int32_t act;             /* PrnAct */
+  float act_param;
+  void* out16;             /* 16-bit output, row pitch ld_out16 elements, or NULL */
+  int32_t ld_out16;
+  float* out32;            /* fp32 output, row pitch ld_out32 elements, or NULL */
+  int32_t ld_out32;
+  int32_t out_img_rows;    /* rows between consecutive images in the outputs; 0 = h_out*w_out */
+  /* per-(image, channel-group) sums for GroupNorm: stats[(img*G + g)*2 + {0,1}] += {sum, sumsq};
+   * G = n_pad / stats_cg.  NULL = off.  stats_cg == 0 with stats != NULL: per-channel sums over all
+   * rows (BatchNorm batch statistics): stats[n*2 + {0,1}]. */
+  float* stats;
+  int32_t stats_cg;
+  int32_t dtype;           /* PrnDtype of src/weight/residual/out16 */
+} PrnConv;
+
+const char* prn_last_error(void);
+int prn_abi_version(void);
+/* SM count of the current device (grid sizing is done inside the library; exposed for bench/roofline). */
+int prn_device_sm_count(void);
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMEM accumulators, TMA-fed weights). */
+int prn_conv2d_fwd(const PrnConv* desc, void* stream);
+/* Workspace-free helper: bytes of dynamic shared memory and CTAs the launch would use (for tests). */
+int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRN_B200_H_ */

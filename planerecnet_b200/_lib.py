@@ -1,0 +1,86 @@
+"""ctypes binding of libprn_b200.so (the C ABI declared in include/prn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libprn_b200.so")
+
+PRN_F16, PRN_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS, ACT_DCN_OFFMASK, ACT_SIGMOID_AVG4 = range(6)
+PAD_ZERO, PAD_REFLECT = 0, 1
+
+
+class PrnError(RuntimeError):
+    pass
+
+
+class PrnConv(C.Structure):
+    _fields_ = [
+        ("src0", C.c_void_p), ("src1", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32),
+        ("batch", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
+        ("upsample", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("pad_mode", C.c_int32),
+        ("h_out", C.c_int32), ("w_out", C.c_int32),
+        ("dcn_offmask", C.c_void_p),
+        ("weight", C.c_void_p),
+        ("n_pad", C.c_int32), ("w_rows_total", C.c_int32), ("w_group_rows", C.c_int32),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ld_res", C.c_int32),
+        ("act", C.c_int32), ("act_param", C.c_float),
+        ("out16", C.c_void_p), ("ld_out16", C.c_int32),
+        ("out32", C.c_void_p), ("ld_out32", C.c_int32),
+        ("out_img_rows", C.c_int32),
+        ("stats", C.c_void_p), ("stats_cg", C.c_int32),
+        ("dtype", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PrnError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the PlaneRecNet hot path)")
+    l = C.CDLL(LIB_PATH)
+    l.prn_last_error.restype = C.c_char_p
+    l.prn_abi_version.restype = C.c_int
+    l.prn_device_sm_count.restype = C.c_int
+    for name in EXPORTS:
+        if not hasattr(l, name):
+            raise PrnError(f"{LIB_PATH} does not export {name}")
+        getattr(l, name).restype = C.c_int if name != "prn_last_error" else C.c_char_p
+    _lib = l
+    return l
+
+
+# every symbol include/prn_b200.h declares (tests check the header against this list and the .so)
+EXPORTS = [
+    "prn_last_error", "prn_abi_version", "prn_device_sm_count",
+    "prn_conv2d_fwd", "prn_conv2d_plan",
+]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().prn_last_error().decode("utf-8", "replace")
+        raise PrnError(f"{what or 'libprn_b200'} failed (status {rc}): {msg}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

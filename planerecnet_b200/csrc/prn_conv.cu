@@ -1,0 +1,568 @@
+// prn_conv.cu — implicit-GEMM convolution for sm_100a.
+//
+// out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] )
+//   m = (image, ho, wo) flattened, 128 rows per CTA tile (one TMEM lane per row)
+//   k = (ky, kx, c), walked in 64-element blocks (128 B rows, 128B-swizzled K-major smem tiles)
+//   n = output channels, n_tile <= 256 columns of fp32 accumulators in TMEM, double buffered
+//
+// Warp roles (320 threads, persistent CTAs, static round-robin tile schedule):
+//   warps 0-3  epilogue   tcgen05.ld -> bias/residual/activation/statistics -> NHWC stores
+//   warps 4-7  A producer im2col gather straight from the NHWC activation: one 16-byte cp.async per
+//                         (pixel, 8 channels), zero-fill / reflect / nearest-x2 / two-source concat
+//                         resolved in the address computation (nothing is materialised in HBM);
+//                         with `dcn_offmask` the rows are bilinear-sampled + modulated in registers
+//                         (torchvision deform_conv2d semantics) and written with st.shared
+//   warp 8     B producer one TMA box {64 k, n_tile rows} of the packed weights per k-block
+//   warp 9     MMA issuer one thread issuing tcgen05.mma (M=128, N=n_tile, K=16) x4 per k-block and
+//                         tcgen05.commit to recycle the smem stage / publish the accumulator
+//
+// Replaces the nn.Conv2d / F.conv2d / deform_conv2d call sites listed in include/prn_b200.h.
+#include <stdio.h>
+#include "prn_internal.h"
+#include "prn_ptx.cuh"
+
+namespace prn {
+
+constexpr int kTileM = 128;
+constexpr int kATileBytes = kTileM * 128;  // 128 rows x 64 16-bit elements
+constexpr int kEpiWarps = 4;
+constexpr int kProdWarps = 4;
+constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
+constexpr int kLag = 3;        // cp.async groups a producer thread keeps in flight
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 225 * 1024;
+
+struct ConvKParams {
+  PrnConv d;
+  int m_group;        // rows per weight group
+  int groups;
+  int imgs_per_group;
+  int m_tiles, n_tiles, total_tiles;
+  int n_tile;
+  int stages;
+  int tmem_cols;
+  int kb_per_tap;
+  int num_kb;
+  int hw_out;
+  int out_img_rows;
+  uint32_t idesc;
+};
+
+__device__ __forceinline__ float act_apply(float x, int act, float param, int col) {
+  switch (act) {
+    case PRN_ACT_RELU: return fmaxf(x, 0.f);
+    case PRN_ACT_SIGMOID:
+    case PRN_ACT_SIGMOID_AVG4: return 1.f / (1.f + __expf(-x));
+    case PRN_ACT_SOFTPLUS: return x > 20.f ? x : log1pf(expf(x));
+    case PRN_ACT_DCN_OFFMASK:
+      if (col < 18) return fminf(fmaxf(x, -param), param);
+      if (col < 27) return 2.f / (1.f + __expf(-x));
+      return 0.f;
+    default: return x;
+  }
+}
+
+template <typename T, bool kDCN>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+
+  // control block (first 1 KB): mbarriers + TMEM base slot
+  const uint32_t bar_full = base;             // [kMaxStages] x 8 B
+  const uint32_t bar_empty = base + 64;       // [kMaxStages] x 8 B
+  const uint32_t bar_tfull = base + 128;      // [2]
+  const uint32_t bar_tempty = base + 144;     // [2]
+  const uint32_t tmem_slot = base + 160;
+  const uint32_t a_base = base + 1024;
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
+  const uint32_t b_base = a_base + static_cast<uint32_t>(p.stages) * kATileBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const PrnConv& d = p.d;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, kProdWarps * 32 + 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, kEpiWarps * 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
+
+  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+    // =========================================================== A producer
+    const int pw = warp - kEpiWarps;
+    const int sub = lane >> 3;    // row within a group of 4
+    const int chunk = lane & 7;   // 16-byte chunk (8 channels) within the 128-byte row
+    const int ups_shift = d.upsample == 2 ? 1 : 0;
+    const int h_eff = d.h_in << ups_shift, w_eff = d.w_in << ups_shift;
+    int s = 0;
+    uint32_t ph = 0;
+    int s_lag = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int rest = tile / p.n_tiles;
+      const int mt = rest % p.m_tiles;
+      const int g = rest / p.m_tiles;
+      int img_pix[8], hy[8], wx[8];
+      int m_glob[8];
+      uint32_t valid = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = pw * 32 + i * 4 + sub;
+        const int m = mt * kTileM + r;
+        const bool v = m < p.m_group;
+        const int mm = v ? m : 0;
+        const int n_local = mm / p.hw_out;
+        const int rem = mm - n_local * p.hw_out;
+        const int ho = rem / d.w_out;
+        const int wo = rem - ho * d.w_out;
+        const int img = g * p.imgs_per_group + n_local;
+        img_pix[i] = img * d.h_in * d.w_in;
+        hy[i] = ho * d.stride - d.pad;
+        wx[i] = wo * d.stride - d.pad;
+        m_glob[i] = g * p.m_group + mm;
+        valid |= (v ? 1u : 0u) << i;
+      }
+      const int taps = d.ksize * d.ksize;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
+        if constexpr (!kDCN) {
+          int pix[8];
+          uint32_t ok = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            int y = hy[i] + ky, x = wx[i] + kx;
+            bool in = (valid >> i) & 1u;
+            if (d.pad_mode == PRN_PAD_REFLECT) {
+              y = y < 0 ? -y : (y >= h_eff ? 2 * h_eff - 2 - y : y);
+              x = x < 0 ? -x : (x >= w_eff ? 2 * w_eff - 2 - x : x);
+            } else {
+              in = in && y >= 0 && y < h_eff && x >= 0 && x < w_eff;
+            }
+            pix[i] = in ? img_pix[i] + (y >> ups_shift) * d.w_in + (x >> ups_shift) : 0;
+            ok |= (in ? 1u : 0u) << i;
+          }
+          for (int cc = 0; cc < p.kb_per_tap; ++cc) {
+            const int c = cc * 64;
+            const bool first = c < d.c0;
+            const uint8_t* src = static_cast<const uint8_t*>(first ? d.src0 : d.src1);
+            const int cs = first ? d.c0 : d.c1;
+            const int coff = (first ? c : c - d.c0) + chunk * 8;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = pw * 32 + i * 4 + sub;
+              const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
+              const bool in = (ok >> i) & 1u;
+              const uint8_t* sp = src + (static_cast<size_t>(pix[i]) * cs + coff) * 2;
+              cp_async16(dst, in ? sp : src, in ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (it >= kLag) {
+              cp_async_wait<kLag>();
+              fence_proxy_async_smem();
+              mbar_arrive(bar_full + 8 * s_lag);
+              if (++s_lag == p.stages) s_lag = 0;
+            }
+            ++it;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        } else {
+          // ---- modulated deformable sampling (models/dcn.py:59-66, torchvision deform_conv2d):
+          //      value = mask * bilinear(x, ho*s - pad + ky + dy, wo*s - pad + kx + dx), zero outside
+          //      (-1, H) x (-1, W); corners outside the image contribute 0.
+          const uint8_t* src = static_cast<const uint8_t*>(d.src0);
+          const int cs = d.c0;
+          for (int cc = 0; cc < p.kb_per_tap; ++cc) {
+            const int coff = cc * 64 + chunk * 8;
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+              const int r = pw * 32 + i * 4 + sub;
+              const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
+              float acc[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+              if ((valid >> i) & 1u) {
+                const float* om = d.dcn_offmask + static_cast<size_t>(m_glob[i]) * 32;
+                const float py = static_cast<float>(hy[i] + ky) + __ldg(om + 2 * tap);
+                const float px = static_cast<float>(wx[i] + kx) + __ldg(om + 2 * tap + 1);
+                const float mk = __ldg(om + 18 + tap);
+                if (py > -1.f && py < static_cast<float>(d.h_in) && px > -1.f && px < static_cast<float>(d.w_in)) {
+                  const float fy = floorf(py), fx = floorf(px);
+                  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+                  const float ly = py - fy, lx = px - fx;
+                  const float wy[2] = {1.f - ly, ly};
+                  const float wxx[2] = {1.f - lx, lx};
+#pragma unroll
+                  for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx) {
+                      const int yy = y0 + cy, xx = x0 + cx;
+                      if (yy >= 0 && yy < d.h_in && xx >= 0 && xx < d.w_in) {
+                        const float wgt = wy[cy] * wxx[cx] * mk;
+                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(
+                            src + (static_cast<size_t>(img_pix[i] + yy * d.w_in + xx) * cs + coff) * 2));
+                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                          const float2 f = Pack2<T>::unpack(w4[j]);
+                          acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]);
+                          acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
+                        }
+                      }
+                    }
+                  }
+                }
+              }
+              const uint32_t o0 = Pack2<T>::pack(acc[0], acc[1]), o1 = Pack2<T>::pack(acc[2], acc[3]);
+              const uint32_t o2 = Pack2<T>::pack(acc[4], acc[5]), o3 = Pack2<T>::pack(acc[6], acc[7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_full + 8 * s);
+            ++it;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+    if constexpr (!kDCN) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      const uint32_t pending = it < static_cast<uint32_t>(kLag) ? it : static_cast<uint32_t>(kLag);
+      for (uint32_t j = 0; j < pending; ++j) {
+        mbar_arrive(bar_full + 8 * s_lag);
+        if (++s_lag == p.stages) s_lag = 0;
+      }
+    }
+  } else if (warp == 8) {
+    // =========================================================== B producer (TMA)
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int g = (tile / p.n_tiles) / p.m_tiles;
+        const int row0 = g * d.w_group_rows + nt * p.n_tile;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * s, b_stage_bytes);
+          tma_load_2d(b_base + static_cast<uint32_t>(s) * b_stage_bytes, &tmap_w, bar_full + 8 * s, kb * 64, row0);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + static_cast<uint32_t>(s) * kATileBytes;
+          const uint32_t b_addr = b_base + static_cast<uint32_t>(s) * b_stage_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(bar_tfull + 8 * acc);
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1u;
+      }
+    }
+  } else {
+    // =========================================================== epilogue (warps 0-3)
+    const int q = warp;  // TMEM lane quarter
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    const bool avg4 = d.act == PRN_ACT_SIGMOID_AVG4;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int mt = rest % p.m_tiles;
+      const int g = rest / p.m_tiles;
+      const int n0 = nt * p.n_tile;
+      const int m = mt * kTileM + q * 32 + lane;
+      const bool valid = m < p.m_group;
+      const int mm = valid ? m : 0;
+      const int n_local = mm / p.hw_out;
+      const int pp = mm - n_local * p.hw_out;
+      const int img = g * p.imgs_per_group + n_local;
+      const size_t orow = avg4 ? static_cast<size_t>(img) * p.out_img_rows + (pp >> 2)
+                               : static_cast<size_t>(img) * p.out_img_rows + pp;
+      const size_t rrow = static_cast<size_t>(g) * p.m_group + mm;
+      const bool img_uniform = __all_sync(0xffffffffu, valid && img == __shfl_sync(0xffffffffu, img, 0));
+
+      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      for (int c = 0; c < p.n_tile; c += 16) {
+        if (n0 + c >= d.n_pad) break;
+        uint32_t v[16];
+        tmem_ld_x16(t_row + c, v);
+        tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+        if (d.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(d.bias + n0 + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 b = __ldg(bp + j);
+            x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+          }
+        }
+        if (d.residual && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(d.residual) + rrow * d.ld_res + n0 + c);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 rv = __ldg(rp + h);
+            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = Pack2<T>::unpack(w4[j]);
+              x[8 * h + 2 * j] += f.x;
+              x[8 * h + 2 * j + 1] += f.y;
+            }
+          }
+        }
+        if (d.stats != nullptr && d.stats_cg > 0) {
+          // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators)
+          const int cg = d.stats_cg;
+          const int G = d.n_pad / cg;
+          float q1[4], q2[4];  // sums over quads of columns (static indexing keeps x[] in registers)
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            q1[qd] = (x[4 * qd] + x[4 * qd + 1]) + (x[4 * qd + 2] + x[4 * qd + 3]);
+            q2[qd] = (x[4 * qd] * x[4 * qd] + x[4 * qd + 1] * x[4 * qd + 1]) +
+                     (x[4 * qd + 2] * x[4 * qd + 2] + x[4 * qd + 3] * x[4 * qd + 3]);
+          }
+          if (cg >= 8) { q1[0] += q1[1]; q2[0] += q2[1]; q1[2] += q1[3]; q2[2] += q2[3]; }
+          if (cg == 16) { q1[0] += q1[2]; q2[0] += q2[2]; }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if ((qd * 4) % cg != 0) continue;
+            float s1 = q1[qd], s2 = q2[qd];
+            const int gi = (n0 + c + qd * 4) / cg;
+            if (img_uniform) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              }
+              if (lane == 0) {
+                atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
+                atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
+              }
+            } else if (valid) {
+              atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
+              atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
+            }
+          }
+        } else if (d.stats != nullptr) {
+          // BatchNorm batch statistics: per-channel sums over all rows
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float s1 = valid ? x[j] : 0.f;
+            float s2 = s1 * s1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) {
+              atomicAdd(d.stats + static_cast<size_t>(n0 + c + j) * 2, s1);
+              atomicAdd(d.stats + static_cast<size_t>(n0 + c + j) * 2 + 1, s2);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = act_apply(x[j], d.act, d.act_param, n0 + c + j);
+        bool store = valid;
+        if (avg4) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = x[j];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            x[j] = 0.25f * t;
+          }
+          store = valid && (lane & 3) == 0;
+        }
+        if (store) {
+          if (d.out16) {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(d.out16) + orow * d.ld_out16 + n0 + c);
+            uint4 o;
+            o.x = Pack2<T>::pack(x[0], x[1]); o.y = Pack2<T>::pack(x[2], x[3]);
+            o.z = Pack2<T>::pack(x[4], x[5]); o.w = Pack2<T>::pack(x[6], x[7]);
+            op[0] = o;
+            o.x = Pack2<T>::pack(x[8], x[9]); o.y = Pack2<T>::pack(x[10], x[11]);
+            o.z = Pack2<T>::pack(x[12], x[13]); o.w = Pack2<T>::pack(x[14], x[15]);
+            op[1] = o;
+          }
+          if (d.out32) {
+            float4* op = reinterpret_cast<float4*>(d.out32 + orow * d.ld_out32 + n0 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8 * acc);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 9) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int plan(const PrnConv& d, ConvKParams* p) {
+  PRN_REQUIRE(d.src0 != nullptr && d.weight != nullptr, "conv: src0/weight must be non-NULL");
+  PRN_REQUIRE(d.c0 > 0 && d.c0 % 64 == 0 && d.c1 >= 0 && d.c1 % 64 == 0, "conv: channel counts must be multiples of 64 (c0=%d c1=%d)", d.c0, d.c1);
+  PRN_REQUIRE(d.c1 == 0 || d.src1 != nullptr, "conv: src1 is NULL but c1=%d", d.c1);
+  PRN_REQUIRE(d.batch > 0 && d.h_in > 0 && d.w_in > 0 && d.h_out > 0 && d.w_out > 0, "conv: bad spatial dims");
+  PRN_REQUIRE(d.upsample == 1 || d.upsample == 2, "conv: upsample must be 1 or 2");
+  PRN_REQUIRE(d.ksize >= 1 && d.ksize <= 7 && d.stride >= 1 && d.pad >= 0, "conv: bad ksize/stride/pad");
+  PRN_REQUIRE(d.pad_mode == PRN_PAD_ZERO || d.pad_mode == PRN_PAD_REFLECT, "conv: bad pad_mode");
+  PRN_REQUIRE(d.n_pad > 0 && d.n_pad % 16 == 0, "conv: n_pad must be a positive multiple of 16 (got %d)", d.n_pad);
+  PRN_REQUIRE(d.dtype == PRN_BF16 || d.dtype == PRN_F16, "conv: dtype must be PRN_BF16 or PRN_F16");
+  PRN_REQUIRE(d.out16 != nullptr || d.out32 != nullptr, "conv: no output buffer");
+  PRN_REQUIRE(d.out16 == nullptr || d.ld_out16 % 8 == 0, "conv: ld_out16 must be a multiple of 8");
+  PRN_REQUIRE(d.out32 == nullptr || d.ld_out32 % 4 == 0, "conv: ld_out32 must be a multiple of 4");
+  PRN_REQUIRE(d.residual == nullptr || d.ld_res % 8 == 0, "conv: ld_res must be a multiple of 8");
+  PRN_REQUIRE(d.stats == nullptr || d.stats_cg == 0 || d.stats_cg == 4 || d.stats_cg == 8 || d.stats_cg == 16,
+              "conv: stats_cg must be 0, 4, 8 or 16");
+  const int h_eff = d.h_in * d.upsample, w_eff = d.w_in * d.upsample;
+  PRN_REQUIRE((h_eff + 2 * d.pad - d.ksize) / d.stride + 1 == d.h_out && (w_eff + 2 * d.pad - d.ksize) / d.stride + 1 == d.w_out,
+              "conv: h_out/w_out inconsistent with input dims (%dx%d -> %dx%d)", h_eff, w_eff, d.h_out, d.w_out);
+  PRN_REQUIRE(d.pad_mode != PRN_PAD_REFLECT || (d.pad < h_eff && d.pad < w_eff), "conv: reflect pad too large");
+  if (d.dcn_offmask) {
+    PRN_REQUIRE(d.c1 == 0 && d.upsample == 1 && d.pad_mode == PRN_PAD_ZERO && d.ksize == 3,
+                "conv: deformable sampling needs a single source, 3x3, zero padding");
+  }
+  p->d = d;
+  p->hw_out = d.h_out * d.w_out;
+  if (d.w_group_rows != 0) {
+    p->groups = d.batch;
+    p->imgs_per_group = 1;
+    PRN_REQUIRE(d.w_group_rows >= 0 && (long long)d.w_group_rows * (d.batch - 1) + d.n_pad <= (long long)d.w_rows_total + 256,
+                "conv: grouped weights exceed w_rows_total");
+  } else {
+    p->groups = 1;
+    p->imgs_per_group = d.batch;
+  }
+  p->m_group = p->imgs_per_group * p->hw_out;
+  if (d.act == PRN_ACT_SIGMOID_AVG4) {
+    PRN_REQUIRE(p->hw_out % 4 == 0, "conv: SIGMOID_AVG4 needs rows per image divisible by 4");
+    p->out_img_rows = d.out_img_rows ? d.out_img_rows : p->hw_out / 4;
+  } else {
+    p->out_img_rows = d.out_img_rows ? d.out_img_rows : p->hw_out;
+  }
+  // N tiling: one tile if it fits TMEM double-buffered, else 256/128-wide tiles.
+  int n_tile;
+  if (d.n_pad <= 256) n_tile = d.n_pad;
+  else if (d.n_pad % 256 == 0) n_tile = 256;
+  else n_tile = 128;
+  p->m_tiles = ceil_div(p->m_group, kTileM);
+  // Small problems: narrower tiles so that more SMs get work.
+  const int sms = sm_count();
+  while (n_tile > 64 && n_tile % 32 == 0 && p->groups * p->m_tiles * ceil_div(d.n_pad, n_tile) < sms) n_tile /= 2;
+  p->n_tile = n_tile;
+  p->n_tiles = ceil_div(d.n_pad, n_tile);
+  p->total_tiles = p->groups * p->m_tiles * p->n_tiles;
+  int cols = 32;
+  while (cols < 2 * n_tile) cols *= 2;
+  p->tmem_cols = cols;
+  const int stage_bytes = kATileBytes + n_tile * 128;
+  int stages = (kSmemBudget - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  PRN_REQUIRE(stages > kLag, "conv: not enough shared memory for %d stages", kLag + 1);
+  p->stages = stages;
+  p->kb_per_tap = (d.c0 + d.c1) / 64;
+  p->num_kb = d.ksize * d.ksize * p->kb_per_tap;
+  p->idesc = umma_idesc(d.dtype == PRN_BF16 ? 1u : 0u, kTileM, static_cast<uint32_t>(n_tile));
+  return PRN_OK;
+}
+
+template <typename T, bool kDCN>
+static int launch(const CUtensorMap& tm, const ConvKParams& p, int grid, size_t smem, cudaStream_t st) {
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    configured = true;
+  }
+  conv_umma_kernel<T, kDCN><<<grid, kThreads, smem, st>>>(tm, p);
+  PRN_CUDA(cudaGetLastError());
+  return PRN_OK;
+}
+
+}  // namespace prn
+
+extern "C" int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid) {
+  if (!desc) return prn::set_error(PRN_ERR_INVALID, "conv: NULL descriptor");
+  prn::ConvKParams p;
+  int rc = prn::plan(*desc, &p);
+  if (rc != PRN_OK) return rc;
+  if (n_tile) *n_tile = p.n_tile;
+  if (stages) *stages = p.stages;
+  if (grid) *grid = p.total_tiles < prn::sm_count() ? p.total_tiles : prn::sm_count();
+  return PRN_OK;
+}
+
+extern "C" int prn_conv2d_fwd(const PrnConv* desc, void* stream) {
+  using namespace prn;
+  if (!desc) return set_error(PRN_ERR_INVALID, "conv: NULL descriptor");
+  ConvKParams p;
+  int rc = plan(*desc, &p);
+  if (rc != PRN_OK) return rc;
+  const PrnConv& d = p.d;
+  CUtensorMap tm;
+  const uint64_t kdim = static_cast<uint64_t>(d.ksize) * d.ksize * (d.c0 + d.c1);
+  const uint64_t rows = d.w_rows_total > 0 ? static_cast<uint64_t>(d.w_rows_total) : static_cast<uint64_t>(d.n_pad);
+  rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile), d.dtype);
+  if (rc != PRN_OK) return rc;
+  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const size_t smem = 2048 + static_cast<size_t>(p.stages) * (kATileBytes + p.n_tile * 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool dcn = d.dcn_offmask != nullptr;
+  if (d.dtype == PRN_BF16)
+    return dcn ? launch<__nv_bfloat16, true>(tm, p, grid, smem, st) : launch<__nv_bfloat16, false>(tm, p, grid, smem, st);
+  return dcn ? launch<__half, true>(tm, p, grid, smem, st) : launch<__half, false>(tm, p, grid, smem, st);
+}

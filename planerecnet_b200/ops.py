@@ -1,0 +1,85 @@
+"""Thin Python wrappers over the C ABI: build the plain-C descriptors from torch tensors (torch is only
+the owner of device memory and streams here) and launch on the current CUDA stream."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def torch_dtype(dtype):
+    return torch.bfloat16 if dtype == L.PRN_BF16 else torch.float16
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pack_conv_weight(w, c_splits=None, n_pad=None, dtype=L.PRN_BF16, scale=None):
+    """[Cout, Cin, kh, kw] fp32 -> packed [n_pad, kh*kw*sum(c_pad)] 16-bit, K ordered (ky, kx, c).
+
+    c_splits: list of (real_channels, padded_channels) per concatenated source; channels of each source
+    are zero-padded to its padded width.  scale: optional per-output-channel fp32 factor (folded BN)."""
+    cout, cin, kh, kw = w.shape
+    w = w.detach().float()
+    if scale is not None:
+        w = w * scale.view(-1, 1, 1, 1).float()
+    if c_splits is None:
+        c_splits = [(cin, round_up(cin, 64))]
+    assert sum(r for r, _ in c_splits) == cin
+    parts, off = [], 0
+    for real, padded in c_splits:
+        blk = w[:, off:off + real]
+        if padded > real:
+            blk = torch.nn.functional.pad(blk, (0, 0, 0, 0, 0, padded - real))
+        parts.append(blk)
+        off += real
+    w = torch.cat(parts, dim=1)                       # [Cout, Cpad, kh, kw]
+    w = w.permute(0, 2, 3, 1).reshape(cout, -1)       # [Cout, kh*kw*Cpad]
+    n_pad = n_pad or round_up(cout, 16)
+    if n_pad > cout:
+        w = torch.nn.functional.pad(w, (0, 0, 0, n_pad - cout))
+    return w.to(torch_dtype(dtype)).contiguous()
+
+
+def pad_vec(v, n_pad):
+    v = v.detach().float()
+    if v.numel() < n_pad:
+        v = torch.nn.functional.pad(v, (0, n_pad - v.numel()))
+    return v.contiguous()
+
+
+def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mode=L.PAD_ZERO, upsample=1,
+           src1=None, bias=None, residual=None, act=L.ACT_NONE, act_param=0.0, out16=None, out32=None,
+           ld_out16=None, ld_out32=None, out_img_rows=0, stats=None, stats_cg=0, dcn_offmask=None,
+           n_pad=None, w_group_rows=0, dtype=L.PRN_BF16, c0=None, c1=None, ld_res=None):
+    """Launch prn_conv2d_fwd.  src*/residual/out16 are 16-bit NHWC tensors (any shape, channels last)."""
+    d = L.PrnConv()
+    d.src0 = src0.data_ptr()
+    d.c0 = c0 if c0 is not None else src0.shape[-1]
+    d.src1 = src1.data_ptr() if src1 is not None else None
+    d.c1 = (c1 if c1 is not None else src1.shape[-1]) if src1 is not None else 0
+    d.batch, d.h_in, d.w_in = batch, h_in, w_in
+    d.upsample = upsample
+    d.ksize, d.stride, d.pad, d.pad_mode = ksize, stride, pad, pad_mode
+    d.h_out = (h_in * upsample + 2 * pad - ksize) // stride + 1
+    d.w_out = (w_in * upsample + 2 * pad - ksize) // stride + 1
+    d.dcn_offmask = dcn_offmask.data_ptr() if dcn_offmask is not None else None
+    d.weight = weight.data_ptr()
+    d.w_rows_total = weight.shape[0]
+    d.n_pad = n_pad if n_pad is not None else weight.shape[0]
+    d.w_group_rows = w_group_rows
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.ld_res = (ld_res if ld_res is not None else residual.shape[-1]) if residual is not None else 0
+    d.act, d.act_param = act, act_param
+    d.out16 = out16.data_ptr() if out16 is not None else None
+    d.ld_out16 = (ld_out16 if ld_out16 is not None else out16.shape[-1]) if out16 is not None else 0
+    d.out32 = out32.data_ptr() if out32 is not None else None
+    d.ld_out32 = (ld_out32 if ld_out32 is not None else out32.shape[-1]) if out32 is not None else 0
+    d.out_img_rows = out_img_rows
+    d.stats = stats.data_ptr() if stats is not None else None
+    d.stats_cg = stats_cg
+    d.dtype = dtype
+    L.check(L.lib().prn_conv2d_fwd(C.byref(d), L.current_stream()), "prn_conv2d_fwd")
+    return d
