@@ -52,6 +52,7 @@ typedef struct PrnConv {
   const void* src0;
   const void* src1;        /* NULL when c1 == 0 */
   int32_t c0, c1;          /* channels, each a multiple of 64 (c1 may be 0) */
+  int32_t ld0, ld1;        /* pixel pitch of src0/src1 in elements (>= c0/c1, multiple of 8); 0 = dense */
   int32_t batch, h_in, w_in;
   int32_t upsample;        /* 1, or 2 = nearest x2 applied before padding (planerecnet.py:541) */
   int32_t ksize, stride, pad;
@@ -94,6 +95,43 @@ int prn_device_sm_count(void);
 int prn_conv2d_fwd(const PrnConv* desc, void* stream);
 /* Workspace-free helper: bytes of dynamic shared memory and CTAs the launch would use (for tests). */
 int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid);
+
+/* ---- HBM-bound passes between the contractions (NHWC 16-bit unless stated) -------------------- */
+
+/* Stem im2col: x NCHW fp32 [B,3,H,W] -> [B*(H/2)*(W/2), 192] 16-bit rows, k = (ky*7+kx)*3+c of the
+ * 7x7/s2/p3 conv (models/backbone.py:101,200), zero padded from 147 to 192, so the stem runs as a
+ * K=192 contraction through prn_conv2d_fwd. */
+int prn_stem_im2col(const float* x_nchw, void* out16, int32_t batch, int32_t h, int32_t w, int32_t dtype, void* stream);
+/* nn.MaxPool2d(3, 2, 1): models/backbone.py:104,203. */
+int prn_maxpool3x3s2(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
+/* 2x2 mean == F.interpolate(bilinear, x0.5, align_corners=False): models/fpn.py:54, planerecnet.py:115. */
+int prn_avgpool2x2(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
+/* F.interpolate(size=(h_out,w_out), bilinear, align_corners=False) with optional x/y coord channels
+ * appended before resizing (planerecnet.py:370-382); output channels [c, c_out) beyond the coords are 0. */
+int prn_resize_bilinear(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t h_out,
+                        int32_t w_out, int32_t c_out, int32_t add_coord, int32_t dtype, void* stream);
+/* torch.cat([feat, x, y], 1) without resizing (planerecnet.py:483-490). */
+int prn_append_coord(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t c_out,
+                     int32_t dtype, void* stream);
+/* nn.GroupNorm(32, C) (+ReLU) from the {sum, sumsq} pairs a prn_conv2d_fwd epilogue accumulated
+ * (planerecnet.py:341-342, 420-421, 463-464). */
+int prn_groupnorm_apply(const void* in16, void* out16, const float* stats, const float* gamma, const float* beta,
+                        int32_t batch, int32_t hw, int32_t c, int32_t ch_per_group, float eps, int32_t relu,
+                        int32_t dtype, void* stream);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=False), optionally accumulated into out16
+ * (planerecnet.py:439,453,493). */
+int prn_upsample2x_bilinear(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                            int32_t accumulate, int32_t dtype, void* stream);
+/* torch.mul(x, attn): planerecnet.py:600. */
+int prn_mul(const void* a16, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream);
+/* Plane-prior attention, pixel selection: the x0.25 bilinear resize at planerecnet.py:594 only reads the
+ * centre 2x2 of every 4x4 block; gathers those pixels as rows (image, block, 2x2 position). */
+int prn_ppa_gather(const void* mask16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
+/* Module-boundary layout changes: NHWC (16-bit or fp32, row pitch ld) <-> NCHW fp32 contiguous. */
+int prn_nhwc_to_nchw_f32(const void* src, int32_t src_is_f32, float* dst, int32_t batch, int32_t hw, int32_t c,
+                         int32_t ld, int32_t src_img_rows, int32_t dtype, void* stream);
+int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t hw, int32_t c, int32_t c_pad,
+                         int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ class PrnConv(C.Structure):
     _fields_ = [
         ("src0", C.c_void_p), ("src1", C.c_void_p),
         ("c0", C.c_int32), ("c1", C.c_int32),
+        ("ld0", C.c_int32), ("ld1", C.c_int32),
         ("batch", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
         ("upsample", C.c_int32),
         ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
@@ -68,6 +69,9 @@ def lib():
 EXPORTS = [
     "prn_last_error", "prn_abi_version", "prn_device_sm_count",
     "prn_conv2d_fwd", "prn_conv2d_plan",
+    "prn_stem_im2col", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
+    "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
+    "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",
 ]
 
 

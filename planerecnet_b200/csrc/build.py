@@ -54,7 +54,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-arch=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as fh:
         fh.write(fp)

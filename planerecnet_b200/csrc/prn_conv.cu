@@ -45,6 +45,7 @@ struct ConvKParams {
   int num_kb;
   int hw_out;
   int out_img_rows;
+  int ld0, ld1;
   uint32_t idesc;
 };
 
@@ -163,7 +164,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const int c = cc * 64;
             const bool first = c < d.c0;
             const uint8_t* src = static_cast<const uint8_t*>(first ? d.src0 : d.src1);
-            const int cs = first ? d.c0 : d.c1;
+            const int cs = first ? p.ld0 : p.ld1;
             const int coff = (first ? c : c - d.c0) + chunk * 8;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
@@ -190,7 +191,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           //      value = mask * bilinear(x, ho*s - pad + ky + dy, wo*s - pad + kx + dx), zero outside
           //      (-1, H) x (-1, W); corners outside the image contribute 0.
           const uint8_t* src = static_cast<const uint8_t*>(d.src0);
-          const int cs = d.c0;
+          const int cs = p.ld0;
           for (int cc = 0; cc < p.kb_per_tap; ++cc) {
             const int coff = cc * 64 + chunk * 8;
             mbar_wait(bar_empty + 8 * s, ph ^ 1u);
@@ -323,7 +324,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const size_t orow = avg4 ? static_cast<size_t>(img) * p.out_img_rows + (pp >> 2)
                                : static_cast<size_t>(img) * p.out_img_rows + pp;
       const size_t rrow = static_cast<size_t>(g) * p.m_group + mm;
-      const bool img_uniform = __all_sync(0xffffffffu, valid && img == __shfl_sync(0xffffffffu, img, 0));
+      // (the shuffle must not sit behind `valid &&`: short-circuiting would leave the invalid lanes out of it)
+      const int img_lane0 = __shfl_sync(0xffffffffu, img, 0);
+      const bool img_uniform = __all_sync(0xffffffffu, valid && img == img_lane0);
 
       mbar_wait(bar_tfull + 8 * acc, acc_ph);
       tc_fence_after();
@@ -331,6 +334,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       for (int c = 0; c < p.n_tile; c += 16) {
         if (n0 + c >= d.n_pad) break;
         uint32_t v[16];
+        // tcgen05.ld is .sync.aligned: lanes diverged by the per-row `valid` predicates below (tiles whose
+        // row count is not a multiple of 32) must reconverge first, or the warp deadlocks.
+        __syncwarp();
         tmem_ld_x16(t_row + c, v);
         tmem_ld_wait();
         float x[16];
@@ -477,7 +483,11 @@ static int plan(const PrnConv& d, ConvKParams* p) {
     PRN_REQUIRE(d.c1 == 0 && d.upsample == 1 && d.pad_mode == PRN_PAD_ZERO && d.ksize == 3,
                 "conv: deformable sampling needs a single source, 3x3, zero padding");
   }
+  PRN_REQUIRE(d.ld0 == 0 || (d.ld0 >= d.c0 && d.ld0 % 8 == 0), "conv: bad ld0");
+  PRN_REQUIRE(d.ld1 == 0 || (d.ld1 >= d.c1 && d.ld1 % 8 == 0), "conv: bad ld1");
   p->d = d;
+  p->ld0 = d.ld0 ? d.ld0 : d.c0;
+  p->ld1 = d.ld1 ? d.ld1 : d.c1;
   p->hw_out = d.h_out * d.w_out;
   if (d.w_group_rows != 0) {
     p->groups = d.batch;

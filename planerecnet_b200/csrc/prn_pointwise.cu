@@ -1,0 +1,494 @@
+// prn_pointwise.cu — the HBM-bound passes between the tensor-core contractions: layout changes,
+// pooling, bilinear resampling, GroupNorm application.  NHWC, 16-bit, 8 channels (16 bytes) per
+// thread, fully coalesced; grids sized in whole waves where the tensor is large enough.
+#include "prn_internal.h"
+#include "prn_ptx.cuh"
+
+namespace prn {
+
+constexpr int kPwThreads = 256;
+
+static inline int pw_grid(long long work_items) {
+  long long b = (work_items + kPwThreads - 1) / kPwThreads;
+  const long long cap = static_cast<long long>(sm_count()) * 16;  // grid-stride beyond 16 CTAs/SM
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* f) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = Pack2<T>::unpack(w[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float* f) {
+  uint4 o;
+  o.x = Pack2<T>::pack(f[0], f[1]);
+  o.y = Pack2<T>::pack(f[2], f[3]);
+  o.z = Pack2<T>::pack(f[4], f[5]);
+  o.w = Pack2<T>::pack(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+// ---------------------------------------------------------------- stem im2col (models/backbone.py:101,200)
+// x NCHW fp32 [B,3,H,W] -> A [B*Ho*Wo, 192] 16-bit, k = (ky*7 + kx)*3 + c for the 7x7/s2/p3 conv, zero
+// padded to 192 so the stem runs as a K=192 GEMM on the tensor cores.
+template <typename T>
+__global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 24;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kc = static_cast<int>(i % 24);
+    const long long m = i / 24;
+    const int wo = static_cast<int>(m % Wo);
+    const int ho = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kc * 8 + j;
+      float v = 0.f;
+      if (k < 147) {
+        const int c = k % 3, tap = k / 3;
+        const int ky = tap / 7, kx = tap % 7;
+        const int y = ho * 2 - 3 + ky, xx = wo * 2 - 3 + kx;
+        if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(b) * 3 + c) * H + y) * W + xx);
+      }
+      f[j] = v;
+    }
+    store8(out + m * 192 + kc * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------- 3x3/s2/p1 max pool (models/backbone.py:104)
+template <typename T>
+__global__ void maxpool3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, cv = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = ho * 2 - 1 + dy;
+      if (y < 0 || y >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = wo * 2 - 1 + dx;
+        if (xx < 0 || xx >= W) continue;
+        float f[8];
+        load8(in + ((static_cast<long long>(b) * H + y) * W + xx) * C + c, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+      }
+    }
+    store8(out + m * C + c, best);
+  }
+}
+
+// ---------------------------------------------------------------- 2x2 average (== bilinear x0.5, align_corners=False:
+// models/fpn.py:54, planerecnet.py:115)
+template <typename T>
+__global__ void avgpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    const T* p = in + ((static_cast<long long>(b) * H + 2 * ho) * W + 2 * wo) * C + c;
+    float a[8], q[8], r[8], s[8], o[8];
+    load8(p, a);
+    load8(p + C, q);
+    load8(p + static_cast<long long>(W) * C, r);
+    load8(p + static_cast<long long>(W) * C + C, s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.25f * ((a[j] + q[j]) + (r[j] + s[j]));
+    store8(out + m * C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------- bilinear resize (+ coord channels)
+// planerecnet.py:370-382: cat[feat, x, y] then F.interpolate(size=S, bilinear, align_corners=False).
+// out [B,Ho,Wo,c_out] with c_out >= C (+2 coords); channels beyond are zero-filled.
+__device__ __forceinline__ void src_index(int dst, float scale, int in_size, int* i0, int* i1, float* l) {
+  float s = (static_cast<float>(dst) + 0.5f) * scale - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  int a = static_cast<int>(s);
+  if (a > in_size - 1) a = in_size - 1;
+  *i0 = a;
+  *i1 = a < in_size - 1 ? a + 1 : a;
+  *l = s - static_cast<float>(a);
+}
+
+template <typename T>
+__global__ void resize_bilinear_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C,
+                                       int Ho, int Wo, int c_out, int add_coord) {
+  const int cv = c_out / 8;
+  const float sh = static_cast<float>(H) / static_cast<float>(Ho), sw = static_cast<float>(W) / static_cast<float>(Wo);
+  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(ho, sh, H, &y0, &y1, &ly);
+    src_index(wo, sw, W, &x0, &x1, &lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float o[8];
+    if (c < C) {
+      const T* base = in + static_cast<long long>(b) * H * W * C + c;
+      float a[8], q[8], r[8], s[8];
+      load8(base + (static_cast<long long>(y0) * W + x0) * C, a);
+      load8(base + (static_cast<long long>(y0) * W + x1) * C, q);
+      load8(base + (static_cast<long long>(y1) * W + x0) * C, r);
+      load8(base + (static_cast<long long>(y1) * W + x1) * C, s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * q[j] + w10 * r[j] + w11 * s[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      if (add_coord && c == C) {
+        // linspace(-1, 1, n)[i] = -1 + 2 i / (n - 1)
+        const float xs = W > 1 ? 2.f / static_cast<float>(W - 1) : 0.f;
+        const float ys = H > 1 ? 2.f / static_cast<float>(H - 1) : 0.f;
+        const float cx0 = -1.f + xs * x0, cx1 = -1.f + xs * x1, cy0 = -1.f + ys * y0, cy1 = -1.f + ys * y1;
+        o[0] = (w00 + w10) * cx0 + (w01 + w11) * cx1;
+        o[1] = (w00 + w01) * cy0 + (w10 + w11) * cy1;
+      }
+    }
+    store8(out + m * c_out + c, o);
+  }
+}
+
+// ---------------------------------------------------------------- coord channel append without resize
+// planerecnet.py:483-490 (mask head level 3): out [B,H,W,c_out] = [in, x, y, 0...]
+template <typename T>
+__global__ void append_coord_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C,
+                                    int c_out) {
+  const int cv = c_out / 8;
+  const long long total = static_cast<long long>(B) * H * W * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    float o[8];
+    if (c < C) {
+      load8(in + m * C + c, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      if (c == C) {
+        const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
+        o[0] = W > 1 ? -1.f + 2.f * x / static_cast<float>(W - 1) : -1.f;
+        o[1] = H > 1 ? -1.f + 2.f * y / static_cast<float>(H - 1) : -1.f;
+      }
+    }
+    store8(out + m * c_out + c, o);
+  }
+}
+
+// ---------------------------------------------------------------- GroupNorm apply (+ReLU) from epilogue sums
+// planerecnet.py:341-342, 420-421, 463-464: y = relu((x - mean) * rstd * gamma + beta), statistics over
+// (C/G channels x H x W) per sample, eps 1e-5; sums come from the conv epilogue (fp32 accumulators).
+template <typename T>
+__global__ void gn_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int B, int HW, int C,
+                                int cg, float eps, int relu) {
+  const int cv = C / 8, G = C / cg;
+  const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
+  const long long total = static_cast<long long>(B) * HW * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int b = static_cast<int>(m / HW);
+    float f[8];
+    load8(in + m * C + c, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cg;
+      const float s1 = __ldg(stats + (static_cast<long long>(b) * G + g) * 2);
+      const float s2 = __ldg(stats + (static_cast<long long>(b) * G + g) * 2 + 1);
+      const float mean = s1 * inv_cnt;
+      const float var = fmaxf(s2 * inv_cnt - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + eps);
+      float y = (f[j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      f[j] = relu ? fmaxf(y, 0.f) : y;
+    }
+    store8(out + m * C + c, f);
+  }
+}
+
+// ---------------------------------------------------------------- bilinear x2 upsample (+ accumulate)
+// planerecnet.py:439,453 (nn.Upsample(scale_factor=2, bilinear, align_corners=False)) and the level sum :493.
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C,
+                                  int accumulate) {
+  const int Ho = 2 * H, Wo = 2 * W, cv = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    int y0, y1, x0, x1;
+    float ly, lx;
+    src_index(ho, 0.5f, H, &y0, &y1, &ly);
+    src_index(wo, 0.5f, W, &x0, &x1, &lx);
+    const T* base = in + static_cast<long long>(b) * H * W * C + c;
+    float a[8], q[8], r[8], s[8], o[8];
+    load8(base + (static_cast<long long>(y0) * W + x0) * C, a);
+    load8(base + (static_cast<long long>(y0) * W + x1) * C, q);
+    load8(base + (static_cast<long long>(y1) * W + x0) * C, r);
+    load8(base + (static_cast<long long>(y1) * W + x1) * C, s);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * q[j] + w10 * r[j] + w11 * s[j];
+    if (accumulate) {
+      float prev[8];
+      load8(out + m * C + c, prev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += prev[j];
+    }
+    store8(out + m * C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------- elementwise product (planerecnet.py:600 x * attn)
+template <typename T>
+__global__ void mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] *= y[j];
+    store8(out + i * 8, x);
+  }
+}
+
+// ---------------------------------------------------------------- plane-prior attention: centre-pixel gather
+// planerecnet.py:594 bilinear x0.25 (align_corners=False) of a map == mean of pixels (4i+1,4i+2)x(4j+1,4j+2);
+// sigmoid and the 3728->256 conv are per-pixel, so only those pixels are needed.  Row order:
+// (image, block row, block col, 2x2 position) so 4 consecutive rows form one output pixel.
+template <typename T>
+__global__ void ppa_gather_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
+  const int Hb = H / 4, Wb = W / 4, cv = C / 8;
+  const long long total = static_cast<long long>(B) * Hb * Wb * 4 * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int pos = static_cast<int>(m & 3);
+    const long long blk = m >> 2;
+    const int bx = static_cast<int>(blk % Wb), by = static_cast<int>((blk / Wb) % Hb);
+    const int b = static_cast<int>(blk / (static_cast<long long>(Wb) * Hb));
+    const int y = 4 * by + 1 + (pos >> 1), x = 4 * bx + 1 + (pos & 1);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * C + c));
+    *reinterpret_cast<uint4*>(out + m * C + c) = v;
+  }
+}
+
+// ---------------------------------------------------------------- layout conversions at the module boundary
+// NHWC (16-bit or fp32, row pitch ld) -> NCHW fp32 contiguous, the layout callers .view() (losses.py:74,130).
+template <typename T, bool kSrcF32>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ src, float* __restrict__ dst, int B, int HW, int C,
+                                    int ld, int src_img_rows) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const long long idx = (static_cast<long long>(b) * src_img_rows + p) * ld + c;
+      if (kSrcF32) v = __ldg(static_cast<const float*>(src) + idx);
+      else v = static_cast<float>(static_cast<const T*>(src)[idx]);
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[(static_cast<long long>(b) * C + c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+// NCHW fp32 -> NHWC 16-bit with channel padding (used by the per-module entry points / tests)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int HW, int C, int c_pad) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (p < HW && c < C) ? __ldg(src + (static_cast<long long>(b) * C + c) * HW + p) : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (p < HW && c < c_pad) dst[(static_cast<long long>(b) * HW + p) * c_pad + c] = static_cast<T>(tile[threadIdx.x][r]);
+  }
+}
+
+}  // namespace prn
+
+// =================================================================================================== C ABI
+using namespace prn;
+
+#define PRN_DISPATCH(dtype, KERNEL_CALL_BF16, KERNEL_CALL_F16) \
+  do {                                                         \
+    if ((dtype) == PRN_BF16) { KERNEL_CALL_BF16; }             \
+    else if ((dtype) == PRN_F16) { KERNEL_CALL_F16; }          \
+    else return set_error(PRN_ERR_INVALID, "bad dtype %d", (int)(dtype)); \
+  } while (0)
+
+#define PRN_LAUNCH_CHECK()                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess) return set_error(PRN_ERR_CUDA, "%s launch: %s", __func__, cudaGetErrorString(_e)); \
+    return PRN_OK;                                                                                \
+  } while (0)
+
+extern "C" {
+
+int prn_stem_im2col(const float* x_nchw, void* out16, int32_t batch, int32_t h, int32_t w, int32_t dtype, void* stream) {
+  PRN_REQUIRE(x_nchw && out16 && batch > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "stem_im2col: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * (h / 2) * (w / 2) * 24;
+  PRN_DISPATCH(dtype,
+               (stem_im2col_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(x_nchw, static_cast<__nv_bfloat16*>(out16), batch, h, w)),
+               (stem_im2col_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(x_nchw, static_cast<__half*>(out16), batch, h, w)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_maxpool3x3s2(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * ((h - 1) / 2 + 1) * ((w - 1) / 2 + 1) * (c / 8);
+  PRN_DISPATCH(dtype,
+               (maxpool3s2_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c)),
+               (maxpool3s2_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), batch, h, w, c)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_avgpool2x2(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && batch > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "avgpool2x2: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * (h / 2) * (w / 2) * (c / 8);
+  PRN_DISPATCH(dtype,
+               (avgpool2_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c)),
+               (avgpool2_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), batch, h, w, c)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_resize_bilinear(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t h_out,
+                        int32_t w_out, int32_t c_out, int32_t add_coord, int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && batch > 0 && h > 0 && w > 0 && h_out > 0 && w_out > 0 && c % 8 == 0 && c_out % 8 == 0 &&
+                  c_out >= c + (add_coord ? 2 : 0), "resize_bilinear: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * h_out * w_out * (c_out / 8);
+  PRN_DISPATCH(dtype,
+               (resize_bilinear_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c, h_out, w_out, c_out, add_coord)),
+               (resize_bilinear_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), batch, h, w, c, h_out, w_out, c_out, add_coord)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_append_coord(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t c_out,
+                     int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && batch > 0 && h > 0 && w > 0 && c % 8 == 0 && c_out % 8 == 0 && c_out >= c + 2, "append_coord: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * h * w * (c_out / 8);
+  PRN_DISPATCH(dtype,
+               (append_coord_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c, c_out)),
+               (append_coord_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), batch, h, w, c, c_out)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_groupnorm_apply(const void* in16, void* out16, const float* stats, const float* gamma, const float* beta,
+                        int32_t batch, int32_t hw, int32_t c, int32_t ch_per_group, float eps, int32_t relu,
+                        int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && stats && gamma && beta && batch > 0 && hw > 0 && c % 8 == 0 && ch_per_group > 0 &&
+                  c % ch_per_group == 0, "groupnorm_apply: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * hw * (c / 8);
+  PRN_DISPATCH(dtype,
+               (gn_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), stats, gamma, beta, batch, hw, c, ch_per_group, eps, relu)),
+               (gn_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), stats, gamma, beta, batch, hw, c, ch_per_group, eps, relu)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_upsample2x_bilinear(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                            int32_t accumulate, int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && out16 && batch > 0 && h > 0 && w > 0 && c % 8 == 0, "upsample2x: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * 4 * h * w * (c / 8);
+  PRN_DISPATCH(dtype,
+               (upsample2x_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c, accumulate)),
+               (upsample2x_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<__half*>(out16), batch, h, w, c, accumulate)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_mul(const void* a16, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream) {
+  PRN_REQUIRE(a16 && b16 && out16 && n > 0 && n % 8 == 0, "mul: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (mul_kernel<__nv_bfloat16><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(a16), static_cast<const __nv_bfloat16*>(b16), static_cast<__nv_bfloat16*>(out16), n / 8)),
+               (mul_kernel<__half><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __half*>(a16), static_cast<const __half*>(b16), static_cast<__half*>(out16), n / 8)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_ppa_gather(const void* mask16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream) {
+  PRN_REQUIRE(mask16 && out16 && batch > 0 && h % 4 == 0 && w % 4 == 0 && c % 8 == 0, "ppa_gather: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * (h / 4) * (w / 4) * 4 * (c / 8);
+  PRN_DISPATCH(dtype,
+               (ppa_gather_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(mask16), static_cast<__nv_bfloat16*>(out16), batch, h, w, c)),
+               (ppa_gather_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(mask16), static_cast<__half*>(out16), batch, h, w, c)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_nhwc_to_nchw_f32(const void* src, int32_t src_is_f32, float* dst, int32_t batch, int32_t hw, int32_t c,
+                         int32_t ld, int32_t src_img_rows, int32_t dtype, void* stream) {
+  PRN_REQUIRE(src && dst && batch > 0 && hw > 0 && c > 0 && ld >= c, "nhwc_to_nchw: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_img_rows == 0) src_img_rows = hw;
+  dim3 grid((hw + 31) / 32, (c + 31) / 32, batch), block(32, 8);
+  if (src_is_f32) nhwc_to_nchw_kernel<__half, true><<<grid, block, 0, st>>>(src, dst, batch, hw, c, ld, src_img_rows);
+  else if (dtype == PRN_BF16) nhwc_to_nchw_kernel<__nv_bfloat16, false><<<grid, block, 0, st>>>(src, dst, batch, hw, c, ld, src_img_rows);
+  else nhwc_to_nchw_kernel<__half, false><<<grid, block, 0, st>>>(src, dst, batch, hw, c, ld, src_img_rows);
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t hw, int32_t c, int32_t c_pad,
+                         int32_t dtype, void* stream) {
+  PRN_REQUIRE(src && dst16 && batch > 0 && hw > 0 && c > 0 && c_pad >= c, "nchw_to_nhwc: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((hw + 31) / 32, (c_pad + 31) / 32, batch), block(32, 8);
+  PRN_DISPATCH(dtype,
+               (nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst16), batch, hw, c, c_pad)),
+               (nchw_to_nhwc_kernel<__half><<<grid, block, 0, st>>>(src, static_cast<__half*>(dst16), batch, hw, c, c_pad)));
+  PRN_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+"""Forward executor of the PlaneRecNet dense hot path on libprn_b200.
+
+Data layout in HBM: activations are NHWC ("pixel rows"), 16-bit, channel counts multiples of 64;
+weights are packed once per parameter version into K-major [Cout_pad, kh*kw*Cin_pad] 16-bit matrices
+with eval-mode BatchNorm folded in (scale into the weights, shift into an fp32 bias vector).  torch is
+used for device memory (caching allocator), streams and weight packing only; every arithmetic step of
+the forward is a launch of a hand-written sm_100a kernel through the C ABI (include/prn_b200.h).
+`Engine.launches` counts those launches.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import ops
+from .models.dcn import DeformableConv2d
+
+_DT = {"bf16": L.PRN_BF16, "f16": L.PRN_F16, L.PRN_BF16: L.PRN_BF16, L.PRN_F16: L.PRN_F16}
+
+
+def _ver(*tensors):
+    return tuple((t._version, t.data_ptr()) for t in tensors if t is not None)
+
+
+class Engine:
+    def __init__(self, dtype="bf16"):
+        self.dt = _DT[dtype]
+        self.tdt = ops.torch_dtype(self.dt)
+        self.lib = L.lib()          # raises if the CUDA library is missing: no fallback
+        self._packed = {}
+        self.launches = 0
+        self._zero_pool = {}
+
+    # ------------------------------------------------------------------ small helpers
+    def _st(self):
+        return L.current_stream()
+
+    def _call(self, fn, *args):
+        self.launches += 1
+        L.check(fn(*args), fn.__name__)
+
+    def _empty(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.tdt, device="cuda")
+
+    def to_nhwc(self, x, c_pad=None):
+        """NCHW fp32 -> NHWC 16-bit, channels zero-padded to a multiple of 64."""
+        assert x.is_cuda and x.dim() == 4, "expected a CUDA NCHW tensor"
+        x = x.detach().float().contiguous()
+        B, Cc, H, W = x.shape
+        c_pad = c_pad or ops.round_up(Cc, 64)
+        out = self._empty(B, H, W, c_pad)
+        self._call(self.lib.prn_nchw_f32_to_nhwc, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, H * W, Cc,
+                   c_pad, self.dt, self._st())
+        return out
+
+    def to_nchw(self, t, channels, src_img_rows=0, hw=None, shape_hw=None):
+        """NHWC (16-bit or fp32, last dim = pitch) -> NCHW fp32 [B, channels, H, W]."""
+        B = t.shape[0]
+        if shape_hw is None:
+            shape_hw = (t.shape[1], t.shape[2])
+        hw = shape_hw[0] * shape_hw[1]
+        out = self._empty(B, channels, shape_hw[0], shape_hw[1], dtype=torch.float32)
+        self._call(self.lib.prn_nhwc_to_nchw_f32, C.c_void_p(t.data_ptr()), 1 if t.dtype == torch.float32 else 0,
+                   C.c_void_p(out.data_ptr()), B, hw, channels, t.shape[-1], src_img_rows, self.dt, self._st())
+        return out
+
+    # ------------------------------------------------------------------ weight packing (cached per parameter version)
+    def _pack(self, key, params, builder):
+        ver = _ver(*params)
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        with torch.no_grad():
+            val = builder()
+        self._packed[key] = (ver, val)
+        return val
+
+    def _fold(self, conv, bn, c_splits=None, n_pad=None):
+        """Packed weights + fp32 bias with eval-mode BatchNorm folded in (scale -> weights, shift -> bias)."""
+        params = [conv.weight, conv.bias]
+        if bn is not None:
+            params += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+
+        def build():
+            w = conv.weight.detach().float()
+            cout = w.shape[0]
+            b = conv.bias.detach().float() if conv.bias is not None else None
+            scale = None
+            if bn is not None:
+                scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+                shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+                b = shift if b is None else b * scale + shift
+            npad = n_pad or ops.round_up(cout, 16)
+            wp = ops.pack_conv_weight(w, c_splits, npad, self.dt, scale=scale).cuda()
+            bp = ops.pad_vec(b, npad).cuda() if b is not None else None
+            return wp, bp
+
+        return self._pack((id(conv), id(bn), "fold", str(c_splits)), params, build)
+
+    # ------------------------------------------------------------------ layers
+    def conv(self, x, conv, bn=None, act=L.ACT_NONE, *, src1=None, residual=None, stride=None, pad=None,
+             pad_mode=L.PAD_ZERO, upsample=1, c_splits=None, out32=False, out16=True, stats_cg=None, stats=None,
+             packed=None, c0=None, out16_buf=None, out32_buf=None, out_img_rows=0, act_param=0.0, dcn_offmask=None):
+        """One conv-like contraction.  x: [B,H,W,C] 16-bit.  Returns (out16, out32)."""
+        B, H, W, _ = x.shape
+        k = conv.kernel_size[0]
+        stride = conv.stride[0] if stride is None else stride
+        pad = conv.padding[0] if pad is None else pad
+        if packed is None:
+            cin0 = c0 if c0 is not None else x.shape[-1]
+            if c_splits is None:
+                real = conv.in_channels
+                if src1 is None:
+                    c_splits = [(real, cin0)]
+                else:
+                    c_splits = [(cin0, cin0), (real - cin0, src1.shape[-1])]
+            packed = self._fold(conv, bn, c_splits)
+        wp, bp = packed
+        n_pad = wp.shape[0]
+        Ho = (H * upsample + 2 * pad - k) // stride + 1
+        Wo = (W * upsample + 2 * pad - k) // stride + 1
+        o16 = out16_buf if out16_buf is not None else (self._empty(B, Ho, Wo, n_pad) if out16 else None)
+        o32 = out32_buf if out32_buf is not None else (self._empty(B, Ho, Wo, n_pad, dtype=torch.float32) if out32 else None)
+        self.launches += 1
+        ops.conv2d(x, wp, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad, pad_mode=pad_mode,
+                   upsample=upsample, src1=src1, bias=bp, residual=residual, act=act, act_param=act_param,
+                   out16=o16, out32=o32, out_img_rows=out_img_rows, stats=stats,
+                   stats_cg=stats_cg or 0, dcn_offmask=dcn_offmask, dtype=self.dt, c0=c0,
+                   ld_out16=(out16_buf.shape[-1] if out16_buf is not None else None),
+                   ld_out32=(out32_buf.shape[-1] if out32_buf is not None else None))
+        return o16, o32
+
+    def dcn(self, x, m, bn=None, relu=False):
+        """models/dcn.py:52-67: fused offset+modulator conv (clamp / 2*sigmoid epilogue), then the
+        bilinear-gather + tensor-core contraction with BN folded."""
+        B, H, W, Cc = x.shape
+
+        def build_om():
+            w = torch.cat([m.offset_conv.weight.detach().float(), m.modulator_conv.weight.detach().float()], 0)
+            b = torch.cat([m.offset_conv.bias.detach().float(), m.modulator_conv.bias.detach().float()], 0)
+            return (ops.pack_conv_weight(w, [(w.shape[1], Cc)], 32, self.dt).cuda(), ops.pad_vec(b, 32).cuda())
+
+        om_packed = self._pack((id(m), "offmask"), [m.offset_conv.weight, m.offset_conv.bias, m.modulator_conv.weight,
+                                                     m.modulator_conv.bias], build_om)
+        _, om = self.conv(x, m.offset_conv, act=L.ACT_DCN_OFFMASK, act_param=max(H, W) / 4.0, packed=om_packed,
+                          out16=False, out32=True)
+        y, _ = self.conv(x, m.regular_conv, bn, L.ACT_RELU if relu else L.ACT_NONE, dcn_offmask=om)
+        return y
+
+    def bottleneck(self, x, blk):
+        """models/backbone.py:53-73."""
+        y, _ = self.conv(x, blk.conv1, blk.bn1, L.ACT_RELU)
+        if isinstance(blk.conv2, DeformableConv2d):
+            y = self.dcn(y, blk.conv2, blk.bn2, relu=True)
+        else:
+            y, _ = self.conv(y, blk.conv2, blk.bn2, L.ACT_RELU)
+        res = x
+        if blk.downsample is not None:
+            res, _ = self.conv(x, blk.downsample[0], blk.downsample[1], L.ACT_NONE)
+        out, _ = self.conv(y, blk.conv3, blk.bn3, L.ACT_RELU, residual=res)
+        return out
+
+    def maxpool(self, x):
+        B, H, W, Cc = x.shape
+        out = self._empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc)
+        self._call(self.lib.prn_maxpool3x3s2, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W, Cc, self.dt, self._st())
+        return out
+
+    def avgpool2(self, x):
+        B, H, W, Cc = x.shape
+        out = self._empty(B, H // 2, W // 2, Cc)
+        self._call(self.lib.prn_avgpool2x2, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W, Cc, self.dt, self._st())
+        return out
+
+    def upsample2x(self, x, into=None):
+        B, H, W, Cc = x.shape
+        out = into if into is not None else self._empty(B, 2 * H, 2 * W, Cc)
+        self._call(self.lib.prn_upsample2x_bilinear, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W, Cc,
+                   1 if into is not None else 0, self.dt, self._st())
+        return out
+
+    def gn_relu(self, x, stats, gn, relu=True):
+        B, H, W, Cc = x.shape
+        gb = self._pack((id(gn), "gn"), [gn.weight, gn.bias],
+                        lambda: (gn.weight.detach().float().cuda().contiguous(), gn.bias.detach().float().cuda().contiguous()))
+        out = self._empty(B, H, W, Cc)
+        self._call(self.lib.prn_groupnorm_apply, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                   C.c_void_p(stats.data_ptr()), C.c_void_p(gb[0].data_ptr()), C.c_void_p(gb[1].data_ptr()), B, H * W, Cc,
+                   Cc // gn.num_groups, C.c_float(gn.eps), 1 if relu else 0, self.dt, self._st())
+        return out
+
+    def conv_gn_relu(self, x, conv, gn, **kw):
+        """conv (no bias) -> GroupNorm(32) -> ReLU; the sums come from the conv epilogue."""
+        B = x.shape[0]
+        G = gn.num_groups
+        stats = torch.zeros(B * G * 2, dtype=torch.float32, device="cuda")
+        y, _ = self.conv(x, conv, None, L.ACT_NONE, stats=stats, stats_cg=conv.out_channels // G, **kw)
+        return self.gn_relu(y, stats, gn)
+
+    # ------------------------------------------------------------------ stages
+    def backbone(self, x, bb):
+        """models/backbone.py:197-209.  x: NCHW fp32 CUDA.  Returns [C2..C5] NHWC 16-bit."""
+        assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+        x = x.detach().float().contiguous()
+        B, _, H, W = x.shape
+        a = self._empty(B, H // 2, W // 2, 192)
+        self._call(self.lib.prn_stem_im2col, C.c_void_p(x.data_ptr()), C.c_void_p(a.data_ptr()), B, H, W, self.dt, self._st())
+
+        def build_stem():
+            w = bb.conv1.weight.detach().float()
+            scale = bb.bn1.weight.detach().float() / torch.sqrt(bb.bn1.running_var.detach().float() + bb.bn1.eps)
+            shift = bb.bn1.bias.detach().float() - bb.bn1.running_mean.detach().float() * scale
+            wk = (w * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(64, 147)
+            wk = torch.nn.functional.pad(wk, (0, 192 - 147)).to(self.tdt).contiguous().cuda()
+            return wk, shift.contiguous().cuda()
+
+        stem = self._pack((id(bb.conv1), "stem"), [bb.conv1.weight, bb.bn1.weight, bb.bn1.bias, bb.bn1.running_mean,
+                                                   bb.bn1.running_var], build_stem)
+        o16 = self._empty(B, H // 2, W // 2, 64)
+        self.launches += 1
+        ops.conv2d(a, stem[0], batch=B, h_in=H // 2, w_in=W // 2, ksize=1, bias=stem[1], act=L.ACT_RELU, out16=o16,
+                   dtype=self.dt)
+        y = self.maxpool(o16)
+        outs = []
+        for layer in bb.layers:
+            for blk in layer:
+                y = self.bottleneck(y, blk)
+            outs.append(y)
+        return outs
+
+    def fpn(self, cs, fpn):
+        """models/fpn.py:45-63: lateral 1x1 + (2x2 mean of the running sum) as epilogue residual; 3x3 + ReLU."""
+        lats, prev = [], None
+        for i, c in enumerate(cs):
+            res = self.avgpool2(prev) if prev is not None else None
+            prev, _ = self.conv(c, fpn.lateral_convs[i], None, L.ACT_NONE, residual=res)
+            lats.append(prev)
+        return [self.conv(l, fpn.fpn_convs[i], None, L.ACT_RELU)[0] for i, l in enumerate(lats)]
+
+    def inst_head(self, feats, head):
+        """planerecnet.py:355-391.  feats: (x0.5 P2, P3, P4, P5) NHWC.  Writes kernel_pred of all levels into one
+        [B, sum(S^2), 128] buffer (16-bit for the attention / mask contractions, fp32 for the caller) and
+        cate_pred into [B, sum(S^2), 16] fp32 (first num_classes columns valid)."""
+        B = feats[0].shape[0]
+        grids = head.num_grids
+        total = sum(s * s for s in grids)
+        nk = head.num_kernels
+        kern16 = self._empty(B, total, nk)
+        kern32 = self._empty(B, total, nk, dtype=torch.float32)
+        cate32 = self._empty(B, total, 16, dtype=torch.float32)
+        off = 0
+        cin = head.instance_in_channels
+        for lvl, f in enumerate(feats):
+            S = grids[lvl]
+            Bf, h, w, cf = f.shape
+            kf = self._empty(B, S, S, ops.round_up(cin + 2, 64))
+            self._call(self.lib.prn_resize_bilinear, C.c_void_p(f.data_ptr()), C.c_void_p(kf.data_ptr()), B, h, w, cf, S, S,
+                       kf.shape[-1], 1, self.dt, self._st())
+            # kernel branch: 258 (padded 320) -> 256 -> 256 -> 256 -> 128
+            t = kf
+            for i in range(0, len(head.kernel_tower), 3):
+                t = self.conv_gn_relu(t, head.kernel_tower[i], head.kernel_tower[i + 1])
+            self.conv(t, head.kernel_pred, None, L.ACT_NONE, out16_buf=kern16[:, off:], out32_buf=kern32[:, off:],
+                      out_img_rows=total)
+            # category branch: first 256 channels of the same resized tensor
+            t = kf
+            for i in range(0, len(head.cate_tower), 3):
+                t = self.conv_gn_relu(t, head.cate_tower[i], head.cate_tower[i + 1], c0=cin if i == 0 else None)
+            self.conv(t, head.cate_pred, None, L.ACT_NONE, out16=False, out32_buf=cate32[:, off:], out_img_rows=total)
+            off += S * S
+        return {"kern16": kern16, "kern32": kern32, "cate32": cate32}
+
+    def inst_outputs_nchw(self, st, head):
+        B = st["kern32"].shape[0]
+        total = st["kern32"].shape[1]
+        cates, kerns, off = [], [], 0
+        for S in head.num_grids:
+            cates.append(self.to_nchw(st["cate32"][:, off:], head.num_classes, src_img_rows=total, shape_hw=(S, S)))
+            kerns.append(self.to_nchw(st["kern32"][:, off:], head.num_kernels, src_img_rows=total, shape_hw=(S, S)))
+            off += S * S
+        return cates, kerns
+
+    def pack_kernel_preds(self, kernel_preds, B):
+        """[[B,128,S,S]] NCHW fp32 -> [B, sum(S^2), 128] 16-bit (module-level entry point only)."""
+        total = sum(k.shape[2] * k.shape[3] for k in kernel_preds)
+        buf = self._empty(B, total, kernel_preds[0].shape[1])
+        off = 0
+        for k in kernel_preds:
+            hw = k.shape[2] * k.shape[3]
+            t = self.to_nhwc(k, c_pad=k.shape[1])
+            buf[:, off:off + hw].copy_(t.reshape(B, hw, -1))
+            off += hw
+        return buf
+
+    def mask_head(self, ps, head):
+        """planerecnet.py:467-496."""
+        lv = head.convs_all_levels
+        acc = self.conv_gn_relu(ps[0], lv[0].conv0[0], lv[0].conv0[1])
+        for i in range(1, head.num_levels):
+            x = ps[i]
+            if i == 3:
+                B, h, w, cf = x.shape
+                xc = self._empty(B, h, w, ops.round_up(cf + 2, 64))
+                self._call(self.lib.prn_append_coord, C.c_void_p(x.data_ptr()), C.c_void_p(xc.data_ptr()), B, h, w, cf,
+                           xc.shape[-1], self.dt, self._st())
+                x = xc
+            for j in range(i):
+                tower = getattr(lv[i], f"conv{j}")
+                x = self.conv_gn_relu(x, tower[0], tower[1])
+                if j < i - 1:
+                    x = self.upsample2x(x)
+                else:
+                    self.upsample2x(x, into=acc)
+        return self.conv_gn_relu(acc, head.conv_pred[0], head.conv_pred[1])
+
+    def depth_decoder(self, cs, mask16, kern16, dec):
+        """planerecnet.py:586-607.  cs: [C2..C5] NHWC; mask16 [B,H/4,W/4,128]; kern16 [B,3728,128].
+        Returns depth as fp32 [B, H/2, W/2, 16] (column 0 valid)."""
+        B, mh, mw, mc = mask16.shape
+        total = kern16.shape[1]
+        kpad = ops.round_up(total, 64)
+        # ---- plane-prior attention: sigmoid(K f_p) only at the pixels the x0.25 resize reads, averaged in the
+        #      epilogue, then the 3728->256 conv at 1/16 of the reference's pixel count (exact algebra)
+        q = self._empty(B, (mh // 4) * (mw // 4) * 4, mc)
+        self._call(self.lib.prn_ppa_gather, C.c_void_p(mask16.data_ptr()), C.c_void_p(q.data_ptr()), B, mh, mw, mc, self.dt, self._st())
+        key = ("ppa_p", B, mh, mw, kpad)
+        p = self._zero_pool.get(key)
+        if p is None:   # padding columns [3728, 3776) stay zero forever; the kernel never writes them
+            p = torch.zeros(B, mh // 4, mw // 4, kpad, dtype=self.tdt, device="cuda")
+            self._zero_pool[key] = p
+        self.launches += 1
+        ops.conv2d(q, kern16.reshape(B * total, mc), batch=B, h_in=(mh // 4) * (mw // 4), w_in=4, ksize=1,
+                   act=L.ACT_SIGMOID_AVG4, out16=p, ld_out16=kpad, n_pad=total, w_group_rows=total,
+                   out_img_rows=(mh // 4) * (mw // 4), dtype=self.dt)
+        attn, _ = self.conv(p, dec.conv1x1[0], None, L.ACT_NONE, c_splits=[(total, kpad)])
+
+        def rconv(x, seq, src1=None, act=L.ACT_RELU, out32=False):
+            up = 2 if isinstance(seq[0], nn.Upsample) else 1
+            conv = next(m for m in seq if isinstance(m, nn.Conv2d))
+            bn = next((m for m in seq if isinstance(m, nn.BatchNorm2d)), None)
+            return self.conv(x, conv, bn, act, src1=src1, pad=1, pad_mode=L.PAD_REFLECT, upsample=up, out32=out32,
+                             out16=not out32)
+
+        feats = list(reversed(cs))
+        x, _ = self.conv(feats[0], dec.latlayer1)
+        x, _ = rconv(x, dec.conv1)
+        x, _ = rconv(x, dec.deconv1)
+        xa = self._empty(*x.shape)
+        self._call(self.lib.prn_mul, C.c_void_p(x.data_ptr()), C.c_void_p(attn.data_ptr()), C.c_void_p(xa.data_ptr()),
+                   C.c_int64(x.numel()), self.dt, self._st())
+        x, _ = rconv(x, dec.refine_conv, src1=xa)
+        for k in (2, 3, 4):
+            skip, _ = self.conv(feats[k - 1], getattr(dec, f"latlayer{k}"))
+            skip, _ = rconv(skip, getattr(dec, f"conv{k}"))
+            x, _ = rconv(skip, getattr(dec, f"deconv{k}"), src1=x)
+        _, d32 = rconv(x, dec.depth_pred, act=L.ACT_SOFTPLUS, out32=True)
+        return d32, attn
+
+    def depth_output_nchw(self, d32, B, H, W):
+        d32 = d32[0] if isinstance(d32, tuple) else d32
+        return self.to_nchw(d32, 1)
+
+    # ------------------------------------------------------------------ whole dense forward (planerecnet.py:73-103)
+    def forward_dense(self, net, x, want_nchw=True):
+        if not x.is_cuda:
+            raise L.PrnError("PlaneRecNet (B200) forward needs a CUDA input tensor; there is no CPU path")
+        cs_all = self.backbone(x, net.backbone)
+        ps = self.fpn([cs_all[i] for i in net.fpn_indices], net.fpn)
+        feats = [self.avgpool2(ps[0]), ps[1], ps[2], ps[3]]
+        inst = self.inst_head(feats, net.inst_head)
+        mask16 = self.mask_head(ps, net.mask_head)
+        d32, attn = self.depth_decoder([cs_all[i] for i in net.depth_decoder_indices], mask16, inst["kern16"],
+                                       net.depth_decoder)
+        st = {"cs": cs_all, "ps": ps, "inst": inst, "mask16": mask16, "depth32": d32, "attn": attn}
+        if want_nchw:
+            cates, kerns = self.inst_outputs_nchw(inst, net.inst_head)
+            st["outputs"] = (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
+        return st
+
+    # ------------------------------------------------------------------ inference bookkeeping
+    def inference(self, net, st, x):
+        from .postprocess import inference as _inference
+        return _inference(self, net, st, x)
+
+
+_default = {}
+
+
+def default_engine(dtype="bf16"):
+    e = _default.get(dtype)
+    if e is None:
+        e = _default[dtype] = Engine(dtype)
+    return e
+
+
+def engine_for(module):
+    return default_engine()

@@ -59,6 +59,8 @@ def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mod
     d.c0 = c0 if c0 is not None else src0.shape[-1]
     d.src1 = src1.data_ptr() if src1 is not None else None
     d.c1 = (c1 if c1 is not None else src1.shape[-1]) if src1 is not None else 0
+    d.ld0 = src0.shape[-1] if src0.shape[-1] != d.c0 else 0
+    d.ld1 = (src1.shape[-1] if src1.shape[-1] != d.c1 else 0) if src1 is not None else 0
     d.batch, d.h_in, d.w_in = batch, h_in, w_in
     d.upsample = upsample
     d.ksize, d.stride, d.pad, d.pad_mode = ksize, stride, pad, pad_mode

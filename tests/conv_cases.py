@@ -22,6 +22,10 @@ CASES = {
     "1x1_c256_n512_multitile": dict(B=2, H=30, W=40, C=256, N=512, k=1, bias=True, act="relu"),
     "3x3_c64_n64": dict(B=1, H=16, W=16, C=64, N=64, k=3, pad=1),
     "3x3_c256_n256_ragged": dict(B=2, H=15, W=20, C=256, N=256, k=3, pad=1, bias=True, residual=True, act="relu"),
+    "bisect_nores": dict(B=2, H=15, W=20, C=256, N=256, k=3, pad=1, bias=True, act="relu"),
+    "bisect_even_res": dict(B=2, H=16, W=16, C=256, N=256, k=3, pad=1, residual=True),
+    "bisect_c128_res": dict(B=2, H=15, W=20, C=128, N=128, k=3, pad=1, residual=True),
+    "bisect_1x1_k2304": dict(B=2, H=15, W=20, C=2304, N=256, k=1),
     "3x3_s2_c128_n128": dict(B=2, H=30, W=40, C=128, N=128, k=3, pad=1, stride=2, bias=True),
     "1x1_s2_c256_n512": dict(B=2, H=30, W=40, C=256, N=512, k=1, stride=2),
     "3x3_reflect_c256_n128": dict(B=2, H=15, W=20, C=256, N=128, k=3, pad=1, reflect=True, bias=True, act="relu"),
