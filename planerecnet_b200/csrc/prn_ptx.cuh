@@ -172,8 +172,10 @@ struct Pack2<__nv_bfloat16> {
 template <>
 struct Pack2<__half> {
   static __device__ __forceinline__ uint32_t pack(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+    // saturate to +-65504 instead of overflowing to inf (fp16 has 5 exponent bits)
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
   }
   static __device__ __forceinline__ float2 unpack(uint32_t u) {
     return __half22float2(*reinterpret_cast<__half2*>(&u));

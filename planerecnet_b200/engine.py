@@ -24,13 +24,17 @@ def _ver(*tensors):
 
 
 class Engine:
-    def __init__(self, dtype="bf16"):
+    def __init__(self, dtype="f16"):
         self.dt = _DT[dtype]
+        self.dtype_name = "bf16" if self.dt == L.PRN_BF16 else "f16"
         self.tdt = ops.torch_dtype(self.dt)
         self.lib = L.lib()          # raises if the CUDA library is missing: no fallback
         self._packed = {}
+        self._pack_gen = 0
         self.launches = 0
         self._zero_pool = {}
+        self._graphs = {}
+        self.profile = None         # list of (name, flops, start_event, end_event) when profiling
 
     # ------------------------------------------------------------------ small helpers
     def _st(self):
@@ -74,6 +78,7 @@ class Engine:
         with torch.no_grad():
             val = builder()
         self._packed[key] = (ver, val)
+        self._pack_gen += 1          # captured graphs hold pointers to the old packed tensors
         return val
 
     def _fold(self, conv, bn, c_splits=None, n_pad=None):
@@ -122,14 +127,36 @@ class Engine:
         Wo = (W * upsample + 2 * pad - k) // stride + 1
         o16 = out16_buf if out16_buf is not None else (self._empty(B, Ho, Wo, n_pad) if out16 else None)
         o32 = out32_buf if out32_buf is not None else (self._empty(B, Ho, Wo, n_pad, dtype=torch.float32) if out32 else None)
-        self.launches += 1
-        ops.conv2d(x, wp, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad, pad_mode=pad_mode,
-                   upsample=upsample, src1=src1, bias=bp, residual=residual, act=act, act_param=act_param,
-                   out16=o16, out32=o32, out_img_rows=out_img_rows, stats=stats,
-                   stats_cg=stats_cg or 0, dcn_offmask=dcn_offmask, dtype=self.dt, c0=c0,
-                   ld_out16=(out16_buf.shape[-1] if out16_buf is not None else None),
-                   ld_out32=(out32_buf.shape[-1] if out32_buf is not None else None))
+        cin_real = conv.in_channels
+        flops = 2.0 * B * Ho * Wo * conv.out_channels * cin_real * k * k
+        with self._timed("dcn" if dcn_offmask is not None else f"conv{k}x{k}", flops):
+            ops.conv2d(x, wp, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad, pad_mode=pad_mode,
+                       upsample=upsample, src1=src1, bias=bp, residual=residual, act=act, act_param=act_param,
+                       out16=o16, out32=o32, out_img_rows=out_img_rows, stats=stats,
+                       stats_cg=stats_cg or 0, dcn_offmask=dcn_offmask, dtype=self.dt, c0=c0,
+                       ld_out16=(out16_buf.shape[-1] if out16_buf is not None else None),
+                       ld_out32=(out32_buf.shape[-1] if out32_buf is not None else None))
         return o16, o32
+
+    def _timed(self, name, flops):
+        """Context manager: counts the launch and, when profiling, brackets it with CUDA events."""
+        eng = self
+
+        class _T:
+            def __enter__(self_t):
+                eng.launches += 1
+                if eng.profile is not None:
+                    self_t.s = torch.cuda.Event(enable_timing=True)
+                    self_t.e = torch.cuda.Event(enable_timing=True)
+                    self_t.s.record()
+
+            def __exit__(self_t, *exc):
+                if eng.profile is not None:
+                    self_t.e.record()
+                    eng.profile.append((name, flops, self_t.s, self_t.e))
+                return False
+
+        return _T()
 
     def dcn(self, x, m, bn=None, relu=False):
         """models/dcn.py:52-67: fused offset+modulator conv (clamp / 2*sigmoid epilogue), then the
@@ -218,9 +245,9 @@ class Engine:
         stem = self._pack((id(bb.conv1), "stem"), [bb.conv1.weight, bb.bn1.weight, bb.bn1.bias, bb.bn1.running_mean,
                                                    bb.bn1.running_var], build_stem)
         o16 = self._empty(B, H // 2, W // 2, 64)
-        self.launches += 1
-        ops.conv2d(a, stem[0], batch=B, h_in=H // 2, w_in=W // 2, ksize=1, bias=stem[1], act=L.ACT_RELU, out16=o16,
-                   dtype=self.dt)
+        with self._timed("conv7x7", 2.0 * B * (H // 2) * (W // 2) * 64 * 147):
+            ops.conv2d(a, stem[0], batch=B, h_in=H // 2, w_in=W // 2, ksize=1, bias=stem[1], act=L.ACT_RELU, out16=o16,
+                       dtype=self.dt)
         y = self.maxpool(o16)
         outs = []
         for layer in bb.layers:
@@ -329,10 +356,10 @@ class Engine:
         if p is None:   # padding columns [3728, 3776) stay zero forever; the kernel never writes them
             p = torch.zeros(B, mh // 4, mw // 4, kpad, dtype=self.tdt, device="cuda")
             self._zero_pool[key] = p
-        self.launches += 1
-        ops.conv2d(q, kern16.reshape(B * total, mc), batch=B, h_in=(mh // 4) * (mw // 4), w_in=4, ksize=1,
-                   act=L.ACT_SIGMOID_AVG4, out16=p, ld_out16=kpad, n_pad=total, w_group_rows=total,
-                   out_img_rows=(mh // 4) * (mw // 4), dtype=self.dt)
+        with self._timed("ppa_dyn", 2.0 * B * (mh // 4) * (mw // 4) * 4 * total * mc):
+            ops.conv2d(q, kern16.reshape(B * total, mc), batch=B, h_in=(mh // 4) * (mw // 4), w_in=4, ksize=1,
+                       act=L.ACT_SIGMOID_AVG4, out16=p, ld_out16=kpad, n_pad=total, w_group_rows=total,
+                       out_img_rows=(mh // 4) * (mw // 4), dtype=self.dt)
         attn, _ = self.conv(p, dec.conv1x1[0], None, L.ACT_NONE, c_splits=[(total, kpad)])
 
         def rconv(x, seq, src1=None, act=L.ACT_RELU, out32=False):
@@ -378,6 +405,34 @@ class Engine:
             st["outputs"] = (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
         return st
 
+    def forward_dense_graph(self, net, x, want_nchw=True):
+        """Same as forward_dense, replayed from a CUDA graph captured per (model, input shape, weight
+        version): several hundred kernel launches become one graph launch.  The returned tensors are the
+        graph's static buffers: consume them before the next call."""
+        key = (id(net), tuple(x.shape), want_nchw)
+        ent = self._graphs.get(key)
+        if ent is None or ent["gen"] != self._pack_gen:
+            sx = torch.empty_like(x)
+            sx.copy_(x)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up: packs weights, primes the allocator
+                for _ in range(2):
+                    self.forward_dense(net, sx, want_nchw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gen = self._pack_gen
+            g = torch.cuda.CUDAGraph()
+            n0 = self.launches
+            with torch.cuda.graph(g):
+                st = self.forward_dense(net, sx, want_nchw)
+            ent = {"graph": g, "x": sx, "st": st, "gen": gen, "launches": self.launches - n0}
+            self._graphs[key] = ent
+        ent["x"].copy_(x, non_blocking=True)
+        ent["graph"].replay()
+        self.launches += ent["launches"]
+        return ent["st"]
+
     # ------------------------------------------------------------------ inference bookkeeping
     def inference(self, net, st, x):
         from .postprocess import inference as _inference
@@ -387,7 +442,7 @@ class Engine:
 _default = {}
 
 
-def default_engine(dtype="bf16"):
+def default_engine(dtype="f16"):
     e = _default.get(dtype)
     if e is None:
         e = _default[dtype] = Engine(dtype)

@@ -63,6 +63,7 @@ class PlaneRecNet(nn.Module):
         self.inst_head = SOLOv2InsHead(cfg, [cfg.fpn.num_features] * len(s.instance_in_features))
         self.mask_head = SOLOv2MaskHead(cfg, [cfg.fpn.num_features] * len(s.masks_in_features))
         self._engine = None
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ engine plumbing
     @property
@@ -73,7 +74,8 @@ class PlaneRecNet(nn.Module):
         return self._engine
 
     def set_precision(self, name):
-        """'bf16' (default) or 'f16' storage/operand type of the tensor-core path."""
+        """'f16' (default: 10-bit mantissa, ~1e-3 end-to-end) or 'bf16' (~1e-2) storage/operand type of the
+        tensor-core path; accumulation is fp32 in TMEM either way."""
         from .engine import Engine
         self._engine = Engine(dtype=name)
         return self
@@ -93,7 +95,7 @@ class PlaneRecNet(nn.Module):
                     "is the next scope row (SURVEY.md §8 a16); call net.eval() or freeze_bn() + forward_dense()")
             return self.forward_dense(x)
         with timer.env("dense forward"):
-            st = self.engine.forward_dense(self, x)
+            st = (self.engine.forward_dense_graph if self.use_cuda_graph else self.engine.forward_dense)(self, x, False)
         with timer.env("Inferencing"):
             return self.engine.inference(self, st, x)
 

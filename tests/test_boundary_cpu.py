@@ -34,7 +34,7 @@ def test_conv_descriptor_struct_matches_header_layout():
     """ctypes mirror of PrnConv must have the same field order as the C struct."""
     from planerecnet_b200 import _lib
     hdr = open(os.path.join(ROOT, "include", "prn_b200.h")).read()
-    body = hdr[hdr.index("typedef struct PrnConv {"):hdr.index("} PrnConv;")]
+    body = hdr[hdr.index("typedef struct PrnConv {") + len("typedef struct PrnConv {"):hdr.index("} PrnConv;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split(";"):

@@ -1,0 +1,135 @@
+"""Parity of the HBM-bound passes (called through the C ABI) against fp32 torch CPU operators on the same
+16-bit-rounded inputs.  Tolerance: one 16-bit rounding of the result (2^-8 bf16 / 2^-11 f16, relative to
+the tensor's max) plus fp32 noise."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from planerecnet_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["bf16", "f16"])
+def eng(request, cuda_lib):
+    from planerecnet_b200.engine import Engine
+    return Engine(request.param)
+
+
+def _tol(eng, ref):
+    return (2.0 ** -8 if eng.dt == L.PRN_BF16 else 2.0 ** -11) * float(ref.abs().max()) + 1e-5
+
+
+def _rand_nhwc(eng, B, H, W, Cc, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(B, H, W, Cc, generator=g).to(eng.tdt)
+    return t.cuda(), t.float().permute(0, 3, 1, 2)
+
+
+def _to_nchw(t):
+    return t.float().cpu().permute(0, 3, 1, 2)
+
+
+def test_layout_roundtrip(eng):
+    x = torch.randn(2, 70, 9, 11, generator=torch.Generator().manual_seed(1))
+    t = eng.to_nhwc(x.cuda())
+    assert t.shape == (2, 9, 11, 128)
+    assert torch.equal(t[..., 70:].float().cpu(), torch.zeros(2, 9, 11, 58))
+    back = eng.to_nchw(t, 70).cpu()
+    assert (back - x.to(eng.tdt).float()).abs().max() == 0
+
+
+def test_maxpool_avgpool(eng):
+    t, ref = _rand_nhwc(eng, 2, 14, 18, 64)
+    got = _to_nchw(eng.maxpool(t))
+    assert torch.equal(got, F.max_pool2d(ref, 3, 2, 1))
+    got = _to_nchw(eng.avgpool2(t))
+    exp = F.interpolate(ref, scale_factor=0.5, mode="bilinear", align_corners=False, recompute_scale_factor=False)
+    assert (got - exp).abs().max() <= _tol(eng, exp)
+
+
+def test_stem_im2col_matches_unfold(eng):
+    x = torch.randn(2, 3, 20, 28, generator=torch.Generator().manual_seed(2))
+    a = eng._empty(2, 10, 14, 192)
+    eng._call(eng.lib.prn_stem_im2col, C.c_void_p(x.cuda().data_ptr()), C.c_void_p(a.data_ptr()), 2, 20, 28, eng.dt, eng._st())
+    cols = F.unfold(x, 7, padding=3, stride=2)                       # [B, 3*49, L] ordered (c, ky, kx)
+    cols = cols.reshape(2, 3, 49, -1).permute(0, 3, 2, 1).reshape(2, 10, 14, 147)   # -> (ky,kx,c)
+    got = a.float().cpu()
+    assert (got[..., :147] - cols.to(eng.tdt).float()).abs().max() == 0
+    assert got[..., 147:].abs().max() == 0
+
+
+@pytest.mark.parametrize("S", [40, 36, 24, 16, 7])
+def test_resize_with_coord(eng, S):
+    t, ref = _rand_nhwc(eng, 2, 15, 20, 64, seed=S)
+    out = eng._empty(2, S, S, 128)
+    eng._call(eng.lib.prn_resize_bilinear, C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), 2, 15, 20, 64, S, S, 128, 1,
+              eng.dt, eng._st())
+    xr, yr = torch.linspace(-1, 1, 20), torch.linspace(-1, 1, 15)
+    yy, xx = torch.meshgrid(yr, xr, indexing="ij")
+    full = torch.cat([ref, xx.expand(2, 1, 15, 20), yy.expand(2, 1, 15, 20)], 1)
+    exp = F.interpolate(full, size=S, mode="bilinear", align_corners=False)
+    got = _to_nchw(out)
+    assert (got[:, :66] - exp).abs().max() <= _tol(eng, exp)
+    assert got[:, 66:].abs().max() == 0
+
+
+def test_append_coord(eng):
+    t, ref = _rand_nhwc(eng, 2, 15, 20, 64)
+    out = eng._empty(2, 15, 20, 128)
+    eng._call(eng.lib.prn_append_coord, C.c_void_p(t.data_ptr()), C.c_void_p(out.data_ptr()), 2, 15, 20, 64, 128, eng.dt, eng._st())
+    got = _to_nchw(out)
+    assert torch.equal(got[:, :64], ref)
+    xr, yr = torch.linspace(-1, 1, 20), torch.linspace(-1, 1, 15)
+    assert (got[0, 64, 3] - xr).abs().max() <= _tol(eng, xr) and (got[1, 65, :, 5] - yr).abs().max() <= _tol(eng, yr)
+
+
+def test_upsample2x_and_accumulate(eng):
+    t, ref = _rand_nhwc(eng, 2, 7, 9, 64)
+    exp = F.interpolate(ref, scale_factor=2, mode="bilinear", align_corners=False)
+    got = _to_nchw(eng.upsample2x(t))
+    assert (got - exp).abs().max() <= _tol(eng, exp)
+    acc, accref = _rand_nhwc(eng, 2, 14, 18, 64, seed=5)
+    eng.upsample2x(t, into=acc)
+    assert (_to_nchw(acc) - (accref + exp)).abs().max() <= _tol(eng, accref + exp)
+
+
+def test_groupnorm_apply_from_sums(eng):
+    t, ref = _rand_nhwc(eng, 2, 9, 11, 128)
+    gn = torch.nn.GroupNorm(32, 128)
+    with torch.no_grad():
+        gn.weight.uniform_(0.5, 1.5)
+        gn.bias.normal_(0, 0.2)
+    cg = 4
+    grp = ref.reshape(2, 32, cg, -1)
+    stats = torch.stack([grp.sum((2, 3)), (grp * grp).sum((2, 3))], -1).reshape(-1).cuda()
+    got = _to_nchw(eng.gn_relu(t, stats, gn))
+    exp = F.relu(gn(ref)).detach()
+    assert (got - exp).abs().max() <= _tol(eng, exp) + 2e-3
+
+
+def test_mul_and_ppa_gather(eng):
+    a, ar = _rand_nhwc(eng, 2, 8, 12, 128, seed=1)
+    b, br = _rand_nhwc(eng, 2, 8, 12, 128, seed=2)
+    out = eng._empty(2, 8, 12, 128)
+    eng._call(eng.lib.prn_mul, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+              C.c_int64(a.numel()), eng.dt, eng._st())
+    assert (_to_nchw(out) - ar * br).abs().max() <= _tol(eng, ar * br)
+    q = eng._empty(2, 2 * 3 * 4, 128)
+    eng._call(eng.lib.prn_ppa_gather, C.c_void_p(a.data_ptr()), C.c_void_p(q.data_ptr()), 2, 8, 12, 128, eng.dt, eng._st())
+    got = q.float().cpu().reshape(2, 2, 3, 2, 2, 128)        # (b, by, bx, dy, dx, c)
+    exp = ar.permute(0, 2, 3, 1).reshape(2, 2, 4, 3, 4, 128)[:, :, 1:3, :, 1:3].permute(0, 1, 3, 2, 4, 5)
+    assert torch.equal(got, exp)
+    # mean of those 4 pixels == bilinear x0.25 (align_corners=False)
+    down = F.interpolate(ar, scale_factor=0.25, mode="bilinear", align_corners=False, recompute_scale_factor=False)
+    assert (got.mean((3, 4)).permute(0, 3, 1, 2) - down).abs().max() < 1e-5
+
+
+def test_bad_arguments_are_rejected(eng):
+    t, _ = _rand_nhwc(eng, 1, 4, 4, 64)
+    with pytest.raises(L.PrnError):
+        eng._call(eng.lib.prn_avgpool2x2, C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()), 1, 3, 4, 64, eng.dt, eng._st())
+    with pytest.raises(L.PrnError):
+        eng._call(eng.lib.prn_mul, None, None, None, C.c_int64(8), eng.dt, eng._st())
