@@ -93,6 +93,10 @@ int prn_device_sm_count(void);
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores (TMEM accumulators, TMA-fed weights). */
 int prn_conv2d_fwd(const PrnConv* desc, void* stream);
+/* Same launch, additionally writing role-level stall counters (SM cycles) of CTA 0 to a device array of
+ * 16 int64: [0..3] A-producer {total, wait-empty, wait-cp.async, k-blocks}, [4..6] MMA issuer {total,
+ * wait-full, wait-tmem-empty}, [7..8] epilogue {total, wait-tmem-full}.  Performance tooling only. */
+int prn_conv2d_fwd_profile(const PrnConv* desc, void* stream, int64_t* counters16);
 /* Workspace-free helper: bytes of dynamic shared memory and CTAs the launch would use (for tests). */
 int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid);
 

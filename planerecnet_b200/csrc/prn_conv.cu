@@ -28,9 +28,9 @@ constexpr int kATileBytes = kTileM * 128;  // 128 rows x 64 16-bit elements
 constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 4;
 constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
-constexpr int kLag = 3;        // cp.async groups a producer thread keeps in flight
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 225 * 1024;
+constexpr int kCtrlBytes = 2048;   // mbarriers + TMEM slot (first 256 B), bias staging for the epilogue (+1024, 1 KB)
 
 struct ConvKParams {
   PrnConv d;
@@ -47,19 +47,158 @@ struct ConvKParams {
   int out_img_rows;
   int ld0, ld1;
   uint32_t idesc;
+  long long* dbg;   // optional role-level cycle counters of CTA 0 (prn_conv2d_fwd_profile)
 };
 
-__device__ __forceinline__ float act_apply(float x, int act, float param, int col) {
+// wait on an mbarrier, optionally accumulating the stall cycles
+__device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  if (!prof) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+template <int W>
+__device__ __forceinline__ void act_apply(float* x, int act, float param, int col0) {
   switch (act) {
-    case PRN_ACT_RELU: return fmaxf(x, 0.f);
+    case PRN_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < W; ++j) x[j] = fmaxf(x[j], 0.f);
+      break;
     case PRN_ACT_SIGMOID:
-    case PRN_ACT_SIGMOID_AVG4: return 1.f / (1.f + __expf(-x));
-    case PRN_ACT_SOFTPLUS: return x > 20.f ? x : log1pf(expf(x));
+    case PRN_ACT_SIGMOID_AVG4:
+#pragma unroll
+      for (int j = 0; j < W; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
+      break;
+    case PRN_ACT_SOFTPLUS:
+#pragma unroll
+      for (int j = 0; j < W; ++j) x[j] = x[j] > 20.f ? x[j] : log1pf(expf(x[j]));
+      break;
     case PRN_ACT_DCN_OFFMASK:
-      if (col < 18) return fminf(fmaxf(x, -param), param);
-      if (col < 27) return 2.f / (1.f + __expf(-x));
-      return 0.f;
-    default: return x;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const int col = col0 + j;
+        x[j] = col < 18 ? fminf(fmaxf(x[j], -param), param) : (col < 27 ? 2.f / (1.f + __expf(-x[j])) : 0.f);
+      }
+      break;
+    default: break;
+  }
+}
+
+// W/8 16-byte residual loads of one row chunk (zeros when the row is out of range)
+template <int W>
+__device__ __forceinline__ void load_res(uint4* r, const void* ptr, bool on) {
+#pragma unroll
+  for (int h = 0; h < W / 8; ++h) r[h] = on ? __ldg(reinterpret_cast<const uint4*>(ptr) + h) : make_uint4(0, 0, 0, 0);
+}
+
+// Epilogue math for W accumulator columns of one output row (one thread = one TMEM lane).
+template <typename T, int W>
+__device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const uint4* res, bool has_res,
+                                          const float* bias_s, int col0, bool valid, bool img_uniform, int img,
+                                          int lane, size_t orow) {
+  const PrnConv& d = p.d;
+  if (bias_s != nullptr) {
+#pragma unroll
+    for (int j = 0; j < W / 4; ++j) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
+      x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+    }
+  }
+  if (has_res) {
+#pragma unroll
+    for (int h = 0; h < W / 8; ++h) {
+      const uint32_t w4[4] = {res[h].x, res[h].y, res[h].z, res[h].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = Pack2<T>::unpack(w4[j]);
+        x[8 * h + 2 * j] += f.x;
+        x[8 * h + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  if (d.stats != nullptr && d.stats_cg > 0) {
+    // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators)
+    const int cg = d.stats_cg;
+    const int G = d.n_pad / cg;
+#pragma unroll
+    for (int hf = 0; hf < W / 16; ++hf) {
+      const float* xx = x + 16 * hf;
+      float q1[4], q2[4];  // sums over quads of columns (static indexing keeps x[] in registers)
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        q1[qd] = (xx[4 * qd] + xx[4 * qd + 1]) + (xx[4 * qd + 2] + xx[4 * qd + 3]);
+        q2[qd] = (xx[4 * qd] * xx[4 * qd] + xx[4 * qd + 1] * xx[4 * qd + 1]) +
+                 (xx[4 * qd + 2] * xx[4 * qd + 2] + xx[4 * qd + 3] * xx[4 * qd + 3]);
+      }
+      if (cg >= 8) { q1[0] += q1[1]; q2[0] += q2[1]; q1[2] += q1[3]; q2[2] += q2[3]; }
+      if (cg == 16) { q1[0] += q1[2]; q2[0] += q2[2]; }
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        if ((qd * 4) % cg != 0) continue;
+        float s1 = q1[qd], s2 = q2[qd];
+        const int gi = (col0 + 16 * hf + qd * 4) / cg;
+        if (img_uniform) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (lane == 0) {
+            atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
+            atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
+          }
+        } else if (valid) {
+          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
+          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
+        }
+      }
+    }
+  } else if (d.stats != nullptr) {
+    // BatchNorm batch statistics: per-channel sums over all rows
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      float s1 = valid ? x[j] : 0.f;
+      float s2 = s1 * s1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) {
+        atomicAdd(d.stats + static_cast<size_t>(col0 + j) * 2, s1);
+        atomicAdd(d.stats + static_cast<size_t>(col0 + j) * 2 + 1, s2);
+      }
+    }
+  }
+  act_apply<W>(x, d.act, d.act_param, col0);
+  bool store = valid;
+  if (d.act == PRN_ACT_SIGMOID_AVG4) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      float t = x[j];
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      x[j] = 0.25f * t;
+    }
+    store = valid && (lane & 3) == 0;
+  }
+  if (store) {
+    if (d.out16) {
+      uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(d.out16) + orow * d.ld_out16 + col0);
+#pragma unroll
+      for (int h = 0; h < W / 8; ++h) {
+        uint4 o;
+        o.x = Pack2<T>::pack(x[8 * h], x[8 * h + 1]); o.y = Pack2<T>::pack(x[8 * h + 2], x[8 * h + 3]);
+        o.z = Pack2<T>::pack(x[8 * h + 4], x[8 * h + 5]); o.w = Pack2<T>::pack(x[8 * h + 6], x[8 * h + 7]);
+        op[h] = o;
+      }
+    }
+    if (d.out32) {
+      float4* op = reinterpret_cast<float4*>(d.out32 + orow * d.ld_out32 + col0);
+#pragma unroll
+      for (int j = 0; j < W / 4; ++j) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    }
   }
 }
 
@@ -71,13 +210,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
 
-  // control block (first 1 KB): mbarriers + TMEM base slot
+  // control block: mbarriers + TMEM base slot, then the epilogue's bias staging area
   const uint32_t bar_full = base;             // [kMaxStages] x 8 B
   const uint32_t bar_empty = base + 64;       // [kMaxStages] x 8 B
   const uint32_t bar_tfull = base + 128;      // [2]
   const uint32_t bar_tempty = base + 144;     // [2]
   const uint32_t tmem_slot = base + 160;
-  const uint32_t a_base = base + 1024;
+  float* bias_s = reinterpret_cast<float*>(base_ptr + 1024);   // [256]
+  const uint32_t a_base = base + kCtrlBytes;
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
   const uint32_t b_base = a_base + static_cast<uint32_t>(p.stages) * kATileBytes;
 
@@ -115,8 +255,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int h_eff = d.h_in << ups_shift, w_eff = d.w_in << ups_shift;
     int s = 0;
     uint32_t ph = 0;
-    int s_lag = 0;
     uint32_t it = 0;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarps * 32;
+    long long w_empty = 0;
+    const long long t_role0 = prof ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
@@ -166,7 +308,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const uint8_t* src = static_cast<const uint8_t*>(first ? d.src0 : d.src1);
             const int cs = first ? p.ld0 : p.ld1;
             const int coff = (first ? c : c - d.c0) + chunk * 8;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -176,71 +318,75 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               const uint8_t* sp = src + (static_cast<size_t>(pix[i]) * cs + coff) * 2;
               cp_async16(dst, in ? sp : src, in ? 16u : 0u);
             }
-            cp_async_commit();
-            if (it >= kLag) {
-              cp_async_wait<kLag>();
-              fence_proxy_async_smem();
-              mbar_arrive(bar_full + 8 * s_lag);
-              if (++s_lag == p.stages) s_lag = 0;
-            }
+            // hardware arrives on the stage's barrier when these copies have landed: the thread never waits
+            // for its own loads, so up to `stages` k-blocks of gathers are in flight per thread
+            cp_async_mbar_arrive_noinc(bar_full + 8 * s);
             ++it;
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         } else {
           // ---- modulated deformable sampling (models/dcn.py:59-66, torchvision deform_conv2d):
           //      value = mask * bilinear(x, ho*s - pad + ky + dy, wo*s - pad + kx + dx), zero outside
-          //      (-1, H) x (-1, W); corners outside the image contribute 0.
+          //      (-1, H) x (-1, W); corners outside the image contribute 0 (weight 0, address clamped).
           const uint8_t* src = static_cast<const uint8_t*>(d.src0);
           const int cs = p.ld0;
+          const float fh = static_cast<float>(d.h_in), fw = static_cast<float>(d.w_in);
           for (int cc = 0; cc < p.kb_per_tap; ++cc) {
             const int coff = cc * 64 + chunk * 8;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
-#pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
-              const int r = pw * 32 + i * 4 + sub;
-              const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
-              float acc[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-              if ((valid >> i) & 1u) {
+            for (int hb = 0; hb < 2; ++hb) {   // two batches of 4 rows: 16 independent 16-byte loads in flight
+              float wg[4][4];
+              uint4 q[4][4];
+#pragma unroll
+              for (int r4 = 0; r4 < 4; ++r4) {
+                const int i = hb * 4 + r4;
                 const float* om = d.dcn_offmask + static_cast<size_t>(m_glob[i]) * 32;
                 const float py = static_cast<float>(hy[i] + ky) + __ldg(om + 2 * tap);
                 const float px = static_cast<float>(wx[i] + kx) + __ldg(om + 2 * tap + 1);
                 const float mk = __ldg(om + 18 + tap);
-                if (py > -1.f && py < static_cast<float>(d.h_in) && px > -1.f && px < static_cast<float>(d.w_in)) {
-                  const float fy = floorf(py), fx = floorf(px);
-                  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-                  const float ly = py - fy, lx = px - fx;
-                  const float wy[2] = {1.f - ly, ly};
-                  const float wxx[2] = {1.f - lx, lx};
+                const bool inside = ((valid >> i) & 1u) && py > -1.f && py < fh && px > -1.f && px < fw;
+                const float fy = floorf(py), fx = floorf(px);
+                const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+                const float ly = py - fy, lx = px - fx;
 #pragma unroll
-                  for (int cy = 0; cy < 2; ++cy) {
+                for (int cy = 0; cy < 2; ++cy) {
 #pragma unroll
-                    for (int cx = 0; cx < 2; ++cx) {
-                      const int yy = y0 + cy, xx = x0 + cx;
-                      if (yy >= 0 && yy < d.h_in && xx >= 0 && xx < d.w_in) {
-                        const float wgt = wy[cy] * wxx[cx] * mk;
-                        const uint4 q = __ldg(reinterpret_cast<const uint4*>(
-                            src + (static_cast<size_t>(img_pix[i] + yy * d.w_in + xx) * cs + coff) * 2));
-                        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                          const float2 f = Pack2<T>::unpack(w4[j]);
-                          acc[2 * j] = fmaf(wgt, f.x, acc[2 * j]);
-                          acc[2 * j + 1] = fmaf(wgt, f.y, acc[2 * j + 1]);
-                        }
-                      }
-                    }
+                  for (int cx = 0; cx < 2; ++cx) {
+                    const int yy = y0 + cy, xx = x0 + cx;
+                    const bool okc = inside && yy >= 0 && yy < d.h_in && xx >= 0 && xx < d.w_in;
+                    wg[r4][cy * 2 + cx] = okc ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) * mk : 0.f;
+                    const int yc = min(max(yy, 0), d.h_in - 1), xc = min(max(xx, 0), d.w_in - 1);
+                    q[r4][cy * 2 + cx] = __ldg(reinterpret_cast<const uint4*>(
+                        src + (static_cast<size_t>(img_pix[i] + yc * d.w_in + xc) * cs + coff) * 2));
                   }
                 }
               }
-              const uint32_t o0 = Pack2<T>::pack(acc[0], acc[1]), o1 = Pack2<T>::pack(acc[2], acc[3]);
-              const uint32_t o2 = Pack2<T>::pack(acc[4], acc[5]), o3 = Pack2<T>::pack(acc[6], acc[7]);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                           : "memory");
+#pragma unroll
+              for (int r4 = 0; r4 < 4; ++r4) {
+                const int r = pw * 32 + (hb * 4 + r4) * 4 + sub;
+                const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
+                float acc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+                for (int cnr = 0; cnr < 4; ++cnr) {
+                  const uint32_t w4[4] = {q[r4][cnr].x, q[r4][cnr].y, q[r4][cnr].z, q[r4][cnr].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = Pack2<T>::unpack(w4[j]);
+                    acc[2 * j] = fmaf(wg[r4][cnr], f.x, acc[2 * j]);
+                    acc[2 * j + 1] = fmaf(wg[r4][cnr], f.y, acc[2 * j + 1]);
+                  }
+                }
+                const uint32_t o0 = Pack2<T>::pack(acc[0], acc[1]), o1 = Pack2<T>::pack(acc[2], acc[3]);
+                const uint32_t o2 = Pack2<T>::pack(acc[4], acc[5]), o3 = Pack2<T>::pack(acc[6], acc[7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                             : "memory");
+              }
             }
-            fence_proxy_async_smem();
+            fence_proxy_async_smem();     // generic-proxy st.shared -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * s);
             ++it;
             if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -248,15 +394,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
-    if constexpr (!kDCN) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      const uint32_t pending = it < static_cast<uint32_t>(kLag) ? it : static_cast<uint32_t>(kLag);
-      for (uint32_t j = 0; j < pending; ++j) {
-        mbar_arrive(bar_full + 8 * s_lag);
-        if (++s_lag == p.stages) s_lag = 0;
-      }
-    }
+    if (prof) { p.dbg[0] = clock64() - t_role0; p.dbg[1] = w_empty; p.dbg[2] = 0; p.dbg[3] = it; }
   } else if (warp == 8) {
     // =========================================================== B producer (TMA)
     if (lane == 0) {
@@ -281,12 +419,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
+      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_role0 = prof ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_ph ^ 1u);
+        mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1u, prof, w_tempty);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(bar_full + 8 * s, ph);
+          mbar_wait_acc(bar_full + 8 * s, ph, prof, w_full);
+          fence_proxy_async_smem();   // cp.async-written operand tile -> async proxy (belt and braces)
           tc_fence_after();
           const uint32_t a_addr = a_base + static_cast<uint32_t>(s) * kATileBytes;
           const uint32_t b_addr = b_base + static_cast<uint32_t>(s) * b_stage_bytes;
@@ -302,19 +444,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1u;
       }
+      if (prof) { p.dbg[4] = clock64() - t_role0; p.dbg[5] = w_full; p.dbg[6] = w_tempty; }
     }
   } else {
     // =========================================================== epilogue (warps 0-3)
     const int q = warp;  // TMEM lane quarter
+    const int etid = threadIdx.x;   // 0..127
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool avg4 = d.act == PRN_ACT_SIGMOID_AVG4;
+    const bool has_res = d.residual != nullptr;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    long long w_tfull = 0;
+    const long long t_role0 = prof ? clock64() : 0;
+    int bias_n0 = -1;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int g = rest / p.m_tiles;
       const int n0 = nt * p.n_tile;
+      const int n_valid = min(p.n_tile, d.n_pad - n0);   // multiple of 16
       const int m = mt * kTileM + q * 32 + lane;
       const bool valid = m < p.m_group;
       const int mm = valid ? m : 0;
@@ -327,129 +477,72 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       // (the shuffle must not sit behind `valid &&`: short-circuiting would leave the invalid lanes out of it)
       const int img_lane0 = __shfl_sync(0xffffffffu, img, 0);
       const bool img_uniform = __all_sync(0xffffffffu, valid && img == img_lane0);
+      const T* res_row = has_res ? static_cast<const T*>(d.residual) + rrow * d.ld_res + n0 : nullptr;
 
-      mbar_wait(bar_tfull + 8 * acc, acc_ph);
+      // bias of this tile's columns -> shared memory (overlaps the tile's MMAs); reloaded only when n0 changes
+      if (d.bias != nullptr && n0 != bias_n0) {
+        named_bar_sync(1, kEpiWarps * 32);          // everyone is done with the previous tile's values
+        for (int i = etid; i < n_valid; i += kEpiWarps * 32) bias_s[i] = __ldg(d.bias + n0 + i);
+        named_bar_sync(1, kEpiWarps * 32);
+        bias_n0 = n0;
+      }
+
+      mbar_wait_acc(bar_tfull + 8 * acc, acc_ph, prof, w_tfull);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
-      for (int c = 0; c < p.n_tile; c += 16) {
-        if (n0 + c >= d.n_pad) break;
-        uint32_t v[16];
-        // tcgen05.ld is .sync.aligned: lanes diverged by the per-row `valid` predicates below (tiles whose
-        // row count is not a multiple of 32) must reconverge first, or the warp deadlocks.
-        __syncwarp();
-        tmem_ld_x16(t_row + c, v);
+
+      // accumulator -> registers, software pipelined: the tcgen05.ld and the residual loads of chunk i+1 are in
+      // flight while chunk i is processed.  tcgen05.ld is .sync.aligned: lanes diverged by per-row predicates
+      // must reconverge (__syncwarp) before each one.
+      const int n32 = n_valid >> 5;
+      const bool tail16 = (n_valid & 16) != 0;
+      uint32_t vb[32];
+      uint4 rb[4];
+      __syncwarp();
+      if (n32 > 0) {
+        tmem_ld_x32(t_row, vb);
+        load_res<32>(rb, res_row, has_res && valid);
+      } else {
+        tmem_ld_x16(t_row, vb);
+        load_res<16>(rb, res_row, has_res && valid);
+      }
+      for (int ci = 0; ci < n32; ++ci) {
         tmem_ld_wait();
+        tmem_ld_publish16(vb);
+        tmem_ld_publish16(vb + 16);
+        float x[32];
+        uint4 rc[4];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vb[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rc[j] = rb[j];
+        const int cn = (ci + 1) * 32;
+        __syncwarp();
+        if (ci + 1 < n32) {
+          tmem_ld_x32(t_row + cn, vb);
+          load_res<32>(rb, res_row + cn, has_res && valid);
+        } else if (tail16) {
+          tmem_ld_x16(t_row + cn, vb);
+          load_res<16>(rb, res_row + cn, has_res && valid);
+        }
+        epi_chunk<T, 32>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+                         img, lane, orow);
+      }
+      if (tail16) {
+        tmem_ld_wait();
+        tmem_ld_publish16(vb);
         float x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-        if (d.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(d.bias + n0 + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 b = __ldg(bp + j);
-            x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
-          }
-        }
-        if (d.residual && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(d.residual) + rrow * d.ld_res + n0 + c);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 rv = __ldg(rp + h);
-            const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = Pack2<T>::unpack(w4[j]);
-              x[8 * h + 2 * j] += f.x;
-              x[8 * h + 2 * j + 1] += f.y;
-            }
-          }
-        }
-        if (d.stats != nullptr && d.stats_cg > 0) {
-          // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators)
-          const int cg = d.stats_cg;
-          const int G = d.n_pad / cg;
-          float q1[4], q2[4];  // sums over quads of columns (static indexing keeps x[] in registers)
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            q1[qd] = (x[4 * qd] + x[4 * qd + 1]) + (x[4 * qd + 2] + x[4 * qd + 3]);
-            q2[qd] = (x[4 * qd] * x[4 * qd] + x[4 * qd + 1] * x[4 * qd + 1]) +
-                     (x[4 * qd + 2] * x[4 * qd + 2] + x[4 * qd + 3] * x[4 * qd + 3]);
-          }
-          if (cg >= 8) { q1[0] += q1[1]; q2[0] += q2[1]; q1[2] += q1[3]; q2[2] += q2[3]; }
-          if (cg == 16) { q1[0] += q1[2]; q2[0] += q2[2]; }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            if ((qd * 4) % cg != 0) continue;
-            float s1 = q1[qd], s2 = q2[qd];
-            const int gi = (n0 + c + qd * 4) / cg;
-            if (img_uniform) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              }
-              if (lane == 0) {
-                atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
-                atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
-              }
-            } else if (valid) {
-              atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
-              atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
-            }
-          }
-        } else if (d.stats != nullptr) {
-          // BatchNorm batch statistics: per-channel sums over all rows
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float s1 = valid ? x[j] : 0.f;
-            float s2 = s1 * s1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            if (lane == 0) {
-              atomicAdd(d.stats + static_cast<size_t>(n0 + c + j) * 2, s1);
-              atomicAdd(d.stats + static_cast<size_t>(n0 + c + j) * 2 + 1, s2);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = act_apply(x[j], d.act, d.act_param, n0 + c + j);
-        bool store = valid;
-        if (avg4) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float t = x[j];
-            t += __shfl_xor_sync(0xffffffffu, t, 1);
-            t += __shfl_xor_sync(0xffffffffu, t, 2);
-            x[j] = 0.25f * t;
-          }
-          store = valid && (lane & 3) == 0;
-        }
-        if (store) {
-          if (d.out16) {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(d.out16) + orow * d.ld_out16 + n0 + c);
-            uint4 o;
-            o.x = Pack2<T>::pack(x[0], x[1]); o.y = Pack2<T>::pack(x[2], x[3]);
-            o.z = Pack2<T>::pack(x[4], x[5]); o.w = Pack2<T>::pack(x[6], x[7]);
-            op[0] = o;
-            o.x = Pack2<T>::pack(x[8], x[9]); o.y = Pack2<T>::pack(x[10], x[11]);
-            o.z = Pack2<T>::pack(x[12], x[13]); o.w = Pack2<T>::pack(x[14], x[15]);
-            op[1] = o;
-          }
-          if (d.out32) {
-            float4* op = reinterpret_cast<float4*>(d.out32 + orow * d.ld_out32 + n0 + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          }
-        }
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(vb[j]);
+        epi_chunk<T, 16>(p, x, rb, has_res, d.bias ? bias_s + n32 * 32 : nullptr, n0 + n32 * 32, valid, img_uniform,
+                         img, lane, orow);
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
     }
+    if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull; }
   }
 
   tc_fence_before();
@@ -521,12 +614,13 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   while (cols < 2 * n_tile) cols *= 2;
   p->tmem_cols = cols;
   const int stage_bytes = kATileBytes + n_tile * 128;
-  int stages = (kSmemBudget - 2048) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kCtrlBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  PRN_REQUIRE(stages > kLag, "conv: not enough shared memory for %d stages", kLag + 1);
+  PRN_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p->stages = stages;
   p->kb_per_tap = (d.c0 + d.c1) / 64;
   p->num_kb = d.ksize * d.ksize * p->kb_per_tap;
+  p->dbg = nullptr;
   p->idesc = umma_idesc(d.dtype == PRN_BF16 ? 1u : 0u, kTileM, static_cast<uint32_t>(n_tile));
   return PRN_OK;
 }
@@ -556,12 +650,21 @@ extern "C" int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* st
   return PRN_OK;
 }
 
-extern "C" int prn_conv2d_fwd(const PrnConv* desc, void* stream) {
+static int conv_launch(const PrnConv* desc, void* stream, long long* dbg);
+
+extern "C" int prn_conv2d_fwd(const PrnConv* desc, void* stream) { return conv_launch(desc, stream, nullptr); }
+
+extern "C" int prn_conv2d_fwd_profile(const PrnConv* desc, void* stream, int64_t* counters16) {
+  return conv_launch(desc, stream, reinterpret_cast<long long*>(counters16));
+}
+
+static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   using namespace prn;
   if (!desc) return set_error(PRN_ERR_INVALID, "conv: NULL descriptor");
   ConvKParams p;
   int rc = plan(*desc, &p);
   if (rc != PRN_OK) return rc;
+  p.dbg = dbg;
   const PrnConv& d = p.d;
   CUtensorMap tm;
   const uint64_t kdim = static_cast<uint64_t>(d.ksize) * d.ksize * (d.c0 + d.c1);
@@ -569,7 +672,7 @@ extern "C" int prn_conv2d_fwd(const PrnConv* desc, void* stream) {
   rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile), d.dtype);
   if (rc != PRN_OK) return rc;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  const size_t smem = 2048 + static_cast<size_t>(p.stages) * (kATileBytes + p.n_tile * 128);
+  const size_t smem = 1024 + kCtrlBytes + static_cast<size_t>(p.stages) * (kATileBytes + p.n_tile * 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool dcn = d.dcn_offmask != nullptr;
   if (d.dtype == PRN_BF16)

@@ -52,7 +52,7 @@ def pad_vec(v, n_pad):
 def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mode=L.PAD_ZERO, upsample=1,
            src1=None, bias=None, residual=None, act=L.ACT_NONE, act_param=0.0, out16=None, out32=None,
            ld_out16=None, ld_out32=None, out_img_rows=0, stats=None, stats_cg=0, dcn_offmask=None,
-           n_pad=None, w_group_rows=0, dtype=L.PRN_BF16, c0=None, c1=None, ld_res=None):
+           n_pad=None, w_group_rows=0, dtype=L.PRN_BF16, c0=None, c1=None, ld_res=None, counters=None):
     """Launch prn_conv2d_fwd.  src*/residual/out16 are 16-bit NHWC tensors (any shape, channels last)."""
     d = L.PrnConv()
     d.src0 = src0.data_ptr()
@@ -83,5 +83,9 @@ def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mod
     d.stats = stats.data_ptr() if stats is not None else None
     d.stats_cg = stats_cg
     d.dtype = dtype
-    L.check(L.lib().prn_conv2d_fwd(C.byref(d), L.current_stream()), "prn_conv2d_fwd")
+    if counters is not None:
+        L.check(L.lib().prn_conv2d_fwd_profile(C.byref(d), L.current_stream(), C.c_void_p(counters.data_ptr())),
+                "prn_conv2d_fwd_profile")
+    else:
+        L.check(L.lib().prn_conv2d_fwd(C.byref(d), L.current_stream()), "prn_conv2d_fwd")
     return d

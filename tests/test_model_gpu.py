@@ -80,22 +80,26 @@ def test_graph_replay_equals_eager_and_tracks_weight_updates(cuda_lib):
     net, x, orc, ref, st = _run("PlaneRecNet_50_config", 1, 128, 160, "f16")
     eng = net.engine
     xc = x.cuda()
+    # GroupNorm sums are accumulated with fp32 atomics (order varies run to run), so two runs agree up to
+    # isolated 16-bit rounding flips, not bit for bit
+    same = lambda p, q: H.rel_l2(p, q) < 1e-3
     with torch.no_grad():
-        eager = [t.clone() for t in (st["outputs"][0], st["outputs"][3])]
+        eager = [st["outputs"][0].clone(), st["outputs"][3].clone()]
         g1 = eng.forward_dense_graph(net, xc)
         a = [g1["outputs"][0].clone(), g1["outputs"][3].clone()]
         x2 = H.make_input(1, 128, 160, seed=3).cuda()
         g2 = eng.forward_dense_graph(net, x2)
-        b = g2["outputs"][0].clone()
-        e2 = eng.forward_dense(net, x2)["outputs"][0]
-    assert torch.equal(a[0], eager[0]) and torch.equal(a[1], eager[1])
-    assert torch.equal(b, e2) and not torch.equal(b, a[0])
-    # an in-place weight update must invalidate packed weights and the captured graph
+        b = [g2["outputs"][0].clone(), g2["outputs"][3].clone()]
+        e2 = eng.forward_dense(net, x2)["outputs"]
+    assert same(a[0], eager[0]) and same(a[1], eager[1]), "graph replay differs from the eager launch sequence"
+    assert same(b[0], e2[0]) and same(b[1], e2[3]), "graph replay ignored the new input"
+    assert not same(b[1], a[1])
+    # an in-place weight update must invalidate the packed weights and the captured graph
     with torch.no_grad():
-        net.fpn.fpn_convs[0].weight.mul_(1.5)
-        g3 = eng.forward_dense_graph(net, xc)["outputs"][0].clone()
-        e3 = eng.forward_dense(net, xc)["outputs"][0]
-    assert torch.equal(g3, e3) and not torch.equal(g3, a[0])
+        net.depth_decoder.latlayer1.weight.mul_(1.5)
+        g3 = eng.forward_dense_graph(net, xc)["outputs"][3].clone()
+        e3 = eng.forward_dense(net, xc)["outputs"][3]
+    assert same(g3, e3) and not same(g3, a[1])
 
 
 def test_module_level_entry_points(cuda_lib):
