@@ -17,6 +17,7 @@
 //                         tcgen05.commit to recycle the smem stage / publish the accumulator
 //
 // Replaces the nn.Conv2d / F.conv2d / deform_conv2d call sites listed in include/prn_b200.h.
+#include <math.h>
 #include <stdio.h>
 #include "prn_internal.h"
 #include "prn_ptx.cuh"
@@ -29,7 +30,8 @@ constexpr int kEpiWarps = 4;
 constexpr int kProdWarps = 4;
 constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 225 * 1024;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kStageOutBytes = kEpiWarps * 8192;   // per warp: two 32-row x 128 B staging tiles for TMA stores
 constexpr int kCtrlBytes = 2048;   // mbarriers + TMEM slot (first 256 B), bias staging for the epilogue (+1024, 1 KB)
 
 struct ConvKParams {
@@ -46,6 +48,9 @@ struct ConvKParams {
   int hw_out;
   int out_img_rows;
   int ld0, ld1;
+  float inv_hw_out, inv_w_out;
+  int lean_epi;       // 1: lean epilogue instantiation (see epi_chunk)
+  int tma_store;      // 1: 16-bit output rows are dense -> epilogue stages 32x64 sub-tiles in smem and TMA-stores them
   uint32_t idesc;
   long long* dbg;   // optional role-level cycle counters of CTA 0 (prn_conv2d_fwd_profile)
 };
@@ -56,6 +61,15 @@ __device__ __forceinline__ void mbar_wait_acc(uint32_t bar, uint32_t parity, boo
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t0;
+}
+
+// q = m / d, r = m % d for 0 <= m < 2^24 with inv = 1.0f / d: one multiply + fix-up instead of a ~40 instruction
+// integer division (the producer and the epilogue decode 8 + 1 rows per tile).
+__device__ __forceinline__ void fast_divmod(int m, int dv, float inv, int& q, int& r) {
+  q = __float2int_rz(__int2float_rz(m) * inv);
+  r = m - q * dv;
+  if (r < 0) { --q; r += dv; }
+  if (r >= dv) { ++q; r -= dv; }
 }
 
 template <int W>
@@ -93,10 +107,13 @@ __device__ __forceinline__ void load_res(uint4* r, const void* ptr, bool on) {
 }
 
 // Epilogue math for W accumulator columns of one output row (one thread = one TMEM lane).
-template <typename T, int W>
+// kFull = false is the lean instantiation used by most layers (bias, residual, none/ReLU, 16-bit output): the
+// generic one (statistics, sigmoid/softplus/DCN activations, fp32 output, row averaging) is ~10x more code and
+// thrashes the instruction cache when it sits inside the per-chunk loop.
+template <typename T, int W, bool kFull>
 __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const uint4* res, bool has_res,
                                           const float* bias_s, int col0, bool valid, bool img_uniform, int img,
-                                          int lane, size_t orow) {
+                                          int lane, size_t orow, uint32_t stage_row, int jbase) {
   const PrnConv& d = p.d;
   if (bias_s != nullptr) {
 #pragma unroll
@@ -116,6 +133,30 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
         x[8 * h + 2 * j + 1] += f.y;
       }
     }
+  }
+  if constexpr (!kFull) {
+    const float lo = d.act == PRN_ACT_RELU ? 0.f : -INFINITY;
+#pragma unroll
+    for (int j = 0; j < W; ++j) x[j] = fmaxf(x[j], lo);
+    if (stage_row != 0) {
+#pragma unroll
+      for (int h = 0; h < W / 8; ++h) {
+        const uint32_t o0 = Pack2<T>::pack(x[8 * h], x[8 * h + 1]), o1 = Pack2<T>::pack(x[8 * h + 2], x[8 * h + 3]);
+        const uint32_t o2 = Pack2<T>::pack(x[8 * h + 4], x[8 * h + 5]), o3 = Pack2<T>::pack(x[8 * h + 6], x[8 * h + 7]);
+        const uint32_t dst = stage_row + ((((jbase + h) ^ (lane & 7))) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      }
+    } else if (valid) {
+      uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(d.out16) + orow * d.ld_out16 + col0);
+#pragma unroll
+      for (int h = 0; h < W / 8; ++h) {
+        uint4 o;
+        o.x = Pack2<T>::pack(x[8 * h], x[8 * h + 1]); o.y = Pack2<T>::pack(x[8 * h + 2], x[8 * h + 3]);
+        o.z = Pack2<T>::pack(x[8 * h + 4], x[8 * h + 5]); o.w = Pack2<T>::pack(x[8 * h + 6], x[8 * h + 7]);
+        op[h] = o;
+      }
+    }
+    return;
   }
   if (d.stats != nullptr && d.stats_cg > 0) {
     // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators)
@@ -183,7 +224,17 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
     }
     store = valid && (lane & 3) == 0;
   }
-  if (store) {
+  if (stage_row != 0) {
+    // 16-byte pieces of this row go to the 128B-swizzled staging tile; a TMA store writes it out coalesced
+    // (rows beyond M and columns beyond n_pad are clipped by the tensor map).
+#pragma unroll
+    for (int h = 0; h < W / 8; ++h) {
+      const uint32_t o0 = Pack2<T>::pack(x[8 * h], x[8 * h + 1]), o1 = Pack2<T>::pack(x[8 * h + 2], x[8 * h + 3]);
+      const uint32_t o2 = Pack2<T>::pack(x[8 * h + 4], x[8 * h + 5]), o3 = Pack2<T>::pack(x[8 * h + 6], x[8 * h + 7]);
+      const uint32_t dst = stage_row + ((((jbase + h) ^ (lane & 7))) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+    }
+  } else if (store) {
     if (d.out16) {
       uint4* op = reinterpret_cast<uint4*>(static_cast<T*>(d.out16) + orow * d.ld_out16 + col0);
 #pragma unroll
@@ -202,9 +253,10 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
   }
 }
 
-template <typename T, bool kDCN>
+template <typename T, bool kDCN, bool kFull>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ ConvKParams p) {
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                 const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -217,7 +269,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const uint32_t bar_tempty = base + 144;     // [2]
   const uint32_t tmem_slot = base + 160;
   float* bias_s = reinterpret_cast<float*>(base_ptr + 1024);   // [256]
-  const uint32_t a_base = base + kCtrlBytes;
+  const uint32_t stg_base = base + kCtrlBytes;                  // [kEpiWarps][2] x 4 KB, 1024-aligned
+  const uint32_t a_base = stg_base + kStageOutBytes;
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
   const uint32_t b_base = a_base + static_cast<uint32_t>(p.stages) * kATileBytes;
 
@@ -227,6 +280,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
+    if (p.tma_store) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, kProdWarps * 32 + 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -258,6 +312,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     uint32_t it = 0;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarps * 32;
     long long w_empty = 0;
+    uint32_t row_off[8];   // swizzled position of this thread's 16-byte chunk in each of its 8 rows of an A stage
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = pw * 32 + i * 4 + sub;
+      row_off[i] = static_cast<uint32_t>(r * 128 + ((chunk ^ (r & 7)) << 4));
+    }
     const long long t_role0 = prof ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int rest = tile / p.n_tiles;
@@ -272,10 +332,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int m = mt * kTileM + r;
         const bool v = m < p.m_group;
         const int mm = v ? m : 0;
-        const int n_local = mm / p.hw_out;
-        const int rem = mm - n_local * p.hw_out;
-        const int ho = rem / d.w_out;
-        const int wo = rem - ho * d.w_out;
+        int n_local, rem, ho, wo;
+        fast_divmod(mm, p.hw_out, p.inv_hw_out, n_local, rem);
+        fast_divmod(rem, d.w_out, p.inv_w_out, ho, wo);
         const int img = g * p.imgs_per_group + n_local;
         img_pix[i] = img * d.h_in * d.w_in;
         hy[i] = ho * d.stride - d.pad;
@@ -284,10 +343,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         valid |= (v ? 1u : 0u) << i;
       }
       const int taps = d.ksize * d.ksize;
+      int ky = 0, kx = -1;
       for (int tap = 0; tap < taps; ++tap) {
-        const int ky = tap / d.ksize, kx = tap - ky * d.ksize;
+        if (++kx == d.ksize) { kx = 0; ++ky; }
         if constexpr (!kDCN) {
-          int pix[8];
+          // per tap: byte offset of every row's source pixel (0 when the tap falls outside: the address stays
+          // valid and the copy is issued with src-size 0 = zero fill)
+          uint32_t poff[8];
           uint32_t ok = 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -297,26 +359,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               y = y < 0 ? -y : (y >= h_eff ? 2 * h_eff - 2 - y : y);
               x = x < 0 ? -x : (x >= w_eff ? 2 * w_eff - 2 - x : x);
             } else {
-              in = in && y >= 0 && y < h_eff && x >= 0 && x < w_eff;
+              in = in && static_cast<unsigned>(y) < static_cast<unsigned>(h_eff) &&
+                   static_cast<unsigned>(x) < static_cast<unsigned>(w_eff);
             }
-            pix[i] = in ? img_pix[i] + (y >> ups_shift) * d.w_in + (x >> ups_shift) : 0;
+            const int pix = in ? img_pix[i] + (y >> ups_shift) * d.w_in + (x >> ups_shift) : 0;
+            poff[i] = static_cast<uint32_t>(pix);
             ok |= (in ? 1u : 0u) << i;
           }
           for (int cc = 0; cc < p.kb_per_tap; ++cc) {
             const int c = cc * 64;
             const bool first = c < d.c0;
-            const uint8_t* src = static_cast<const uint8_t*>(first ? d.src0 : d.src1);
-            const int cs = first ? p.ld0 : p.ld1;
-            const int coff = (first ? c : c - d.c0) + chunk * 8;
+            const uint8_t* srcb = static_cast<const uint8_t*>(first ? d.src0 : d.src1) +
+                                  static_cast<size_t>((first ? c : c - d.c0) + chunk * 8) * 2;
+            const uint32_t pitch = static_cast<uint32_t>(first ? p.ld0 : p.ld1) * 2u;   // bytes per pixel
             mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int r = pw * 32 + i * 4 + sub;
-              const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
-              const bool in = (ok >> i) & 1u;
-              const uint8_t* sp = src + (static_cast<size_t>(pix[i]) * cs + coff) * 2;
-              cp_async16(dst, in ? sp : src, in ? 16u : 0u);
+              cp_async16(a_stage + row_off[i], srcb + poff[i] * pitch, ((ok >> i) & 1u) ? 16u : 0u);   // < 4 GiB (host-checked)
             }
             // hardware arrives on the stage's barrier when these copies have landed: the thread never waits
             // for its own loads, so up to `stages` k-blocks of gathers are in flight per thread
@@ -458,6 +518,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     long long w_tfull = 0;
     const long long t_role0 = prof ? clock64() : 0;
     int bias_n0 = -1;
+    uint32_t sgrp = 0;   // running count of 64-column groups this warp has staged (selects the staging tile)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -468,8 +529,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const int m = mt * kTileM + q * 32 + lane;
       const bool valid = m < p.m_group;
       const int mm = valid ? m : 0;
-      const int n_local = mm / p.hw_out;
-      const int pp = mm - n_local * p.hw_out;
+      int n_local, pp;
+      fast_divmod(mm, p.hw_out, p.inv_hw_out, n_local, pp);
       const int img = g * p.imgs_per_group + n_local;
       const size_t orow = avg4 ? static_cast<size_t>(img) * p.out_img_rows + (pp >> 2)
                                : static_cast<size_t>(img) * p.out_img_rows + pp;
@@ -506,6 +567,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         tmem_ld_x16(t_row, vb);
         load_res<16>(rb, res_row, has_res && valid);
       }
+      const uint32_t stg_warp = stg_base + static_cast<uint32_t>(q) * 8192u;
+      const int row0_out = mt * kTileM + q * 32;          // first output row of this warp's sub-tile
       for (int ci = 0; ci < n32; ++ci) {
         tmem_ld_wait();
         tmem_ld_publish16(vb);
@@ -525,23 +588,53 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           tmem_ld_x16(t_row + cn, vb);
           load_res<16>(rb, res_row + cn, has_res && valid);
         }
-        epi_chunk<T, 32>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
-                         img, lane, orow);
+        const uint32_t stg_tile = stg_warp + (sgrp & 1u) * 4096u;
+        if (p.tma_store && (ci & 1) == 0) {
+          // this staging tile was last used two groups ago: that TMA store must have finished reading it
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        epi_chunk<T, 32, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+                         img, lane, orow, p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u, (ci & 1) * 4);
+        if (p.tma_store && ((ci & 1) == 1 || (ci + 1 == n32 && !tail16))) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stg_tile, n0 + (ci >> 1) * 64, row0_out);
+            bulk_commit();
+          }
+          ++sgrp;
+        }
       }
-      if (tail16) {
+      if (kFull && tail16) {
         tmem_ld_wait();
         tmem_ld_publish16(vb);
         float x[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(vb[j]);
-        epi_chunk<T, 16>(p, x, rb, has_res, d.bias ? bias_s + n32 * 32 : nullptr, n0 + n32 * 32, valid, img_uniform,
-                         img, lane, orow);
+        const uint32_t stg_tile = stg_warp + (sgrp & 1u) * 4096u;
+        if (p.tma_store && (n32 & 1) == 0) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        epi_chunk<T, 16, kFull>(p, x, rb, has_res, d.bias ? bias_s + n32 * 32 : nullptr, n0 + n32 * 32, valid, img_uniform,
+                         img, lane, orow, p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u, (n32 & 1) * 4);
+        if (p.tma_store) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stg_tile, n0 + (n32 >> 1) * 64, row0_out);
+            bulk_commit();
+          }
+          ++sgrp;
+        }
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1u;
     }
+    if (p.tma_store && lane == 0) bulk_wait<0>();   // all TMA stores of this warp have completed
     if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull; }
   }
 
@@ -598,15 +691,36 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   } else {
     p->out_img_rows = d.out_img_rows ? d.out_img_rows : p->hw_out;
   }
-  // N tiling: one tile if it fits TMEM double-buffered, else 256/128-wide tiles.
-  int n_tile;
-  if (d.n_pad <= 256) n_tile = d.n_pad;
-  else if (d.n_pad % 256 == 0) n_tile = 256;
-  else n_tile = 128;
+  PRN_REQUIRE(p->m_group < (1 << 24), "conv: more than 2^24 output rows per group is not supported");
+  PRN_REQUIRE(static_cast<unsigned long long>(d.batch) * d.h_in * d.w_in * (d.ld0 ? d.ld0 : d.c0) * 2ull < (1ull << 32) &&
+                  static_cast<unsigned long long>(d.batch) * d.h_in * d.w_in * (d.ld1 ? d.ld1 : (d.c1 ? d.c1 : 1)) * 2ull < (1ull << 32),
+              "conv: source tensors of 4 GiB or more are not supported (32-bit byte offsets in the gather)");
+  p->inv_hw_out = 1.0f / static_cast<float>(p->hw_out);
+  p->inv_w_out = 1.0f / static_cast<float>(d.w_out);
+  // N tiling.  Candidates: the whole (padded) width if it fits the double-buffered TMEM, else 256/128/64.  Pick the
+  // one with the smallest modelled time: waves x (k-blocks x max(MMA issue, L2->SM operand stream) + epilogue).
+  // Narrow tiles give more CTAs work but re-gather the A tile once per N tile (9x more expensive for DCN).
   p->m_tiles = ceil_div(p->m_group, kTileM);
-  // Small problems: narrower tiles so that more SMs get work.
   const int sms = sm_count();
-  while (n_tile > 64 && n_tile % 32 == 0 && p->groups * p->m_tiles * ceil_div(d.n_pad, n_tile) < sms) n_tile /= 2;
+  const int kb = d.ksize * d.ksize * ((d.c0 + d.c1) / 64);
+  int cands[4];
+  int nc = 0;
+  if (d.n_pad <= 256) cands[nc++] = d.n_pad;
+  else cands[nc++] = (d.n_pad % 256 == 0) ? 256 : 128;
+  for (int t = 128; t >= 64; t /= 2)
+    if (t < cands[0] && d.n_pad % t == 0) cands[nc++] = t;
+  int n_tile = cands[0];
+  double best = 1e300;
+  for (int i = 0; i < nc; ++i) {
+    const int t = cands[i];
+    const long long tiles = static_cast<long long>(p->groups) * p->m_tiles * ceil_div(d.n_pad, t);
+    const double waves = static_cast<double>((tiles + sms - 1) / sms);
+    const double a_cost = d.dcn_offmask ? 3400.0 : 16384.0 / 46.0;          // cycles to produce one A k-block
+    const double per_kb = fmax(2.0 * t, a_cost + 128.0 * t / 46.0) + 60.0;
+    const double tile_cost = kb * per_kb + 30.0 * t + 2500.0;
+    const double cost = waves * tile_cost;
+    if (cost < best) { best = cost; n_tile = t; }
+  }
   p->n_tile = n_tile;
   p->n_tiles = ceil_div(d.n_pad, n_tile);
   p->total_tiles = p->groups * p->m_tiles * p->n_tiles;
@@ -614,25 +728,32 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   while (cols < 2 * n_tile) cols *= 2;
   p->tmem_cols = cols;
   const int stage_bytes = kATileBytes + n_tile * 128;
-  int stages = (kSmemBudget - 1024 - kCtrlBytes) / stage_bytes;
+  int stages = (kSmemBudget - 1024 - kCtrlBytes - kStageOutBytes) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   PRN_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p->stages = stages;
   p->kb_per_tap = (d.c0 + d.c1) / 64;
   p->num_kb = d.ksize * d.ksize * p->kb_per_tap;
   p->dbg = nullptr;
+  // dense 16-bit output rows (row index == m) can go through the smem-staged TMA store
+  p->tma_store = (d.out16 != nullptr && d.out32 == nullptr && d.act != PRN_ACT_SIGMOID_AVG4 && p->groups == 1 &&
+                  p->out_img_rows == p->hw_out && (reinterpret_cast<uintptr_t>(d.out16) & 15) == 0 && d.ld_out16 % 8 == 0)
+                     ? 1 : 0;
+  p->lean_epi = (d.out16 != nullptr && d.out32 == nullptr && d.stats == nullptr &&
+                 (d.act == PRN_ACT_NONE || d.act == PRN_ACT_RELU) && n_tile % 32 == 0 && d.n_pad % 32 == 0) ? 1 : 0;
   p->idesc = umma_idesc(d.dtype == PRN_BF16 ? 1u : 0u, kTileM, static_cast<uint32_t>(n_tile));
   return PRN_OK;
 }
 
-template <typename T, bool kDCN>
-static int launch(const CUtensorMap& tm, const ConvKParams& p, int grid, size_t smem, cudaStream_t st) {
+template <typename T, bool kDCN, bool kFull>
+static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKParams& p, int grid, size_t smem,
+                  cudaStream_t st) {
   static bool configured = false;  // per instantiation
   if (!configured) {
-    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = true;
   }
-  conv_umma_kernel<T, kDCN><<<grid, kThreads, smem, st>>>(tm, p);
+  conv_umma_kernel<T, kDCN, kFull><<<grid, kThreads, smem, st>>>(tm, tmo, p);
   PRN_CUDA(cudaGetLastError());
   return PRN_OK;
 }
@@ -672,10 +793,20 @@ static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile), d.dtype);
   if (rc != PRN_OK) return rc;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  const size_t smem = 1024 + kCtrlBytes + static_cast<size_t>(p.stages) * (kATileBytes + p.n_tile * 128);
+  CUtensorMap tmo = tm;
+  if (p.tma_store) {
+    rc = encode_tmap_2d_sw128(&tmo, d.out16, static_cast<uint64_t>(p.m_group), static_cast<uint64_t>(d.n_pad), 32, d.dtype,
+                              static_cast<uint64_t>(d.ld_out16));
+    if (rc != PRN_OK) return rc;
+  }
+  const size_t smem = 1024 + kCtrlBytes + kStageOutBytes + static_cast<size_t>(p.stages) * (kATileBytes + p.n_tile * 128);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool dcn = d.dcn_offmask != nullptr;
-  if (d.dtype == PRN_BF16)
-    return dcn ? launch<__nv_bfloat16, true>(tm, p, grid, smem, st) : launch<__nv_bfloat16, false>(tm, p, grid, smem, st);
-  return dcn ? launch<__half, true>(tm, p, grid, smem, st) : launch<__half, false>(tm, p, grid, smem, st);
+  const bool full = !p.lean_epi;
+#define PRN_LAUNCH(T)                                                                               \
+  (dcn ? (full ? launch<T, true, true>(tm, tmo, p, grid, smem, st) : launch<T, true, false>(tm, tmo, p, grid, smem, st)) \
+       : (full ? launch<T, false, true>(tm, tmo, p, grid, smem, st) : launch<T, false, false>(tm, tmo, p, grid, smem, st)))
+  if (d.dtype == PRN_BF16) return PRN_LAUNCH(__nv_bfloat16);
+  return PRN_LAUNCH(__half);
+#undef PRN_LAUNCH
 }

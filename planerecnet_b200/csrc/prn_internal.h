@@ -22,8 +22,9 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 // 2D row-major [rows][cols] 16-bit matrix -> tensor map with box {64 cols, box_rows}, 128B swizzle.
+// pitch_elems: row pitch in elements (0 = cols).
 int encode_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         int dtype);
+                         int dtype, uint64_t pitch_elems = 0);
 
 int sm_count();
 

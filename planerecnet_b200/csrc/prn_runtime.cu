@@ -33,13 +33,14 @@ static EncodeTiledFn get_encode_tiled() {
 }
 
 int encode_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         int dtype) {
+                         int dtype, uint64_t pitch_elems) {
+  if (pitch_elems == 0) pitch_elems = cols;
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return set_error(PRN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 2) % 16 != 0)
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_elems * 2) % 16 != 0)
     return set_error(PRN_ERR_INVALID, "tensor map base/pitch must be 16-byte aligned");
   cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dtype == PRN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,

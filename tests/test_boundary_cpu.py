@@ -159,3 +159,24 @@ def test_init_weights_semantics(tmp_path):
     net2 = H.build_ours("PlaneRecNet_50_config", seed=5)
     net2.load_weights(str(tmp_path / "w.pth"))
     assert torch.equal(net2.fpn.fpn_convs[2].weight, net.fpn.fpn_convs[2].weight)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_dropin_shims_work_with_the_reference_config():
+    """with dropin/ ahead of the reference on sys.path, the reference's own data/config.py builds
+    our model (construction only; no GPU here)."""
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, '/root/reference']\n"
+        "import torch\n"
+        "from data.config import cfg, set_cfg\n"
+        "import models.backbone as mb\n"
+        "assert mb.__name__ == 'models.backbone' and 'planerecnet_b200' in mb.ResNetBackbone.__module__\n"
+        "set_cfg('PlaneRecNet_50_config')\n"
+        "from planerecnet import PlaneRecNet\n"
+        "net = PlaneRecNet(cfg)\n"
+        "assert len(net.state_dict()) == 520\n"
+        "from models.functions.nms import matrix_nms, point_nms\n"
+        "import models.functions.funcs as f; assert abs(f.bias_init_with_prob(0.01) + 4.59512) < 1e-4\n"
+        "print('ok')\n" % (os.path.join(ROOT, "dropin"), ROOT))
+    out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
