@@ -137,6 +137,23 @@ int prn_nhwc_to_nchw_f32(const void* src, int32_t src_is_f32, float* dst, int32_
 int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t hw, int32_t c, int32_t c_pad,
                          int32_t dtype, void* stream);
 
+/* ---- inference bookkeeping (planerecnet.py:106-107, 182-289; models/functions/nms.py:8-12) --------- */
+
+/* scores = point_nms(sigmoid(logits)): logits fp32 [B, total, ld] with rows level-major then (y,x) and the first
+ * nc columns valid; scores fp32 [B, total, nc].  grids_dev: int32[n_levels] grid sizes on the device. */
+int prn_point_nms_sigmoid(const float* logits, float* scores, int32_t batch, int32_t total, int32_t ld, int32_t nc,
+                          int32_t n_levels, const int32_t* grids_dev, void* stream);
+/* Per candidate row of seg fp32 [rows][pixels]: area = #(seg > thr), ssum = sum(seg where > thr)
+ * (planerecnet.py:216-232) and the 0/1 mask as 16-bit [rows][pixels] (operand of the matrix-NMS Gram matrix,
+ * nms.py:20-22). */
+int prn_mask_stats(const float* seg, void* mask16, float* area, float* ssum, int32_t rows, int32_t pixels, float thr,
+                   int32_t dtype, void* stream);
+/* masks[i] = bilinear(seg[sel[i]], (h_out, w_out), align_corners=False) > thr as bool [n, h_out, w_out], and the
+ * tight xyxy box of each mask accumulated with atomicMin/Max into int32 boxes [n,4] (caller initialises to
+ * {w_out, h_out, -1, -1}): planerecnet.py:272-286. */
+int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool, int32_t* boxes, int32_t n_inst, int32_t h,
+                          int32_t w, int32_t h_out, int32_t w_out, float thr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

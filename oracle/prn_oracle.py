@@ -307,25 +307,10 @@ def inference_single(seg_preds, cate_preds, kernel_preds, depth_pred, ori_size, 
     strides = strides[inds[:, 0]]
     N, I = kernel_preds.shape
     seg = F.conv2d(seg_preds, kernel_preds.view(N, I, 1, 1)).squeeze(0).sigmoid()
-    seg_masks = seg > p["mask_thr"]
-    sum_masks = seg_masks.sum((1, 2)).to(seg.dtype)
-    keep = sum_masks > strides
-    if keep.sum() == 0:
+    det = bookkeeping(seg, cate_scores, cate_labels, strides, p)
+    if det is None:
         return result
-    seg_masks, seg, sum_masks = seg_masks[keep], seg[keep], sum_masks[keep]
-    cate_scores, cate_labels = cate_scores[keep], cate_labels[keep]
-    seg_scores = (seg * seg_masks.to(seg.dtype)).sum((1, 2)) / sum_masks
-    cate_scores = cate_scores * seg_scores
-    order = torch.argsort(cate_scores, descending=True)[:p["nms_pre"]]
-    seg_masks, seg, sum_masks = seg_masks[order], seg[order], sum_masks[order]
-    cate_scores, cate_labels = cate_scores[order], cate_labels[order]
-    cate_scores = matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=p["sigma"], kernel=p["kernel"])
-    keep = cate_scores >= p["update_thr"]
-    if keep.sum() == 0:
-        return result
-    seg, cate_scores, cate_labels = seg[keep], cate_scores[keep], cate_labels[keep]
-    order = torch.argsort(cate_scores, descending=True)[:p["top_k"]]
-    seg, cate_scores, cate_labels = seg[order], cate_scores[order], cate_labels[order]
+    seg, cate_scores, cate_labels, _ = det
     masks = F.interpolate(seg.unsqueeze(0), size=ori_size, mode="bilinear", align_corners=False).squeeze(0) > p["mask_thr"]
     boxes = torch.zeros(masks.size(0), 4)
     for i in range(masks.size(0)):
@@ -333,6 +318,32 @@ def inference_single(seg_preds, cate_preds, kernel_preds, depth_pred, ori_size, 
         boxes[i] = torch.tensor([xs.min(), ys.min(), xs.max(), ys.max()]).float()
     result.update(pred_scores=cate_scores, pred_classes=cate_labels, pred_masks=masks, pred_boxes=boxes)
     return result
+
+
+def bookkeeping(seg, cate_scores, cate_labels, strides, p=INFER):
+    """planerecnet.py:216-269 given the candidates' sigmoid masks seg [N,h,w]: area filter, maskness rescoring,
+    sort/top-500, matrix-NMS, update threshold, sort/top-100.  Returns (seg, scores, labels, candidate index) of the
+    surviving detections in output order, or None."""
+    cand = torch.arange(seg.shape[0])
+    seg_masks = seg > p["mask_thr"]
+    sum_masks = seg_masks.sum((1, 2)).to(seg.dtype)
+    keep = sum_masks > strides
+    if keep.sum() == 0:
+        return None
+    seg_masks, seg, sum_masks = seg_masks[keep], seg[keep], sum_masks[keep]
+    cate_scores, cate_labels, cand = cate_scores[keep], cate_labels[keep], cand[keep]
+    seg_scores = (seg * seg_masks.to(seg.dtype)).sum((1, 2)) / sum_masks
+    cate_scores = cate_scores * seg_scores
+    order = torch.argsort(cate_scores, descending=True)[:p["nms_pre"]]
+    seg_masks, seg, sum_masks = seg_masks[order], seg[order], sum_masks[order]
+    cate_scores, cate_labels, cand = cate_scores[order], cate_labels[order], cand[order]
+    cate_scores = matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=p["sigma"], kernel=p["kernel"])
+    keep = cate_scores >= p["update_thr"]
+    if keep.sum() == 0:
+        return None
+    seg, cate_scores, cate_labels, cand = seg[keep], cate_scores[keep], cate_labels[keep], cand[keep]
+    order = torch.argsort(cate_scores, descending=True)[:p["top_k"]]
+    return seg[order], cate_scores[order], cate_labels[order], cand[order]
 
 
 def inference(mask_pred, cate_preds, kernel_preds, depth_pred, ori_size):

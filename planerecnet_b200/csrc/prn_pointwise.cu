@@ -40,17 +40,33 @@ __device__ __forceinline__ void store8(T* p, const float* f) {
 // ---------------------------------------------------------------- stem im2col (models/backbone.py:101,200)
 // x NCHW fp32 [B,3,H,W] -> A [B*Ho*Wo, 192] 16-bit, k = (ky*7 + kx)*3 + c for the 7x7/s2/p3 conv, zero
 // padded to 192 so the stem runs as a K=192 GEMM on the tensor cores.
+// One CTA = 64 consecutive output pixels of one output row.  Stage 1 copies the 3 x 7 x 133 fp32 input patch
+// they read into shared memory with coalesced row loads; stage 2 emits the [64][192] rows with 16-byte
+// stores that are contiguous per pixel (384 B), so both sides of the pass stream at full sector width.
+constexpr int kStemPx = 64;
+constexpr int kStemPatchW = 2 * kStemPx + 5;   // 133 input columns
 template <typename T>
-__global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W) {
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W) {
+  __shared__ float patch[3][7][kStemPatchW + 3];
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 24;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int kc = static_cast<int>(i % 24);
-    const long long m = i / 24;
-    const int wo = static_cast<int>(m % Wo);
-    const int ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+  const int strips = (Wo + kStemPx - 1) / kStemPx;
+  const int strip = blockIdx.x % strips;
+  const int ho = (blockIdx.x / strips) % Ho;
+  const int b = blockIdx.x / (strips * Ho);
+  const int wo0 = strip * kStemPx;
+  const int x0 = 2 * wo0 - 3, y0 = 2 * ho - 3;
+  for (int i = threadIdx.x; i < 21 * kStemPatchW; i += blockDim.x) {
+    const int col = i % kStemPatchW, rc = i / kStemPatchW;
+    const int ky = rc % 7, c = rc / 7;
+    const int yy = y0 + ky, xx = x0 + col;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(b) * 3 + c) * H + yy) * W + xx);
+    patch[c][ky][col] = v;
+  }
+  __syncthreads();
+  const int npx = min(kStemPx, Wo - wo0);
+  for (int i = threadIdx.x; i < npx * 24; i += blockDim.x) {
+    const int kc = i % 24, px = i / 24;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -58,12 +74,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ 
       float v = 0.f;
       if (k < 147) {
         const int c = k % 3, tap = k / 3;
-        const int ky = tap / 7, kx = tap % 7;
-        const int y = ho * 2 - 3 + ky, xx = wo * 2 - 3 + kx;
-        if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(b) * 3 + c) * H + y) * W + xx);
+        v = patch[c][tap / 7][2 * px + tap % 7];
       }
       f[j] = v;
     }
+    const long long m = (static_cast<long long>(b) * Ho + ho) * Wo + wo0 + px;
     store8(out + m * 192 + kc * 8, f);
   }
 }
@@ -375,10 +390,11 @@ extern "C" {
 int prn_stem_im2col(const float* x_nchw, void* out16, int32_t batch, int32_t h, int32_t w, int32_t dtype, void* stream) {
   PRN_REQUIRE(x_nchw && out16 && batch > 0 && h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, "stem_im2col: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long work = static_cast<long long>(batch) * (h / 2) * (w / 2) * 24;
+  const int strips = (w / 2 + kStemPx - 1) / kStemPx;
+  const int grid = batch * (h / 2) * strips;
   PRN_DISPATCH(dtype,
-               (stem_im2col_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(x_nchw, static_cast<__nv_bfloat16*>(out16), batch, h, w)),
-               (stem_im2col_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(x_nchw, static_cast<__half*>(out16), batch, h, w)));
+               (stem_im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x_nchw, static_cast<__nv_bfloat16*>(out16), batch, h, w)),
+               (stem_im2col_kernel<__half><<<grid, 256, 0, st>>>(x_nchw, static_cast<__half*>(out16), batch, h, w)));
   PRN_LAUNCH_CHECK();
 }
 

@@ -34,6 +34,7 @@ class Engine:
         self.launches = 0
         self._zero_pool = {}
         self._graphs = {}
+        self._net_tensors = {}
         self.profile = None         # list of (name, flops, start_event, end_event) when profiling
 
     # ------------------------------------------------------------------ small helpers
@@ -411,7 +412,13 @@ class Engine:
         graph's static buffers: consume them before the next call."""
         key = (id(net), tuple(x.shape), want_nchw)
         ent = self._graphs.get(key)
-        if ent is None or ent["gen"] != self._pack_gen:
+        # the graph bakes in pointers to the packed weights: any in-place parameter / buffer update (optimizer step,
+        # load_state_dict, BN statistics) bumps a tensor version and forces a re-pack + re-capture
+        tensors = self._net_tensors.get(id(net))
+        if tensors is None:
+            tensors = self._net_tensors[id(net)] = [t for t in list(net.parameters()) + list(net.buffers())]
+        wver = (sum(t._version for t in tensors), tensors[0].data_ptr())
+        if ent is None or ent["gen"] != self._pack_gen or ent["wver"] != wver:
             sx = torch.empty_like(x)
             sx.copy_(x)
             side = torch.cuda.Stream()
@@ -426,7 +433,7 @@ class Engine:
             n0 = self.launches
             with torch.cuda.graph(g):
                 st = self.forward_dense(net, sx, want_nchw)
-            ent = {"graph": g, "x": sx, "st": st, "gen": gen, "launches": self.launches - n0}
+            ent = {"graph": g, "x": sx, "st": st, "gen": self._pack_gen, "wver": wver, "launches": self.launches - n0}
             self._graphs[key] = ent
         ent["x"].copy_(x, non_blocking=True)
         ent["graph"].replay()

@@ -1,9 +1,14 @@
-"""Inference bookkeeping on top of the dense outputs (planerecnet.py:106-111, 155-289; nms.py:8-50).
+"""Inference bookkeeping on top of the dense outputs (planerecnet.py:106-111, 155-289; nms.py:8-50),
+batched over the images of a step with three host synchronisations per batch instead of ~8 per image.
 
-The per-candidate mask contraction (F.conv2d with the selected kernels, planerecnet.py:210-212) runs on
-the tensor-core conv kernel; index bookkeeping (thresholding, sorting, top-k, matrix-NMS on <= 500
-candidates) is expressed with torch device ops on the engine's outputs and keeps the reference's
-order of operations so that, given identical dense inputs, indices and counts are identical."""
+Dense / reduction work runs in libprn_b200 kernels: sigmoid + point-NMS (`prn_point_nms_sigmoid`), the
+per-candidate mask contraction and the matrix-NMS Gram matrix on the tensor-core conv kernel
+(`prn_conv2d_fwd`, per-image operands), mask area / maskness sums (`prn_mask_stats`), final bilinear
+upsampling + thresholding + boxes (`prn_upsample_mask_box`).  Index bookkeeping (compaction, sorting,
+the n x n decay algebra on <= 500 candidates) is expressed with torch device ops and follows the
+reference's order of operations, so identical dense inputs give identical indices and counts."""
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 
@@ -12,30 +17,38 @@ from . import ops
 
 
 def point_nms(heat, kernel=2):
-    """nms.py:8-12."""
+    """nms.py:8-12 (torch formulation, kept for callers of models.functions.nms)."""
     hmax = F.max_pool2d(heat, (kernel, kernel), stride=1, padding=1)
     keep = (hmax[:, :, :-1, :-1] == heat).float()
     return heat * keep
 
 
 def matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=2.0, kernel="gaussian"):
-    """nms.py:15-50 (seg_masks given as [n, pixels] float)."""
+    """nms.py:15-50 for one image (seg_masks given as [n, pixels] float)."""
     n = len(cate_labels)
     if n == 0:
         return []
     inter = torch.mm(seg_masks, seg_masks.t())
-    sx = sum_masks.expand(n, n)
-    iou = (inter / (sx + sx.t() - inter)).triu(diagonal=1)
-    lx = cate_labels.expand(n, n)
-    label = (lx == lx.t()).float().triu(diagonal=1)
-    comp, _ = (iou * label).max(0)
-    comp = comp.expand(n, n).t()
-    decay = iou * label
+    return _decay(inter[None], sum_masks[None], cate_labels[None], cate_scores[None],
+                  torch.ones(1, n, dtype=torch.bool, device=cate_scores.device), sigma, kernel)[0]
+
+
+def _decay(inter, areas, labels, scores, valid, sigma, kernel):
+    """Batched nms.py:24-48.  inter [B,n,n] mask intersections (sorted order), areas/labels/scores/valid [B,n]."""
+    n = inter.shape[-1]
+    sx = areas[:, None, :].expand(-1, n, n)                     # sum_masks_x[i][j] = area_j
+    pair = valid[:, :, None] & valid[:, None, :]
+    union = sx + sx.transpose(1, 2) - inter
+    iou = torch.where(pair, inter / union, torch.zeros_like(inter)).triu(diagonal=1)
+    label = ((labels[:, None, :] == labels[:, :, None]) & pair).float().triu(diagonal=1)
+    decay_iou = iou * label
+    comp = decay_iou.max(1).values                               # per column j: max over i
+    comp_m = comp[:, :, None].expand(-1, n, n)                   # [i][j] = comp[i]
     if kernel == "linear":
-        coef, _ = ((1 - decay) / (1 - comp)).min(0)
+        coef = ((1 - decay_iou) / (1 - comp_m)).min(1).values
     else:
-        coef, _ = (torch.exp(-1 * sigma * (decay ** 2)) / torch.exp(-1 * sigma * (comp ** 2))).min(0)
-    return cate_scores * coef
+        coef = (torch.exp(-1 * sigma * (decay_iou ** 2)) / torch.exp(-1 * sigma * (comp_m ** 2))).min(1).values
+    return scores * coef
 
 
 def _strides_table(net, device):
@@ -45,84 +58,139 @@ def _strides_table(net, device):
     return torch.tensor(t, device=device)
 
 
+def select(scores, seg_fn, strides_all, nc, p):
+    """Candidate selection + matrix-NMS for a batch (planerecnet.py:189-269).
+
+    scores: fp32 [B, total, nc] after point-NMS.  seg_fn(rows [B,n] long, n) -> (seg32 [B*n, P] fp32 sigmoid
+    masks, mask16 [B*n, P] 0/1, area [B*n], ssum [B*n], inter [B, n, n] fp32) for the candidates' kernel rows.
+    Returns per image (sel_rows into seg32, scores, labels) of the final detections (possibly empty) + seg32."""
+    B, total, _ = scores.shape
+    dev = scores.device
+    flat = scores.reshape(B, total * nc)
+    cand = flat > p["score_thr"]
+    counts = cand.sum(1)
+    n_max = int(counts.max().item())                              # host sync 1
+    empty = [(None, None, None)] * B
+    if n_max == 0:
+        return empty, None
+    n = ops.round_up(n_max, 16)
+    # stable compaction in reference order (row-major over [total, nc]): rank of every candidate within its image
+    rank = torch.cumsum(cand, 1) - 1
+    slot = torch.where(cand, rank, torch.full_like(rank, n))      # non-candidates -> overflow slot n
+    src = torch.arange(total * nc, device=dev).expand(B, -1)
+    idx = torch.full((B, n + 1), -1, dtype=torch.long, device=dev)
+    idx.scatter_(1, slot, src)
+    idx = idx[:, :n]                                              # [B, n] flat index or -1
+    valid = idx >= 0
+    idxc = idx.clamp(min=0)
+    rows = idxc // nc
+    labels = idxc % nc
+    sc = torch.where(valid, flat.gather(1, idxc), torch.zeros((), device=dev))
+    strides = strides_all[rows]
+    seg32, mask16, area, ssum, inter = seg_fn(rows, valid, n)
+    area = area.view(B, n)
+    ssum = ssum.view(B, n)
+    keep = valid & (area > strides)                               # planerecnet.py:219-220
+    sc = sc * (ssum / area)                                       # maskness (planerecnet.py:231-232)
+    key = torch.where(keep, sc, torch.full_like(sc, -1.0))
+    order = torch.argsort(key, dim=1, descending=True)
+    n_pre = min(n, p["nms_pre"])
+    order = order[:, :n_pre]
+    v1 = keep.gather(1, order)
+    s1 = key.gather(1, order)
+    a1 = area.gather(1, order)
+    l1 = labels.gather(1, order)
+    inter1 = inter.gather(1, order[:, :, None].expand(-1, -1, n)).gather(2, order[:, None, :].expand(-1, n_pre, -1))
+    s2 = _decay(inter1, a1, l1, s1, v1, p["sigma"], p["kernel"])  # nms.py
+    keep2 = v1 & (s2 >= p["update_thr"])
+    key2 = torch.where(keep2, s2, torch.full_like(s2, -1.0))
+    order2 = torch.argsort(key2, dim=1, descending=True)[:, :p["top_k"]]
+    fin_valid = keep2.gather(1, order2)
+    fin_score = key2.gather(1, order2)
+    fin_label = l1.gather(1, order2)
+    fin_slot = order.gather(1, order2)                            # slot in the candidate list
+    n_fin = fin_valid.sum(1).tolist()                             # host sync 2
+    out = []
+    base = torch.arange(B, device=dev)[:, None] * n
+    fin_rows = (base + fin_slot)
+    for b in range(B):
+        k = n_fin[b]
+        if k == 0:
+            out.append((None, None, None))
+        else:
+            out.append((fin_rows[b, :k], fin_score[b, :k], fin_label[b, :k]))
+    return out, seg32
+
+
 def inference(eng, net, st, x):
     """Returns list[dict] with the reference's keys in the reference's order (planerecnet.py:183)."""
     B, _, H, W = x.shape
+    dev = x.device
     inst = st["inst"]
     nc = net.num_classes
     total = inst["cate32"].shape[1]
-    # sigmoid + point-NMS per level on [B, nc, S, S] views of the category logits
-    scores = torch.empty(B, total, nc, device=x.device)
-    off = 0
-    for S in net.num_grids:
-        lg = inst["cate32"][:, off:off + S * S, :nc].reshape(B, S, S, nc).permute(0, 3, 1, 2)
-        scores[:, off:off + S * S] = point_nms(lg.sigmoid()).permute(0, 2, 3, 1).reshape(B, S * S, nc)
-        off += S * S
-    depth = st["depth32"][..., 0].unsqueeze(1)                         # [B,1,H/2,W/2]
-    strides_all = _strides_table(net, x.device)
+    lib = eng.lib
+    p = dict(score_thr=net.score_threshold, mask_thr=net.mask_threshold, update_thr=net.update_threshold,
+             nms_pre=net.max_before_nms, top_k=net.max_per_img, sigma=net.nms_sigma, kernel=net.nms_kernel)
+    if net.nms_type != "matrix":
+        raise NotImplementedError("nms_type %r (only 'matrix', the presets' default, is implemented)" % net.nms_type)
+
+    grids = eng._zero_pool.get(("grids", tuple(net.num_grids)))
+    if grids is None:
+        grids = torch.tensor(list(net.num_grids), dtype=torch.int32, device=dev)
+        eng._zero_pool[("grids", tuple(net.num_grids))] = grids
+        eng._zero_pool[("strides", tuple(net.num_grids))] = _strides_table(net, dev)
+    strides_all = eng._zero_pool[("strides", tuple(net.num_grids))]
+
+    scores = torch.empty(B, total, nc, device=dev)
+    eng._call(lib.prn_point_nms_sigmoid, C.c_void_p(inst["cate32"].data_ptr()), C.c_void_p(scores.data_ptr()), B, total,
+              inst["cate32"].shape[-1], nc, len(net.num_grids), C.c_void_p(grids.data_ptr()), eng._st())
+
     mask16 = st["mask16"]
     _, mh, mw, mc = mask16.shape
-    results = []
-    for b in range(B):
-        result = {"pred_masks": None, "pred_boxes": None, "pred_classes": None, "pred_scores": None, "pred_depth": None}
-        result["pred_depth"] = F.interpolate(depth[b:b + 1], size=(H, W), mode="bilinear", align_corners=False)
-        results.append(result)
-        cate = scores[b]
-        inds = cate > net.score_threshold
-        cate_scores = cate[inds]
-        if len(cate_scores) == 0:
-            continue
-        inds = inds.nonzero(as_tuple=False)
-        cate_labels = inds[:, 1]
-        sel = inds[:, 0]
-        strides = strides_all[sel]
-        n = sel.numel()
-        n_pad = ops.round_up(n, 16)
-        wsel = torch.zeros(n_pad, mc, dtype=eng.tdt, device=x.device)
-        wsel[:n] = inst["kern16"][b, sel]
-        seg = torch.empty(mh * mw, n_pad, dtype=torch.float32, device=x.device)
+    P = mh * mw
+
+    def seg_fn(rows, valid, n):
+        # per-image contraction sigmoid(K_sel . mask^T): rows of A = selected kernels, "weights" = mask pixels
+        wsel = inst["kern16"].gather(1, rows[:, :, None].expand(-1, -1, mc)) * valid[:, :, None].to(eng.tdt)
+        seg32 = torch.empty(B * n, P, device=dev)
         eng.launches += 1
-        ops.conv2d(mask16[b:b + 1], wsel, batch=1, h_in=mh, w_in=mw, ksize=1, act=L.ACT_SIGMOID, out32=seg,
-                   dtype=eng.dt)
-        seg = seg[:, :n].t().contiguous()                              # [n, mh*mw]
-        seg_masks = seg > net.mask_threshold
-        sum_masks = seg_masks.sum(1).float()
-        keep = sum_masks > strides
-        if keep.sum() == 0:
-            continue
-        seg_masks, seg, sum_masks = seg_masks[keep], seg[keep], sum_masks[keep]
-        cate_scores, cate_labels = cate_scores[keep], cate_labels[keep]
-        seg_scores = (seg * seg_masks.float()).sum(1) / sum_masks
-        cate_scores = cate_scores * seg_scores
-        sort_inds = torch.argsort(cate_scores, descending=True)
-        if len(sort_inds) > net.max_before_nms:
-            sort_inds = sort_inds[:net.max_before_nms]
-        seg_masks, seg, sum_masks = seg_masks[sort_inds], seg[sort_inds], sum_masks[sort_inds]
-        cate_scores, cate_labels = cate_scores[sort_inds], cate_labels[sort_inds]
-        if net.nms_type == "matrix":
-            cate_scores = matrix_nms(cate_labels, seg_masks.float(), sum_masks, cate_scores, sigma=net.nms_sigma,
-                                     kernel=net.nms_kernel)
-            keep = cate_scores >= net.update_threshold
-        else:
-            raise NotImplementedError("nms_type %r (only 'matrix', the presets' default, is implemented)" % net.nms_type)
-        if keep.sum() == 0:
-            continue
-        seg, cate_scores, cate_labels = seg[keep], cate_scores[keep], cate_labels[keep]
-        sort_inds = torch.argsort(cate_scores, descending=True)
-        if len(sort_inds) > net.max_per_img:
-            sort_inds = sort_inds[:net.max_per_img]
-        seg, cate_scores, cate_labels = seg[sort_inds], cate_scores[sort_inds], cate_labels[sort_inds]
-        masks = F.interpolate(seg.reshape(1, -1, mh, mw), size=(H, W), mode="bilinear", align_corners=False).squeeze(0)
-        masks = masks > net.mask_threshold
-        # bbox from mask without the per-instance python loop of planerecnet.py:282-286
-        ys = masks.any(2)
-        xs = masks.any(1)
-        ar_y = torch.arange(H, device=x.device)
-        ar_x = torch.arange(W, device=x.device)
-        y0 = torch.where(ys, ar_y, H).min(1).values
-        y1 = torch.where(ys, ar_y, -1).max(1).values
-        x0 = torch.where(xs, ar_x, W).min(1).values
-        x1 = torch.where(xs, ar_x, -1).max(1).values
-        boxes = torch.stack([x0, y0, x1, y1], 1).float()
-        result.update(pred_scores=cate_scores, pred_classes=cate_labels, pred_masks=masks, pred_boxes=boxes)
+        ops.conv2d(wsel, mask16.reshape(B * P, mc), batch=B, h_in=n, w_in=1, ksize=1, act=L.ACT_SIGMOID, out32=seg32,
+                   ld_out32=P, n_pad=P, w_group_rows=P, dtype=eng.dt)
+        m16 = torch.empty(B * n, P, dtype=eng.tdt, device=dev)
+        area = torch.empty(B * n, device=dev)
+        ssum = torch.empty(B * n, device=dev)
+        eng._call(lib.prn_mask_stats, C.c_void_p(seg32.data_ptr()), C.c_void_p(m16.data_ptr()), C.c_void_p(area.data_ptr()),
+                  C.c_void_p(ssum.data_ptr()), B * n, P, C.c_float(p["mask_thr"]), eng.dt, eng._st())
+        # Gram matrix of the binary masks (nms.py:20-22): exact in fp32 (integer counts < 2^24)
+        inter = torch.empty(B, n, n, device=dev)
+        eng.launches += 1
+        ops.conv2d(m16.view(B, n, 1, P), m16, batch=B, h_in=n, w_in=1, ksize=1, act=L.ACT_NONE, out32=inter, ld_out32=n,
+                   n_pad=n, w_group_rows=n, dtype=eng.dt)
+        return seg32, m16, area, ssum, inter
+
+    dets, seg32 = select(scores, seg_fn, strides_all, nc, p)
+
+    depth = st["depth32"][..., 0].unsqueeze(1)                         # [B,1,H/2,W/2]
+    depth_up = F.interpolate(depth, size=(H, W), mode="bilinear", align_corners=False)
+    sel_all = [d[0] for d in dets if d[0] is not None]
+    masks_all = boxes_all = None
+    if sel_all:
+        sel = torch.cat(sel_all).to(torch.int32)
+        nf = sel.numel()
+        masks_all = torch.empty(nf, H, W, dtype=torch.bool, device=dev)
+        boxes_i = torch.tensor([W, H, -1, -1], dtype=torch.int32, device=dev).repeat(nf, 1)
+        eng._call(lib.prn_upsample_mask_box, C.c_void_p(seg32.data_ptr()), C.c_void_p(sel.data_ptr()),
+                  C.c_void_p(masks_all.data_ptr()), C.c_void_p(boxes_i.data_ptr()), nf, mh, mw, H, W, C.c_float(p["mask_thr"]),
+                  eng._st())
+        boxes_all = boxes_i.float()
+    results, off = [], 0
+    for b in range(B):
+        r = {"pred_masks": None, "pred_boxes": None, "pred_classes": None, "pred_scores": None, "pred_depth": depth_up[b:b + 1]}
+        rows, sc, lab = dets[b]
+        if rows is not None:
+            k = rows.numel()
+            r.update(pred_masks=masks_all[off:off + k], pred_boxes=boxes_all[off:off + k], pred_classes=lab, pred_scores=sc)
+            off += k
+        results.append(r)
     return results

@@ -96,7 +96,7 @@ def test_graph_replay_equals_eager_and_tracks_weight_updates(cuda_lib):
     assert not same(b[1], a[1])
     # an in-place weight update must invalidate the packed weights and the captured graph
     with torch.no_grad():
-        net.depth_decoder.latlayer1.weight.mul_(1.5)
+        net.depth_decoder.depth_pred[1].bias.add_(1.0)
         g3 = eng.forward_dense_graph(net, xc)["outputs"][3].clone()
         e3 = eng.forward_dense(net, xc)["outputs"][3]
     assert same(g3, e3) and not same(g3, a[1])
