@@ -159,39 +159,54 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
     return;
   }
   if (d.stats != nullptr && d.stats_cg > 0) {
-    // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators)
+    // GroupNorm partial sums of the pre-normalisation conv output (fp32 accumulators).  Per 16 columns every
+    // lane holds 4 (sum, sumsq) pairs over column quads; pairs are merged for 8/16-channel groups.  When the whole
+    // warp belongs to one image the 8 values are reduce-scattered over the lanes with a butterfly (8+4+2+1
+    // shuffles + 2 for the replicated pair instead of 8 x 5), and 8 lanes issue one atomic each.
     const int cg = d.stats_cg;
     const int G = d.n_pad / cg;
 #pragma unroll
     for (int hf = 0; hf < W / 16; ++hf) {
       const float* xx = x + 16 * hf;
-      float q1[4], q2[4];  // sums over quads of columns (static indexing keeps x[] in registers)
+      float v[8];   // v[2*qd] = sum, v[2*qd+1] = sumsq of quad qd
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) {
-        q1[qd] = (xx[4 * qd] + xx[4 * qd + 1]) + (xx[4 * qd + 2] + xx[4 * qd + 3]);
-        q2[qd] = (xx[4 * qd] * xx[4 * qd] + xx[4 * qd + 1] * xx[4 * qd + 1]) +
-                 (xx[4 * qd + 2] * xx[4 * qd + 2] + xx[4 * qd + 3] * xx[4 * qd + 3]);
+        v[2 * qd] = (xx[4 * qd] + xx[4 * qd + 1]) + (xx[4 * qd + 2] + xx[4 * qd + 3]);
+        v[2 * qd + 1] = (xx[4 * qd] * xx[4 * qd] + xx[4 * qd + 1] * xx[4 * qd + 1]) +
+                        (xx[4 * qd + 2] * xx[4 * qd + 2] + xx[4 * qd + 3] * xx[4 * qd + 3]);
       }
-      if (cg >= 8) { q1[0] += q1[1]; q2[0] += q2[1]; q1[2] += q1[3]; q2[2] += q2[3]; }
-      if (cg == 16) { q1[0] += q1[2]; q2[0] += q2[2]; }
+      const int colq = col0 + 16 * hf;
+      if (img_uniform) {
+        // reduce-scatter: after the 3 halving steps lane bits (4,3,2) select the value index; bits (1,0) replicate
+        const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0, h2 = (lane & 4) != 0;
+        float w4[4], w2[2], w1;
 #pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {
-        if ((qd * 4) % cg != 0) continue;
-        float s1 = q1[qd], s2 = q2[qd];
-        const int gi = (col0 + 16 * hf + qd * 4) / cg;
-        if (img_uniform) {
+        for (int i = 0; i < 4; ++i) {
+          const float keep = h4 ? v[4 + i] : v[i], send = h4 ? v[i] : v[4 + i];
+          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          }
-          if (lane == 0) {
-            atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
-            atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
-          }
-        } else if (valid) {
-          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, s1);
-          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, s2);
+        for (int i = 0; i < 2; ++i) {
+          const float keep = h3 ? w4[2 + i] : w4[i], send = h3 ? w4[i] : w4[2 + i];
+          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+          const float keep = h2 ? w2[1] : w2[0], send = h2 ? w2[0] : w2[1];
+          w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+        if ((lane & 3) == 0) {
+          const int vi = (h4 ? 4 : 0) + (h3 ? 2 : 0) + (h2 ? 1 : 0);     // value index 0..7 = quad * 2 + {sum, sumsq}
+          const int gi = (colq + (vi >> 1) * 4) / cg;
+          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + (vi & 1), w1);
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int gi = (colq + qd * 4) / cg;
+          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2, v[2 * qd]);
+          atomicAdd(d.stats + (static_cast<size_t>(img) * G + gi) * 2 + 1, v[2 * qd + 1]);
         }
       }
     }
