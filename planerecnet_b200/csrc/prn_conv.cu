@@ -26,12 +26,14 @@ namespace prn {
 
 constexpr int kTileM = 128;
 constexpr int kATileBytes = kTileM * 128;  // 128 rows x 64 16-bit elements
-constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 4;
-constexpr int kThreads = 32 * (kEpiWarps + kProdWarps + 2);
+// 16 warps = 4 warpgroups: WG0 epilogue A | WG1 epilogue B (plain conv) or A-producer B (deformable) |
+// WG2 A-producer A | WG3 warp 12 = TMA weight producer, warp 13 = MMA issuer + TMEM owner, 14-15 idle.
+// Registers are re-balanced per warpgroup with setmaxnreg (128/thread at launch).
+constexpr int kThreads = 512;
+constexpr int kEpiWarps = 4;   // warps per epilogue group (one per TMEM lane quarter)
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kStageOutBytes = kEpiWarps * 8192;   // per warp: two 32-row x 128 B staging tiles for TMA stores
+constexpr int kStageOutBytes = 8 * 4096;   // per epilogue warp: one 32-row x 128 B staging tile for TMA stores
 constexpr int kCtrlBytes = 2048;   // mbarriers + TMEM slot (first 256 B), bias staging for the epilogue (+1024, 1 KB)
 
 struct ConvKParams {
@@ -268,10 +270,18 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
   }
 }
 
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <typename T, bool kDCN, bool kFull>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ ConvKParams p) {
+  constexpr int kEpiGroups = kDCN ? 1 : 2;              // epilogue warpgroups
+  constexpr int kProdWarps = kDCN ? 8 : 4;              // A-producer warps
+  constexpr int kRows = kDCN ? 4 : 8;                   // A rows per producer thread
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -284,16 +294,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const uint32_t bar_tempty = base + 144;     // [2]
   const uint32_t tmem_slot = base + 160;
   float* bias_s = reinterpret_cast<float*>(base_ptr + 1024);   // [256]
-  const uint32_t stg_base = base + kCtrlBytes;                  // [kEpiWarps][2] x 4 KB, 1024-aligned
+  const uint32_t stg_base = base + kCtrlBytes;                  // [8 warps] x 4 KB, 1024-aligned
   const uint32_t a_base = stg_base + kStageOutBytes;
   const uint32_t b_stage_bytes = static_cast<uint32_t>(p.n_tile) * 128u;
   const uint32_t b_base = a_base + static_cast<uint32_t>(p.stages) * kATileBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
   const PrnConv& d = p.d;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
     if (p.tma_store) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
@@ -302,11 +313,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, kEpiWarps * 32);
+      mbar_init(bar_tempty + 8 * a, kEpiGroups * kEpiWarps * 32);
     }
     mbar_fence_init();
   }
-  if (warp == 9) {
+  if (warp == 13) {
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     tmem_relinquish();
   }
@@ -315,9 +326,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
 
-  if (warp >= kEpiWarps && warp < kEpiWarps + kProdWarps) {
+  const bool is_prod = wg == 2 || (kDCN && wg == 1);
+  const bool is_epi = wg == 0 || (!kDCN && wg == 1);
+
+  if (is_prod) {
     // =========================================================== A producer
-    const int pw = warp - kEpiWarps;
+    if constexpr (kDCN) reg_inc<144>(); else reg_dec<104>();
+    const int pw = kDCN ? ((wg == 2 ? 0 : 4) + (warp & 3)) : (warp & 3);
     const int sub = lane >> 3;    // row within a group of 4
     const int chunk = lane & 7;   // 16-byte chunk (8 channels) within the 128-byte row
     const int ups_shift = d.upsample == 2 ? 1 : 0;
@@ -325,12 +340,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     int s = 0;
     uint32_t ph = 0;
     uint32_t it = 0;
-    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == kEpiWarps * 32;
+    const bool prof = p.dbg != nullptr && blockIdx.x == 0 && warp == 8 && lane == 0;
     long long w_empty = 0;
-    uint32_t row_off[8];   // swizzled position of this thread's 16-byte chunk in each of its 8 rows of an A stage
+    uint32_t row_off[kRows];   // swizzled position of this thread's 16-byte chunk in each of its rows of an A stage
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = pw * 32 + i * 4 + sub;
+    for (int i = 0; i < kRows; ++i) {
+      const int r = pw * (4 * kRows) + i * 4 + sub;
       row_off[i] = static_cast<uint32_t>(r * 128 + ((chunk ^ (r & 7)) << 4));
     }
     const long long t_role0 = prof ? clock64() : 0;
@@ -338,12 +353,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const int rest = tile / p.n_tiles;
       const int mt = rest % p.m_tiles;
       const int g = rest / p.m_tiles;
-      int img_pix[8], hy[8], wx[8];
-      int m_glob[8];
+      int img_pix[kRows], hy[kRows], wx[kRows];
+      int m_glob[kRows];
       uint32_t valid = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = pw * 32 + i * 4 + sub;
+      for (int i = 0; i < kRows; ++i) {
+        const int r = pw * (4 * kRows) + i * 4 + sub;
         const int m = mt * kTileM + r;
         const bool v = m < p.m_group;
         const int mm = v ? m : 0;
@@ -362,12 +377,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       for (int tap = 0; tap < taps; ++tap) {
         if (++kx == d.ksize) { kx = 0; ++ky; }
         if constexpr (!kDCN) {
-          // per tap: byte offset of every row's source pixel (0 when the tap falls outside: the address stays
-          // valid and the copy is issued with src-size 0 = zero fill)
-          uint32_t poff[8];
+          // per tap: pixel index of every row's source (0 when the tap falls outside: the address stays valid
+          // and the copy is issued with src-size 0 = zero fill)
+          uint32_t poff[kRows];
           uint32_t ok = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < kRows; ++i) {
             int y = hy[i] + ky, x = wx[i] + kx;
             bool in = (valid >> i) & 1u;
             if (d.pad_mode == PRN_PAD_REFLECT) {
@@ -390,7 +405,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kRows; ++i) {
               cp_async16(a_stage + row_off[i], srcb + poff[i] * pitch, ((ok >> i) & 1u) ? 16u : 0u);   // < 4 GiB (host-checked)
             }
             // hardware arrives on the stage's barrier when these copies have landed: the thread never waits
@@ -403,63 +418,62 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           // ---- modulated deformable sampling (models/dcn.py:59-66, torchvision deform_conv2d):
           //      value = mask * bilinear(x, ho*s - pad + ky + dy, wo*s - pad + kx + dx), zero outside
           //      (-1, H) x (-1, W); corners outside the image contribute 0 (weight 0, address clamped).
+          //      Coefficients are per (row, tap): computed once and reused for every 64-channel block.
           const uint8_t* src = static_cast<const uint8_t*>(d.src0);
-          const int cs = p.ld0;
+          const uint32_t pitch = static_cast<uint32_t>(p.ld0) * 2u;
           const float fh = static_cast<float>(d.h_in), fw = static_cast<float>(d.w_in);
+          float wg4[kRows][4];
+          uint32_t po[kRows][4];
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) {
+            const float* om = d.dcn_offmask + static_cast<size_t>(m_glob[i]) * 32;
+            const float py = static_cast<float>(hy[i] + ky) + __ldg(om + 2 * tap);
+            const float px = static_cast<float>(wx[i] + kx) + __ldg(om + 2 * tap + 1);
+            const float mk = __ldg(om + 18 + tap);
+            const bool inside = ((valid >> i) & 1u) && py > -1.f && py < fh && px > -1.f && px < fw;
+            const float fy = floorf(py), fx = floorf(px);
+            const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+            const float ly = py - fy, lx = px - fx;
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+              for (int cx = 0; cx < 2; ++cx) {
+                const int yy = y0 + cy, xx = x0 + cx;
+                const bool okc = inside && yy >= 0 && yy < d.h_in && xx >= 0 && xx < d.w_in;
+                wg4[i][cy * 2 + cx] = okc ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) * mk : 0.f;
+                const int yc = min(max(yy, 0), d.h_in - 1), xc = min(max(xx, 0), d.w_in - 1);
+                po[i][cy * 2 + cx] = static_cast<uint32_t>(img_pix[i] + yc * d.w_in + xc) * pitch;
+              }
+            }
+          }
           for (int cc = 0; cc < p.kb_per_tap; ++cc) {
-            const int coff = cc * 64 + chunk * 8;
+            const uint8_t* srcb = src + static_cast<size_t>(cc * 64 + chunk * 8) * 2;
+            uint4 q[kRows][4];
+#pragma unroll
+            for (int i = 0; i < kRows; ++i)
+#pragma unroll
+              for (int cnr = 0; cnr < 4; ++cnr) q[i][cnr] = __ldg(reinterpret_cast<const uint4*>(srcb + po[i][cnr]));
             mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {   // two batches of 4 rows: 16 independent 16-byte loads in flight
-              float wg[4][4];
-              uint4 q[4][4];
+            for (int i = 0; i < kRows; ++i) {
+              float acc[8];
 #pragma unroll
-              for (int r4 = 0; r4 < 4; ++r4) {
-                const int i = hb * 4 + r4;
-                const float* om = d.dcn_offmask + static_cast<size_t>(m_glob[i]) * 32;
-                const float py = static_cast<float>(hy[i] + ky) + __ldg(om + 2 * tap);
-                const float px = static_cast<float>(wx[i] + kx) + __ldg(om + 2 * tap + 1);
-                const float mk = __ldg(om + 18 + tap);
-                const bool inside = ((valid >> i) & 1u) && py > -1.f && py < fh && px > -1.f && px < fw;
-                const float fy = floorf(py), fx = floorf(px);
-                const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-                const float ly = py - fy, lx = px - fx;
+              for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
-                for (int cy = 0; cy < 2; ++cy) {
+              for (int cnr = 0; cnr < 4; ++cnr) {
+                const uint32_t w4[4] = {q[i][cnr].x, q[i][cnr].y, q[i][cnr].z, q[i][cnr].w};
 #pragma unroll
-                  for (int cx = 0; cx < 2; ++cx) {
-                    const int yy = y0 + cy, xx = x0 + cx;
-                    const bool okc = inside && yy >= 0 && yy < d.h_in && xx >= 0 && xx < d.w_in;
-                    wg[r4][cy * 2 + cx] = okc ? (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) * mk : 0.f;
-                    const int yc = min(max(yy, 0), d.h_in - 1), xc = min(max(xx, 0), d.w_in - 1);
-                    q[r4][cy * 2 + cx] = __ldg(reinterpret_cast<const uint4*>(
-                        src + (static_cast<size_t>(img_pix[i] + yc * d.w_in + xc) * cs + coff) * 2));
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = Pack2<T>::unpack(w4[j]);
+                  acc[2 * j] = fmaf(wg4[i][cnr], f.x, acc[2 * j]);
+                  acc[2 * j + 1] = fmaf(wg4[i][cnr], f.y, acc[2 * j + 1]);
                 }
               }
-#pragma unroll
-              for (int r4 = 0; r4 < 4; ++r4) {
-                const int r = pw * 32 + (hb * 4 + r4) * 4 + sub;
-                const uint32_t dst = a_stage + r * 128 + ((chunk ^ (r & 7)) << 4);
-                float acc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-                for (int cnr = 0; cnr < 4; ++cnr) {
-                  const uint32_t w4[4] = {q[r4][cnr].x, q[r4][cnr].y, q[r4][cnr].z, q[r4][cnr].w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = Pack2<T>::unpack(w4[j]);
-                    acc[2 * j] = fmaf(wg[r4][cnr], f.x, acc[2 * j]);
-                    acc[2 * j + 1] = fmaf(wg[r4][cnr], f.y, acc[2 * j + 1]);
-                  }
-                }
-                const uint32_t o0 = Pack2<T>::pack(acc[0], acc[1]), o1 = Pack2<T>::pack(acc[2], acc[3]);
-                const uint32_t o2 = Pack2<T>::pack(acc[4], acc[5]), o3 = Pack2<T>::pack(acc[6], acc[7]);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                             : "memory");
-              }
+              const uint32_t o0 = Pack2<T>::pack(acc[0], acc[1]), o1 = Pack2<T>::pack(acc[2], acc[3]);
+              const uint32_t o2 = Pack2<T>::pack(acc[4], acc[5]), o3 = Pack2<T>::pack(acc[6], acc[7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + row_off[i]), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                           : "memory");
             }
             fence_proxy_async_smem();     // generic-proxy st.shared -> visible to the tensor core (async proxy)
             mbar_arrive(bar_full + 8 * s);
@@ -470,61 +484,66 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       }
     }
     if (prof) { p.dbg[0] = clock64() - t_role0; p.dbg[1] = w_empty; p.dbg[2] = 0; p.dbg[3] = it; }
-  } else if (warp == 8) {
-    // =========================================================== B producer (TMA)
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        const int g = (tile / p.n_tiles) / p.m_tiles;
-        const int row0 = g * d.w_group_rows + nt * p.n_tile;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          mbar_arrive_expect_tx(bar_full + 8 * s, b_stage_bytes);
-          tma_load_2d(b_base + static_cast<uint32_t>(s) * b_stage_bytes, &tmap_w, bar_full + 8 * s, kb * 64, row0);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      const bool prof = p.dbg != nullptr && blockIdx.x == 0;
-      long long w_full = 0, w_tempty = 0;
-      const long long t_role0 = prof ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1u, prof, w_tempty);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait_acc(bar_full + 8 * s, ph, prof, w_full);
-          fence_proxy_async_smem();   // cp.async-written operand tile -> async proxy (belt and braces)
-          tc_fence_after();
-          const uint32_t a_addr = a_base + static_cast<uint32_t>(s) * kATileBytes;
-          const uint32_t b_addr = b_base + static_cast<uint32_t>(s) * b_stage_bytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+  } else if (wg == 3) {
+    reg_dec<40>();
+    if (warp == 12) {
+      // =========================================================== B producer (TMA)
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          const int nt = tile % p.n_tiles;
+          const int g = (tile / p.n_tiles) / p.m_tiles;
+          const int row0 = g * d.w_group_rows + nt * p.n_tile;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_arrive_expect_tx(bar_full + 8 * s, b_stage_bytes);
+            tma_load_2d(b_base + static_cast<uint32_t>(s) * b_stage_bytes, &tmap_w, bar_full + 8 * s, kb * 64, row0);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
-          umma_commit(bar_empty + 8 * s);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        umma_commit(bar_tfull + 8 * acc);
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1u;
       }
-      if (prof) { p.dbg[4] = clock64() - t_role0; p.dbg[5] = w_full; p.dbg[6] = w_tempty; }
+    } else if (warp == 13) {
+      // =========================================================== MMA issuer
+      if (lane == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        const bool prof = p.dbg != nullptr && blockIdx.x == 0;
+        long long w_full = 0, w_tempty = 0;
+        const long long t_role0 = prof ? clock64() : 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1u, prof, w_tempty);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait_acc(bar_full + 8 * s, ph, prof, w_full);
+            fence_proxy_async_smem();   // cp.async-written operand tile -> async proxy (belt and braces)
+            tc_fence_after();
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(s) * kATileBytes;
+            const uint32_t b_addr = b_base + static_cast<uint32_t>(s) * b_stage_bytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_empty + 8 * s);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+          umma_commit(bar_tfull + 8 * acc);
+          acc ^= 1;
+          if (acc == 0) acc_ph ^= 1u;
+        }
+        if (prof) { p.dbg[4] = clock64() - t_role0; p.dbg[5] = w_full; p.dbg[6] = w_tempty; }
+      }
     }
-  } else {
-    // =========================================================== epilogue (warps 0-3)
-    const int q = warp;  // TMEM lane quarter
-    const int etid = threadIdx.x;   // 0..127
+  } else if (is_epi) {
+    // =========================================================== epilogue (WG0, and WG1 for plain convs)
+    if constexpr (kDCN) reg_inc<168>(); else reg_inc<184>();
+    const int q = warp & 3;         // TMEM lane quarter
+    const int ge = wg;              // epilogue group: owns the 64-column groups with index % kEpiGroups == ge
+    const int etid = threadIdx.x;   // 0 .. kEpiGroups*128-1
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool avg4 = d.act == PRN_ACT_SIGMOID_AVG4;
@@ -533,7 +552,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     long long w_tfull = 0;
     const long long t_role0 = prof ? clock64() : 0;
     int bias_n0 = -1;
-    uint32_t sgrp = 0;   // running count of 64-column groups this warp has staged (selects the staging tile)
+    const uint32_t stg_tile = stg_base + static_cast<uint32_t>(warp) * 4096u;   // warps 0-7
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
@@ -557,34 +576,41 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
       // bias of this tile's columns -> shared memory (overlaps the tile's MMAs); reloaded only when n0 changes
       if (d.bias != nullptr && n0 != bias_n0) {
-        named_bar_sync(1, kEpiWarps * 32);          // everyone is done with the previous tile's values
-        for (int i = etid; i < n_valid; i += kEpiWarps * 32) bias_s[i] = __ldg(d.bias + n0 + i);
-        named_bar_sync(1, kEpiWarps * 32);
+        named_bar_sync(1, kEpiGroups * kEpiWarps * 32);          // everyone is done with the previous tile's values
+        for (int i = etid; i < n_valid; i += kEpiGroups * kEpiWarps * 32) bias_s[i] = __ldg(d.bias + n0 + i);
+        named_bar_sync(1, kEpiGroups * kEpiWarps * 32);
         bias_n0 = n0;
       }
 
       mbar_wait_acc(bar_tfull + 8 * acc, acc_ph, prof, w_tfull);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * p.n_tile);
+      const int row0_out = mt * kTileM + q * 32;          // first output row of this warp's sub-tile
 
-      // accumulator -> registers, software pipelined: the tcgen05.ld and the residual loads of chunk i+1 are in
-      // flight while chunk i is processed.  tcgen05.ld is .sync.aligned: lanes diverged by per-row predicates
-      // must reconverge (__syncwarp) before each one.
+      // accumulator -> registers, software pipelined over this group's column chunks: the tcgen05.ld and the
+      // residual loads of the next chunk are in flight while the current one is processed.  tcgen05.ld is
+      // .sync.aligned: lanes diverged by per-row predicates must reconverge (__syncwarp) before each one.
       const int n32 = n_valid >> 5;
-      const bool tail16 = (n_valid & 16) != 0;
+      const int ntot = n32 + ((kFull && (n_valid & 16)) ? 1 : 0);       // 32-wide chunks (+ one 16-wide tail)
+      auto next_of = [&](int c) {
+        ++c;
+        while (c < ntot && ((c >> 1) % kEpiGroups) != ge) ++c;
+        return c;
+      };
+      int ci = (0 % kEpiGroups) == ge ? 0 : next_of(0);
       uint32_t vb[32];
       uint4 rb[4];
       __syncwarp();
-      if (n32 > 0) {
-        tmem_ld_x32(t_row, vb);
-        load_res<32>(rb, res_row, has_res && valid);
-      } else {
-        tmem_ld_x16(t_row, vb);
-        load_res<16>(rb, res_row, has_res && valid);
+      if (ci < ntot) {
+        if (ci < n32) {
+          tmem_ld_x32(t_row + ci * 32, vb);
+          load_res<32>(rb, res_row + ci * 32, has_res && valid);
+        } else {
+          tmem_ld_x16(t_row + ci * 32, vb);
+          load_res<16>(rb, res_row + ci * 32, has_res && valid);
+        }
       }
-      const uint32_t stg_warp = stg_base + static_cast<uint32_t>(q) * 8192u;
-      const int row0_out = mt * kTileM + q * 32;          // first output row of this warp's sub-tile
-      for (int ci = 0; ci < n32; ++ci) {
+      while (ci < ntot) {
         tmem_ld_wait();
         tmem_ld_publish16(vb);
         tmem_ld_publish16(vb + 16);
@@ -594,55 +620,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vb[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) rc[j] = rb[j];
-        const int cn = (ci + 1) * 32;
+        const int cn = next_of(ci);
         __syncwarp();
-        if (ci + 1 < n32) {
-          tmem_ld_x32(t_row + cn, vb);
-          load_res<32>(rb, res_row + cn, has_res && valid);
-        } else if (tail16) {
-          tmem_ld_x16(t_row + cn, vb);
-          load_res<16>(rb, res_row + cn, has_res && valid);
+        if (cn < ntot) {
+          if (cn < n32) {
+            tmem_ld_x32(t_row + cn * 32, vb);
+            load_res<32>(rb, res_row + cn * 32, has_res && valid);
+          } else {
+            tmem_ld_x16(t_row + cn * 32, vb);
+            load_res<16>(rb, res_row + cn * 32, has_res && valid);
+          }
         }
-        const uint32_t stg_tile = stg_warp + (sgrp & 1u) * 4096u;
         if (p.tma_store && (ci & 1) == 0) {
-          // this staging tile was last used two groups ago: that TMA store must have finished reading it
-          if (lane == 0) bulk_wait_read<1>();
+          // the staging tile is about to be overwritten: its previous TMA store must have finished reading it
+          if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
         }
-        epi_chunk<T, 32, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
-                         img, lane, orow, p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u, (ci & 1) * 4);
-        if (p.tma_store && ((ci & 1) == 1 || (ci + 1 == n32 && !tail16))) {
+        const uint32_t srow = p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u;
+        if (!kFull || ci < n32)
+          epi_chunk<T, 32, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+                                  img, lane, orow, srow, (ci & 1) * 4);
+        else
+          epi_chunk<T, 16, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+                                  img, lane, orow, srow, (ci & 1) * 4);
+        if (p.tma_store && ((ci & 1) == 1 || ci + 1 == ntot)) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmap_out, stg_tile, n0 + (ci >> 1) * 64, row0_out);
             bulk_commit();
           }
-          ++sgrp;
         }
-      }
-      if (kFull && tail16) {
-        tmem_ld_wait();
-        tmem_ld_publish16(vb);
-        float x[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(vb[j]);
-        const uint32_t stg_tile = stg_warp + (sgrp & 1u) * 4096u;
-        if (p.tma_store && (n32 & 1) == 0) {
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-        }
-        epi_chunk<T, 16, kFull>(p, x, rb, has_res, d.bias ? bias_s + n32 * 32 : nullptr, n0 + n32 * 32, valid, img_uniform,
-                         img, lane, orow, p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u, (n32 & 1) * 4);
-        if (p.tma_store) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmap_out, stg_tile, n0 + (n32 >> 1) * 64, row0_out);
-            bulk_commit();
-          }
-          ++sgrp;
-        }
+        ci = cn;
       }
       tc_fence_before();
       mbar_arrive(bar_tempty + 8 * acc);
@@ -656,7 +665,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 9) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == 13) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
 // ------------------------------------------------------------------------------------------------ host
