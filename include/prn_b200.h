@@ -137,6 +137,11 @@ int prn_nhwc_to_nchw_f32(const void* src, int32_t src_is_f32, float* dst, int32_
 int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t hw, int32_t c, int32_t c_pad,
                          int32_t dtype, void* stream);
 
+/* 3x3 reflect-padded conv to a single output channel (+bias, optional softplus), fp32 output [B,H,W]: the depth
+ * head nn.Sequential(ReflectionPad2d(1), Conv2d(64,1,3), Softplus) at planerecnet.py:570-573.  weight9c: fp32 [9][C]. */
+int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, float bias, float* out, int32_t batch, int32_t h,
+                            int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream);
+
 /* ---- inference bookkeeping (planerecnet.py:106-107, 182-289; models/functions/nms.py:8-12) --------- */
 
 /* scores = point_nms(sigmoid(logits)): logits fp32 [B, total, ld] with rows level-major then (y,x) and the first

@@ -72,7 +72,7 @@ EXPORTS = [
     "prn_stem_im2col", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
     "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",
-    "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box",
+    "prn_conv3x3_to1_reflect", "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box",
 ]
 
 

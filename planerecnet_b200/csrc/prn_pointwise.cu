@@ -47,7 +47,9 @@ constexpr int kStemPx = 64;
 constexpr int kStemPatchW = 2 * kStemPx + 5;   // 133 input columns
 template <typename T>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int H, int W) {
-  __shared__ float patch[3][7][kStemPatchW + 3];
+  __shared__ float patch[21 * (kStemPatchW + 3)];
+  __shared__ __align__(16) short koff[192];      // k -> offset of tap (c, ky, kx) inside the patch, -1 for the zero padding
+  constexpr int kPW = kStemPatchW + 3;
   const int Ho = H / 2, Wo = W / 2;
   const int strips = (Wo + kStemPx - 1) / kStemPx;
   const int strip = blockIdx.x % strips;
@@ -55,29 +57,28 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   const int b = blockIdx.x / (strips * Ho);
   const int wo0 = strip * kStemPx;
   const int x0 = 2 * wo0 - 3, y0 = 2 * ho - 3;
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x;
+    const int c = k % 3, tap = k / 3;
+    koff[k] = k < 147 ? static_cast<short>((c * 7 + tap / 7) * kPW + tap % 7) : static_cast<short>(-1);
+  }
   for (int i = threadIdx.x; i < 21 * kStemPatchW; i += blockDim.x) {
     const int col = i % kStemPatchW, rc = i / kStemPatchW;
     const int ky = rc % 7, c = rc / 7;
     const int yy = y0 + ky, xx = x0 + col;
     float v = 0.f;
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + ((static_cast<long long>(b) * 3 + c) * H + yy) * W + xx);
-    patch[c][ky][col] = v;
+    patch[rc * kPW + col] = v;
   }
   __syncthreads();
   const int npx = min(kStemPx, Wo - wo0);
   for (int i = threadIdx.x; i < npx * 24; i += blockDim.x) {
     const int kc = i % 24, px = i / 24;
+    const uint4 ko = *reinterpret_cast<const uint4*>(koff + kc * 8);
+    const short* o = reinterpret_cast<const short*>(&ko);
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kc * 8 + j;
-      float v = 0.f;
-      if (k < 147) {
-        const int c = k % 3, tap = k / 3;
-        v = patch[c][tap / 7][2 * px + tap % 7];
-      }
-      f[j] = v;
-    }
+    for (int j = 0; j < 8; ++j) f[j] = o[j] >= 0 ? patch[o[j] + 2 * px] : 0.f;
     const long long m = (static_cast<long long>(b) * Ho + ho) * Wo + wo0 + px;
     store8(out + m * 192 + kc * 8, f);
   }
@@ -508,3 +509,82 @@ int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t h
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// 3x3 reflect-padded conv to ONE output channel (+bias, softplus): the depth head (planerecnet.py:570-573).
+// N = 1 wastes a tensor-core tile (and re-gathers the 64-channel input 9x for one column), so this layer
+// runs on the CUDA cores: a CTA stages a 16x16 output tile's 18x18x C halo in shared memory (pixel
+// stride padded by 16 B against bank conflicts) and every thread accumulates one pixel in fp32.
+namespace prn {
+
+constexpr int kD1Tile = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(kD1Tile * kD1Tile)
+conv3x3_to1_kernel(const T* __restrict__ in, const float* __restrict__ wgt /*[9][C] fp32*/, float bias,
+                   float* __restrict__ out, int B, int H, int W, int C, int softplus) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int pstride = C * 2 + 16;                          // bytes per staged pixel
+  float* wsm = reinterpret_cast<float*>(sm);               // [9*C]
+  uint8_t* tile = sm + 9 * C * 4;                          // [(18*18)][pstride]
+  const int tiles_x = (W + kD1Tile - 1) / kD1Tile, tiles_y = (H + kD1Tile - 1) / kD1Tile;
+  const int tx0 = (blockIdx.x % tiles_x) * kD1Tile;
+  const int ty0 = ((blockIdx.x / tiles_x) % tiles_y) * kD1Tile;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) wsm[i] = __ldg(wgt + i);
+  const int cv = C / 8, halo = kD1Tile + 2;
+  for (int i = threadIdx.x; i < halo * halo * cv; i += blockDim.x) {
+    const int c8 = i % cv, pix = i / cv;
+    int y = ty0 - 1 + pix / halo, x = tx0 - 1 + pix % halo;
+    y = y < 0 ? -y : (y >= H ? 2 * H - 2 - y : y);         // nn.ReflectionPad2d(1)
+    x = x < 0 ? -x : (x >= W ? 2 * W - 2 - x : x);
+    y = min(max(y, 0), H - 1);                             // tiles hanging over the border: any valid address
+    x = min(max(x, 0), W - 1);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + y) * W + x) * C) + c8);
+    *reinterpret_cast<uint4*>(tile + pix * pstride + c8 * 16) = v;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kD1Tile, lx = threadIdx.x % kD1Tile;
+  const int oy = ty0 + ly, ox = tx0 + lx;
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint8_t* px = tile + ((ly + tap / 3) * halo + lx + tap % 3) * pstride;
+    const float* wt = wsm + tap * C;
+    for (int c8 = 0; c8 < cv; ++c8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(px + c8 * 16);
+      const float4 w0 = *reinterpret_cast<const float4*>(wt + c8 * 8), w1 = *reinterpret_cast<const float4*>(wt + c8 * 8 + 4);
+      const float2 f0 = Pack2<T>::unpack(v.x), f1 = Pack2<T>::unpack(v.y), f2 = Pack2<T>::unpack(v.z), f3 = Pack2<T>::unpack(v.w);
+      acc = fmaf(f0.x, w0.x, acc); acc = fmaf(f0.y, w0.y, acc); acc = fmaf(f1.x, w0.z, acc); acc = fmaf(f1.y, w0.w, acc);
+      acc = fmaf(f2.x, w1.x, acc); acc = fmaf(f2.y, w1.y, acc); acc = fmaf(f3.x, w1.z, acc); acc = fmaf(f3.y, w1.w, acc);
+    }
+  }
+  if (oy < H && ox < W) {
+    float v = acc + bias;
+    if (softplus) v = v > 20.f ? v : log1pf(expf(v));
+    out[(static_cast<long long>(b) * H + oy) * W + ox] = v;
+  }
+}
+
+}  // namespace prn
+
+extern "C" int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, float bias, float* out, int32_t batch,
+                                       int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && weight9c && out && batch > 0 && h > 1 && w > 1 && c > 0 && c % 8 == 0 && c <= 128,
+              "conv3x3_to1_reflect: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = batch * ((h + kD1Tile - 1) / kD1Tile) * ((w + kD1Tile - 1) / kD1Tile);
+  const size_t smem = static_cast<size_t>(9) * c * 4 + static_cast<size_t>(kD1Tile + 2) * (kD1Tile + 2) * (c * 2 + 16);
+  if (dtype == PRN_BF16) {
+    static bool cfg = false;
+    if (!cfg) { PRN_CUDA(cudaFuncSetAttribute(conv3x3_to1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; }
+    conv3x3_to1_kernel<__nv_bfloat16><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __nv_bfloat16*>(in16), weight9c, bias, out, batch, h, w, c, softplus);
+  } else if (dtype == PRN_F16) {
+    static bool cfg = false;
+    if (!cfg) { PRN_CUDA(cudaFuncSetAttribute(conv3x3_to1_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; }
+    conv3x3_to1_kernel<__half><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __half*>(in16), weight9c, bias, out, batch, h, w, c, softplus);
+  } else {
+    return set_error(PRN_ERR_INVALID, "conv3x3_to1_reflect: bad dtype");
+  }
+  PRN_LAUNCH_CHECK();
+}

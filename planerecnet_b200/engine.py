@@ -382,7 +382,15 @@ class Engine:
             skip, _ = self.conv(feats[k - 1], getattr(dec, f"latlayer{k}"))
             skip, _ = rconv(skip, getattr(dec, f"conv{k}"))
             x, _ = rconv(skip, getattr(dec, f"deconv{k}"), src1=x)
-        _, d32 = rconv(x, dec.depth_pred, act=L.ACT_SOFTPLUS, out32=True)
+        # depth head: 64 -> 1 channel, on the CUDA cores (one output column would waste a tensor-core tile)
+        dconv = dec.depth_pred[1]
+        w9c = self._pack((id(dconv), "to1"), [dconv.weight, dconv.bias],
+                         lambda: (dconv.weight.detach().float()[0].permute(1, 2, 0).reshape(9, -1).contiguous().cuda(),
+                                  float(dconv.bias.detach().float()[0])))
+        Bx, Hx, Wx, Cx = x.shape
+        d32 = self._empty(Bx, Hx, Wx, 1, dtype=torch.float32)
+        self._call(self.lib.prn_conv3x3_to1_reflect, C.c_void_p(x.data_ptr()), C.c_void_p(w9c[0].data_ptr()), C.c_float(w9c[1]),
+                   C.c_void_p(d32.data_ptr()), Bx, Hx, Wx, Cx, 1, self.dt, self._st())
         return d32, attn
 
     def depth_output_nchw(self, d32, B, H, W):

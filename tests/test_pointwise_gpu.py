@@ -133,3 +133,15 @@ def test_bad_arguments_are_rejected(eng):
         eng._call(eng.lib.prn_avgpool2x2, C.c_void_p(t.data_ptr()), C.c_void_p(t.data_ptr()), 1, 3, 4, 64, eng.dt, eng._st())
     with pytest.raises(L.PrnError):
         eng._call(eng.lib.prn_mul, None, None, None, C.c_int64(8), eng.dt, eng._st())
+
+
+def test_conv3x3_to1_reflect_softplus(eng):
+    t, ref = _rand_nhwc(eng, 2, 21, 35, 64, seed=9)            # sizes that are not multiples of the 16x16 tile
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(1, 64, 3, 3, generator=g) * 0.1
+    w9c = w[0].permute(1, 2, 0).reshape(9, 64).contiguous().cuda()
+    out = torch.empty(2, 21, 35, 1, device="cuda")
+    eng._call(eng.lib.prn_conv3x3_to1_reflect, C.c_void_p(t.data_ptr()), C.c_void_p(w9c.data_ptr()), C.c_float(0.3),
+              C.c_void_p(out.data_ptr()), 2, 21, 35, 64, 1, eng.dt, eng._st())
+    exp = F.softplus(F.conv2d(F.pad(ref, (1, 1, 1, 1), mode="reflect"), w, torch.tensor([0.3])))
+    assert (out.cpu().permute(0, 3, 1, 2) - exp).abs().max() < 1e-4
