@@ -149,6 +149,8 @@ def main():
     x_host = make_input(B, H_IMG, W_IMG, seed=rank).pin_memory()
     x_dev = x_host.cuda()
 
+    from planerecnet_b200.utils import dist as D
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:

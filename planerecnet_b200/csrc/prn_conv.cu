@@ -19,6 +19,7 @@
 // Replaces the nn.Conv2d / F.conv2d / deform_conv2d call sites listed in include/prn_b200.h.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "prn_internal.h"
 #include "prn_ptx.cuh"
 
@@ -303,6 +304,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int wg = warp >> 2;
   const PrnConv& d = p.d;
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue on SMs this grid has
+  // already left; our own reads/writes of activations wait (below) until the previous grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -325,6 +329,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // everything above overlapped the previous kernel's tail
 
   const bool is_prod = wg == 2 || (kDCN && wg == 1);
   const bool is_epi = wg == 0 || (!kDCN && wg == 1);
@@ -769,6 +774,15 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   return PRN_OK;
 }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PRN_PDL");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <typename T, bool kDCN, bool kFull>
 static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKParams& p, int grid, size_t smem,
                   cudaStream_t st) {
@@ -777,8 +791,17 @@ static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKPara
     PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = true;
   }
-  conv_umma_kernel<T, kDCN, kFull><<<grid, kThreads, smem, st>>>(tm, tmo, p);
-  PRN_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  PRN_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, kDCN, kFull>, tm, tmo, p));
   return PRN_OK;
 }
 
