@@ -158,11 +158,7 @@ def main():
             torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(ms, device="cuda")     # planerecnet_b200/utils/dist.py (gloo-tested in tests/test_dist_cpu.py)
 
     # ---------------------------------------------------------------- device-resident throughput
     with torch.no_grad():
@@ -190,11 +186,13 @@ def main():
         xb = x_host.cuda(non_blocking=True)
         res = net(xb)
         out_bytes = 0
-        for r in res:
-            for k in ("pred_scores", "pred_classes", "pred_boxes", "pred_depth"):
-                if r[k] is not None:
-                    t = r[k].cpu()
-                    out_bytes += t.numel() * t.element_size()
+        # device -> host read of the step's result: detections (scores, classes, boxes) and depth maps of all images,
+        # concatenated per field so that the step issues 4 copies instead of 4 per image
+        for k in ("pred_scores", "pred_classes", "pred_boxes", "pred_depth"):
+            parts = [r[k] for r in res if r[k] is not None]
+            if parts:
+                t = torch.cat(parts).cpu()
+                out_bytes += t.numel() * t.element_size()
         return out_bytes
 
     with torch.no_grad():

@@ -35,6 +35,8 @@ class Engine:
         self._zero_pool = {}
         self._graphs = {}
         self._net_tensors = {}
+        self._side = None
+        self.multi_stream = True    # run independent branches (decoder prefix, instance-head levels) on side streams
         self.profile = None         # list of (name, flops, start_event, end_event) when profiling
 
     # ------------------------------------------------------------------ small helpers
@@ -266,7 +268,7 @@ class Engine:
             lats.append(prev)
         return [self.conv(l, fpn.fpn_convs[i], None, L.ACT_RELU)[0] for i, l in enumerate(lats)]
 
-    def inst_head(self, feats, head):
+    def inst_head(self, feats, head, streams=None):
         """planerecnet.py:355-391.  feats: (x0.5 P2, P3, P4, P5) NHWC.  Writes kernel_pred of all levels into one
         [B, sum(S^2), 128] buffer (16-bit for the attention / mask contractions, fp32 for the caller) and
         cate_pred into [B, sum(S^2), 16] fp32 (first num_classes columns valid)."""
@@ -277,11 +279,12 @@ class Engine:
         kern16 = self._empty(B, total, nk)
         kern32 = self._empty(B, total, nk, dtype=torch.float32)
         cate32 = self._empty(B, total, 16, dtype=torch.float32)
-        off = 0
         cin = head.instance_in_channels
-        for lvl, f in enumerate(feats):
-            S = grids[lvl]
-            Bf, h, w, cf = f.shape
+        offs = [sum(g * g for g in grids[:l]) for l in range(len(grids))]
+
+        def level(lvl):
+            f, S, off = feats[lvl], grids[lvl], offs[lvl]
+            _, h, w, cf = f.shape
             kf = self._empty(B, S, S, ops.round_up(cin + 2, 64))
             self._call(self.lib.prn_resize_bilinear, C.c_void_p(f.data_ptr()), C.c_void_p(kf.data_ptr()), B, h, w, cf, S, S,
                        kf.shape[-1], 1, self.dt, self._st())
@@ -296,7 +299,22 @@ class Engine:
             for i in range(0, len(head.cate_tower), 3):
                 t = self.conv_gn_relu(t, head.cate_tower[i], head.cate_tower[i + 1], c0=cin if i == 0 else None)
             self.conv(t, head.cate_pred, None, L.ACT_NONE, out16=False, out32_buf=cate32[:, off:], out_img_rows=total)
-            off += S * S
+
+        if streams is None:
+            for lvl in range(len(feats)):
+                level(lvl)
+        else:
+            # the levels are independent small problems (S^2 <= 1600 cells): run them on side streams so that they
+            # fill SMs the other branches leave idle; the output buffers above were allocated on the main stream
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            order = sorted(range(len(feats)), key=lambda l: -grids[l])
+            for i, st_ in enumerate(streams):
+                st_.wait_event(ev)
+                with torch.cuda.stream(st_):
+                    for lvl in order[i::len(streams)]:
+                        level(lvl)
         return {"kern16": kern16, "kern32": kern32, "cate32": cate32}
 
     def inst_outputs_nchw(self, st, head):
@@ -342,9 +360,29 @@ class Engine:
                     self.upsample2x(x, into=acc)
         return self.conv_gn_relu(acc, head.conv_pred[0], head.conv_pred[1])
 
-    def depth_decoder(self, cs, mask16, kern16, dec):
+    def _rconv(self, x, seq, src1=None, act=L.ACT_RELU):
+        """[nearest x2] -> ReflectionPad2d(1) -> conv3x3 -> BN -> ReLU block of the decoder (planerecnet.py:515-568)."""
+        up = 2 if isinstance(seq[0], nn.Upsample) else 1
+        conv = next(m for m in seq if isinstance(m, nn.Conv2d))
+        bn = next((m for m in seq if isinstance(m, nn.BatchNorm2d)), None)
+        return self.conv(x, conv, bn, act, src1=src1, pad=1, pad_mode=L.PAD_REFLECT, upsample=up)[0]
+
+    def depth_decoder_prefix(self, cs, dec):
+        """The part of planerecnet.py:595-604 that only depends on the backbone: x1 = deconv1(conv1(lat1(C5))) and the
+        three skip branches conv_k(lat_k(C_{6-k}))."""
+        feats = list(reversed(cs))
+        x = self.conv(feats[0], dec.latlayer1)[0]
+        x = self._rconv(x, dec.conv1)
+        x1 = self._rconv(x, dec.deconv1)
+        skips = {}
+        for k in (2, 3, 4):
+            sk = self.conv(feats[k - 1], getattr(dec, f"latlayer{k}"))[0]
+            skips[k] = self._rconv(sk, getattr(dec, f"conv{k}"))
+        return x1, skips
+
+    def depth_decoder(self, cs, mask16, kern16, dec, prefix=None):
         """planerecnet.py:586-607.  cs: [C2..C5] NHWC; mask16 [B,H/4,W/4,128]; kern16 [B,3728,128].
-        Returns depth as fp32 [B, H/2, W/2, 16] (column 0 valid)."""
+        Returns depth as fp32 [B, H/2, W/2, 1]."""
         B, mh, mw, mc = mask16.shape
         total = kern16.shape[1]
         kpad = ops.round_up(total, 64)
@@ -363,25 +401,13 @@ class Engine:
                        out_img_rows=(mh // 4) * (mw // 4), dtype=self.dt)
         attn, _ = self.conv(p, dec.conv1x1[0], None, L.ACT_NONE, c_splits=[(total, kpad)])
 
-        def rconv(x, seq, src1=None, act=L.ACT_RELU, out32=False):
-            up = 2 if isinstance(seq[0], nn.Upsample) else 1
-            conv = next(m for m in seq if isinstance(m, nn.Conv2d))
-            bn = next((m for m in seq if isinstance(m, nn.BatchNorm2d)), None)
-            return self.conv(x, conv, bn, act, src1=src1, pad=1, pad_mode=L.PAD_REFLECT, upsample=up, out32=out32,
-                             out16=not out32)
-
-        feats = list(reversed(cs))
-        x, _ = self.conv(feats[0], dec.latlayer1)
-        x, _ = rconv(x, dec.conv1)
-        x, _ = rconv(x, dec.deconv1)
+        x, skips = prefix if prefix is not None else self.depth_decoder_prefix(cs, dec)
         xa = self._empty(*x.shape)
         self._call(self.lib.prn_mul, C.c_void_p(x.data_ptr()), C.c_void_p(attn.data_ptr()), C.c_void_p(xa.data_ptr()),
                    C.c_int64(x.numel()), self.dt, self._st())
-        x, _ = rconv(x, dec.refine_conv, src1=xa)
+        x = self._rconv(x, dec.refine_conv, src1=xa)
         for k in (2, 3, 4):
-            skip, _ = self.conv(feats[k - 1], getattr(dec, f"latlayer{k}"))
-            skip, _ = rconv(skip, getattr(dec, f"conv{k}"))
-            x, _ = rconv(skip, getattr(dec, f"deconv{k}"), src1=x)
+            x = self._rconv(skips[k], getattr(dec, f"deconv{k}"), src1=x)
         # depth head: 64 -> 1 channel, on the CUDA cores (one output column would waste a tensor-core tile)
         dconv = dec.depth_pred[1]
         w9c = self._pack((id(dconv), "to1"), [dconv.weight, dconv.bias],
@@ -402,12 +428,41 @@ class Engine:
         if not x.is_cuda:
             raise L.PrnError("PlaneRecNet (B200) forward needs a CUDA input tensor; there is no CPU path")
         cs_all = self.backbone(x, net.backbone)
-        ps = self.fpn([cs_all[i] for i in net.fpn_indices], net.fpn)
-        feats = [self.avgpool2(ps[0]), ps[1], ps[2], ps[3]]
-        inst = self.inst_head(feats, net.inst_head)
-        mask16 = self.mask_head(ps, net.mask_head)
-        d32, attn = self.depth_decoder([cs_all[i] for i in net.depth_decoder_indices], mask16, inst["kern16"],
-                                       net.depth_decoder)
+        dec_cs = [cs_all[i] for i in net.depth_decoder_indices]
+        if not self.multi_stream:
+            ps = self.fpn([cs_all[i] for i in net.fpn_indices], net.fpn)
+            feats = [self.avgpool2(ps[0]), ps[1], ps[2], ps[3]]
+            inst = self.inst_head(feats, net.inst_head)
+            mask16 = self.mask_head(ps, net.mask_head)
+            d32, attn = self.depth_decoder(dec_cs, mask16, inst["kern16"], net.depth_decoder)
+        else:
+            # Branches that do not depend on each other run on side streams (fork/join with events; captured as
+            # parallel branches of the CUDA graph): decoder prefix || FPN -> (instance head levels || mask head).
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = [torch.cuda.Stream() for _ in range(3)]
+            s_dec, s_i0, s_i1 = self._side
+            ev_bb = torch.cuda.Event()
+            ev_bb.record(main)
+            s_dec.wait_event(ev_bb)
+            with torch.cuda.stream(s_dec):
+                prefix = self.depth_decoder_prefix(dec_cs, net.depth_decoder)
+                ev_dec = torch.cuda.Event()
+                ev_dec.record(s_dec)
+            ps = self.fpn([cs_all[i] for i in net.fpn_indices], net.fpn)
+            feats = [self.avgpool2(ps[0]), ps[1], ps[2], ps[3]]
+            inst = self.inst_head(feats, net.inst_head, streams=[s_i0, s_i1])
+            evs = []
+            for s_ in (s_i0, s_i1):
+                e = torch.cuda.Event()
+                e.record(s_)
+                evs.append(e)
+            mask16 = self.mask_head(ps, net.mask_head)
+            for e in evs + [ev_dec]:
+                main.wait_event(e)
+            for t in [prefix[0]] + list(prefix[1].values()):
+                t.record_stream(main)
+            d32, attn = self.depth_decoder(dec_cs, mask16, inst["kern16"], net.depth_decoder, prefix=prefix)
         st = {"cs": cs_all, "ps": ps, "inst": inst, "mask16": mask16, "depth32": d32, "attn": attn}
         if want_nchw:
             cates, kerns = self.inst_outputs_nchw(inst, net.inst_head)

@@ -61,8 +61,9 @@ def _strides_table(net, device):
 def select(scores, seg_fn, strides_all, nc, p):
     """Candidate selection + matrix-NMS for a batch (planerecnet.py:189-269).
 
-    scores: fp32 [B, total, nc] after point-NMS.  seg_fn(rows [B,n] long, n) -> (seg32 [B*n, P] fp32 sigmoid
-    masks, mask16 [B*n, P] 0/1, area [B*n], ssum [B*n], inter [B, n, n] fp32) for the candidates' kernel rows.
+    scores: fp32 [B, total, nc] after point-NMS.  seg_fn(rows [B,n] long, valid, n) -> (seg32 [B*n, P] fp32 sigmoid
+    masks, mask16 [B*n, P] 0/1, area [B*n], ssum [B*n], gram_fn) for the candidates' kernel rows;
+    gram_fn(order [B,n1], n1) -> [B, n1, n1] fp32 mask intersections of the selected candidates, in that order.
     Returns per image (sel_rows into seg32, scores, labels) of the final detections (possibly empty) + seg32."""
     B, total, _ = scores.shape
     dev = scores.device
@@ -87,20 +88,22 @@ def select(scores, seg_fn, strides_all, nc, p):
     labels = idxc % nc
     sc = torch.where(valid, flat.gather(1, idxc), torch.zeros((), device=dev))
     strides = strides_all[rows]
-    seg32, mask16, area, ssum, inter = seg_fn(rows, valid, n)
+    seg32, mask16, area, ssum, gram_fn = seg_fn(rows, valid, n)
     area = area.view(B, n)
     ssum = ssum.view(B, n)
     keep = valid & (area > strides)                               # planerecnet.py:219-220
     sc = sc * (ssum / area)                                       # maskness (planerecnet.py:231-232)
     key = torch.where(keep, sc, torch.full_like(sc, -1.0))
     order = torch.argsort(key, dim=1, descending=True)
-    n_pre = min(n, p["nms_pre"])
+    n_pre = min(n, ops.round_up(p["nms_pre"], 16))                # sort, keep the best nms_pre (planerecnet.py:235-242)
     order = order[:, :n_pre]
     v1 = keep.gather(1, order)
+    if n_pre > p["nms_pre"]:
+        v1[:, p["nms_pre"]:] = False
     s1 = key.gather(1, order)
     a1 = area.gather(1, order)
     l1 = labels.gather(1, order)
-    inter1 = inter.gather(1, order[:, :, None].expand(-1, -1, n)).gather(2, order[:, None, :].expand(-1, n_pre, -1))
+    inter1 = gram_fn(order, n_pre)                                # intersections of the sorted survivors only
     s2 = _decay(inter1, a1, l1, s1, v1, p["sigma"], p["kernel"])  # nms.py
     keep2 = v1 & (s2 >= p["update_thr"])
     key2 = torch.where(keep2, s2, torch.full_like(s2, -1.0))
@@ -162,12 +165,17 @@ def inference(eng, net, st, x):
         ssum = torch.empty(B * n, device=dev)
         eng._call(lib.prn_mask_stats, C.c_void_p(seg32.data_ptr()), C.c_void_p(m16.data_ptr()), C.c_void_p(area.data_ptr()),
                   C.c_void_p(ssum.data_ptr()), B * n, P, C.c_float(p["mask_thr"]), eng.dt, eng._st())
-        # Gram matrix of the binary masks (nms.py:20-22): exact in fp32 (integer counts < 2^24)
-        inter = torch.empty(B, n, n, device=dev)
-        eng.launches += 1
-        ops.conv2d(m16.view(B, n, 1, P), m16, batch=B, h_in=n, w_in=1, ksize=1, act=L.ACT_NONE, out32=inter, ld_out32=n,
-                   n_pad=n, w_group_rows=n, dtype=eng.dt)
-        return seg32, m16, area, ssum, inter
+        def gram_fn(order, n1):
+            # Gram matrix of the binary masks of the sorted top-nms_pre candidates (nms.py:20-22): exact in fp32
+            # (integer counts < 2^24), on the tensor cores with per-image operands
+            msel = m16.view(B, n, P).gather(1, order[:, :, None].expand(-1, -1, P))
+            inter = torch.empty(B, n1, n1, device=dev)
+            eng.launches += 1
+            ops.conv2d(msel.view(B, n1, 1, P), msel.view(B * n1, P), batch=B, h_in=n1, w_in=1, ksize=1, act=L.ACT_NONE,
+                       out32=inter, ld_out32=n1, n_pad=n1, w_group_rows=n1, dtype=eng.dt)
+            return inter
+
+        return seg32, m16, area, ssum, gram_fn
 
     dets, seg32 = select(scores, seg_fn, strides_all, nc, p)
 

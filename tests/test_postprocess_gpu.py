@@ -66,14 +66,19 @@ def test_selection_and_matrix_nms_match_oracle_exactly(cuda_lib, seed, n_cand):
         ssum = torch.empty(B * n, device=dev)
         eng._call(eng.lib.prn_mask_stats, C.c_void_p(seg32.data_ptr()), C.c_void_p(m16.data_ptr()), C.c_void_p(area.data_ptr()),
                   C.c_void_p(ssum.data_ptr()), B * n, P, C.c_float(O.INFER["mask_thr"]), eng.dt, eng._st())
-        inter = torch.empty(B, n, n, device=dev)
-        ops.conv2d(m16.view(B, n, 1, P), m16, batch=B, h_in=n, w_in=1, ksize=1, out32=inter, ld_out32=n, n_pad=n,
-                   w_group_rows=n, dtype=eng.dt)
-        # the kernels' sums against torch on the same data: area exact, intersections exact
         mk = (seg32 > O.INFER["mask_thr"]).float().view(B, n, P)
-        assert torch.equal(area.view(B, n), mk.sum(-1))
-        assert torch.equal(inter, torch.bmm(mk, mk.transpose(1, 2)))
-        return seg32, m16, area, ssum, inter
+        assert torch.equal(area.view(B, n), mk.sum(-1))          # the kernel's areas are exact
+
+        def gram_fn(order, n1):
+            msel = m16.view(B, n, P).gather(1, order[:, :, None].expand(-1, -1, P))
+            inter = torch.empty(B, n1, n1, device=dev)
+            ops.conv2d(msel.view(B, n1, 1, P), msel.view(B * n1, P), batch=B, h_in=n1, w_in=1, ksize=1, out32=inter,
+                       ld_out32=n1, n_pad=n1, w_group_rows=n1, dtype=eng.dt)
+            ms = mk.gather(1, order[:, :, None].expand(-1, -1, P))
+            assert torch.equal(inter, torch.bmm(ms, ms.transpose(1, 2)))     # intersections are exact integers
+            return inter
+
+        return seg32, m16, area, ssum, gram_fn
 
     p = dict(score_thr=0.1, mask_thr=0.1, update_thr=0.15, nms_pre=500, top_k=100, sigma=2.0, kernel="gaussian")
     dets, seg32 = PP.select(scores.to(dev), seg_fn, strides_all.to(dev), 2, p)
