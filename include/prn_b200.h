@@ -99,6 +99,8 @@ int prn_conv2d_fwd(const PrnConv* desc, void* stream);
 int prn_conv2d_fwd_profile(const PrnConv* desc, void* stream, int64_t* counters16);
 /* Workspace-free helper: bytes of dynamic shared memory and CTAs the launch would use (for tests). */
 int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid);
+/* out8 = {n_tile, stages, grid, cluster size, m_tiles, n_tiles, lean epilogue?, TMA store?}. */
+int prn_conv2d_plan_ex(const PrnConv* desc, int32_t* out8);
 
 /* ---- HBM-bound passes between the contractions (NHWC 16-bit unless stated) -------------------- */
 

@@ -68,7 +68,7 @@ def lib():
 # every symbol include/prn_b200.h declares (tests check the header against this list and the .so)
 EXPORTS = [
     "prn_last_error", "prn_abi_version", "prn_device_sm_count",
-    "prn_conv2d_fwd", "prn_conv2d_fwd_profile", "prn_conv2d_plan",
+    "prn_conv2d_fwd", "prn_conv2d_fwd_profile", "prn_conv2d_plan", "prn_conv2d_plan_ex",
     "prn_stem_im2col", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
     "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",

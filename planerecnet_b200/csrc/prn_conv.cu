@@ -43,6 +43,9 @@ struct ConvKParams {
   int groups;
   int imgs_per_group;
   int m_tiles, n_tiles, total_tiles;
+  int cluster;        // 1, or 2 = CTA pairs over consecutive M tiles sharing every weight k-block (TMA multicast)
+  int m_ptiles;       // ceil(m_tiles / cluster)
+  int total_ptiles;   // groups * m_ptiles * n_tiles: loop count of every CTA (pair)
   int n_tile;
   int stages;
   int tmem_cols;
@@ -276,7 +279,7 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <typename T, bool kDCN, bool kFull>
+template <typename T, bool kDCN, bool kFull, int kCl>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ ConvKParams p) {
@@ -313,7 +316,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (p.tma_store) tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, kProdWarps * 32 + 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, kCl);     // one tcgen05.commit per CTA of the cluster (they share the B stage)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -329,7 +332,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
+  const int crank = kCl > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  if constexpr (kCl > 1) cluster_sync_all();           // peer barriers are initialised before anything targets them
   asm volatile("griddepcontrol.wait;" ::: "memory");   // everything above overlapped the previous kernel's tail
+  // tile walk shared by all roles: pair-tile pt -> (group g, M tile mt = mp * kCl + rank, N tile nt)
+  const int pt0 = static_cast<int>(blockIdx.x) / kCl, pt_step = static_cast<int>(gridDim.x) / kCl;
 
   const bool is_prod = wg == 2 || (kDCN && wg == 1);
   const bool is_epi = wg == 0 || (!kDCN && wg == 1);
@@ -354,10 +361,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       row_off[i] = static_cast<uint32_t>(r * 128 + ((chunk ^ (r & 7)) << 4));
     }
     const long long t_role0 = prof ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = pt0; tile < p.total_ptiles; tile += pt_step) {
       const int rest = tile / p.n_tiles;
-      const int mt = rest % p.m_tiles;
-      const int g = rest / p.m_tiles;
+      const int mt = (rest % p.m_ptiles) * kCl + crank;
+      const int g = rest / p.m_ptiles;
       int img_pix[kRows], hy[kRows], wx[kRows];
       int m_glob[kRows];
       uint32_t valid = 0;
@@ -496,14 +503,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       if (lane == 0) {
         int s = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = pt0; tile < p.total_ptiles; tile += pt_step) {
           const int nt = tile % p.n_tiles;
-          const int g = (tile / p.n_tiles) / p.m_tiles;
+          const int g = (tile / p.n_tiles) / p.m_ptiles;
           const int row0 = g * d.w_group_rows + nt * p.n_tile;
           for (int kb = 0; kb < p.num_kb; ++kb) {
-            mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+            mbar_wait(bar_empty + 8 * s, ph ^ 1u);        // (cluster: both CTAs' MMAs have released the stage)
             mbar_arrive_expect_tx(bar_full + 8 * s, b_stage_bytes);
-            tma_load_2d(b_base + static_cast<uint32_t>(s) * b_stage_bytes, &tmap_w, bar_full + 8 * s, kb * 64, row0);
+            if constexpr (kCl == 1) {
+              tma_load_2d(b_base + static_cast<uint32_t>(s) * b_stage_bytes, &tmap_w, bar_full + 8 * s, kb * 64, row0);
+            } else {
+              // this CTA fetches its half of the weight rows and multicasts it into both CTAs' stage
+              const uint32_t half = b_stage_bytes / 2;
+              tma_load_2d_mcast(b_base + static_cast<uint32_t>(s) * b_stage_bytes + crank * half, &tmap_w, bar_full + 8 * s,
+                                kb * 64, row0 + crank * (p.n_tile / 2), static_cast<uint16_t>(0x3));
+            }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -518,7 +532,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const bool prof = p.dbg != nullptr && blockIdx.x == 0;
         long long w_full = 0, w_tempty = 0;
         const long long t_role0 = prof ? clock64() : 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = pt0; tile < p.total_ptiles; tile += pt_step) {
           mbar_wait_acc(bar_tempty + 8 * acc, acc_ph ^ 1u, prof, w_tempty);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * p.n_tile);
@@ -533,7 +547,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               umma_f16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), p.idesc,
                        (kb | k) != 0 ? 1u : 0u);
             }
-            umma_commit(bar_empty + 8 * s);
+            if constexpr (kCl == 1) umma_commit(bar_empty + 8 * s);
+            else umma_commit_mcast(bar_empty + 8 * s, static_cast<uint16_t>(0x3));
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
           umma_commit(bar_tfull + 8 * acc);
@@ -558,11 +573,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const long long t_role0 = prof ? clock64() : 0;
     int bias_n0 = -1;
     const uint32_t stg_tile = stg_base + static_cast<uint32_t>(warp) * 4096u;   // warps 0-7
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = pt0; tile < p.total_ptiles; tile += pt_step) {
       const int nt = tile % p.n_tiles;
       const int rest = tile / p.n_tiles;
-      const int mt = rest % p.m_tiles;
-      const int g = rest / p.m_tiles;
+      const int mt = (rest % p.m_ptiles) * kCl + crank;
+      const int g = rest / p.m_ptiles;
       const int n0 = nt * p.n_tile;
       const int n_valid = min(p.n_tile, d.n_pad - n0);   // multiple of 16
       const int m = mt * kTileM + q * 32 + lane;
@@ -670,10 +685,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (kCl > 1) cluster_sync_all();   // the peer may still multicast into / arrive on this CTA's shared memory
   if (warp == 13) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static bool cluster_enabled();
 static int plan(const PrnConv& d, ConvKParams* p) {
   PRN_REQUIRE(d.src0 != nullptr && d.weight != nullptr, "conv: src0/weight must be non-NULL");
   PRN_REQUIRE(d.c0 > 0 && d.c0 % 64 == 0 && d.c1 >= 0 && d.c1 % 64 == 0, "conv: channel counts must be multiples of 64 (c0=%d c1=%d)", d.c0, d.c1);
@@ -753,6 +770,10 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   p->n_tile = n_tile;
   p->n_tiles = ceil_div(d.n_pad, n_tile);
   p->total_tiles = p->groups * p->m_tiles * p->n_tiles;
+  // CTA pairs sharing the weight stream pay off when the weight k-blocks dominate the L2->SM traffic
+  p->cluster = (cluster_enabled() && !d.dcn_offmask && n_tile >= 128 && n_tile % 32 == 0 && p->m_tiles >= 2 && kb >= 4) ? 2 : 1;
+  p->m_ptiles = ceil_div(p->m_tiles, p->cluster);
+  p->total_ptiles = p->groups * p->m_ptiles * p->n_tiles;
   int cols = 32;
   while (cols < 2 * n_tile) cols *= 2;
   p->tmem_cols = cols;
@@ -774,6 +795,15 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   return PRN_OK;
 }
 
+static bool cluster_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PRN_CLUSTER");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -783,12 +813,12 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
-template <typename T, bool kDCN, bool kFull>
+template <typename T, bool kDCN, bool kFull, int kCl>
 static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKParams& p, int grid, size_t smem,
                   cudaStream_t st) {
   static bool configured = false;  // per instantiation
   if (!configured) {
-    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kFull>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kFull, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -796,16 +826,32 @@ static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKPara
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kCl > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = kCl;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  PRN_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, kDCN, kFull>, tm, tmo, p));
+  cfg.numAttrs = na;
+  PRN_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, kDCN, kFull, kCl>, tm, tmo, p));
   return PRN_OK;
 }
 
 }  // namespace prn
+
+static int launch_grid(const prn::ConvKParams& p) {
+  const int sms = prn::sm_count();
+  return p.total_ptiles * p.cluster < sms ? p.total_ptiles * p.cluster : (sms / p.cluster) * p.cluster;
+}
 
 extern "C" int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* stages, int32_t* grid) {
   if (!desc) return prn::set_error(PRN_ERR_INVALID, "conv: NULL descriptor");
@@ -814,7 +860,17 @@ extern "C" int prn_conv2d_plan(const PrnConv* desc, int32_t* n_tile, int32_t* st
   if (rc != PRN_OK) return rc;
   if (n_tile) *n_tile = p.n_tile;
   if (stages) *stages = p.stages;
-  if (grid) *grid = p.total_tiles < prn::sm_count() ? p.total_tiles : prn::sm_count();
+  if (grid) *grid = launch_grid(p);
+  return PRN_OK;
+}
+
+extern "C" int prn_conv2d_plan_ex(const PrnConv* desc, int32_t* out8) {
+  if (!desc || !out8) return prn::set_error(PRN_ERR_INVALID, "conv: NULL argument");
+  prn::ConvKParams p;
+  int rc = prn::plan(*desc, &p);
+  if (rc != PRN_OK) return rc;
+  out8[0] = p.n_tile; out8[1] = p.stages; out8[2] = launch_grid(p); out8[3] = p.cluster;
+  out8[4] = p.m_tiles; out8[5] = p.n_tiles; out8[6] = p.lean_epi; out8[7] = p.tma_store;
   return PRN_OK;
 }
 
@@ -837,7 +893,7 @@ static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   CUtensorMap tm;
   const uint64_t kdim = static_cast<uint64_t>(d.ksize) * d.ksize * (d.c0 + d.c1);
   const uint64_t rows = d.w_rows_total > 0 ? static_cast<uint64_t>(d.w_rows_total) : static_cast<uint64_t>(d.n_pad);
-  rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile), d.dtype);
+  rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile / p.cluster), d.dtype);
   if (rc != PRN_OK) return rc;
   const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   CUtensorMap tmo = tm;
@@ -850,9 +906,11 @@ static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool dcn = d.dcn_offmask != nullptr;
   const bool full = !p.lean_epi;
-#define PRN_LAUNCH(T)                                                                               \
-  (dcn ? (full ? launch<T, true, true>(tm, tmo, p, grid, smem, st) : launch<T, true, false>(tm, tmo, p, grid, smem, st)) \
-       : (full ? launch<T, false, true>(tm, tmo, p, grid, smem, st) : launch<T, false, false>(tm, tmo, p, grid, smem, st)))
+#define PRN_LAUNCH(T)                                                                                                  \
+  (dcn ? (full ? launch<T, true, true, 1>(tm, tmo, p, grid, smem, st) : launch<T, true, false, 1>(tm, tmo, p, grid, smem, st)) \
+       : (p.cluster == 2                                                                                               \
+              ? (full ? launch<T, false, true, 2>(tm, tmo, p, grid, smem, st) : launch<T, false, false, 2>(tm, tmo, p, grid, smem, st)) \
+              : (full ? launch<T, false, true, 1>(tm, tmo, p, grid, smem, st) : launch<T, false, false, 1>(tm, tmo, p, grid, smem, st))))
   if (d.dtype == PRN_BF16) return PRN_LAUNCH(__nv_bfloat16);
   return PRN_LAUNCH(__half);
 #undef PRN_LAUNCH

@@ -30,6 +30,7 @@ SHAPES = {
     "inst_3x3_256_s40": (8, 40, 40, 256, 256, 3, 1, {}),
     "ppa_dyn": (8, 1200, 4, 128, 3728, 1, 1, {"grouped": True, "act": L.ACT_SIGMOID_AVG4}),
     "ppa_1x1_3776_256": (8, 30, 40, 3776, 256, 1, 1, {}),
+    "mask2_3x3_256_128": (8, 30, 40, 256, 128, 3, 1, {}),
     "dcn_l2_256": (8, 30, 40, 256, 256, 3, 1, {"dcn": True}),
     "dcn_l1_128": (8, 60, 80, 128, 128, 3, 1, {"dcn": True}),
     "dcn_l3_512": (8, 15, 20, 512, 512, 3, 1, {"dcn": True}),
@@ -103,4 +104,7 @@ def C_int():
 if __name__ == "__main__":
     names = sys.argv[1:] or list(SHAPES)
     for n in names:
-        probe(n)
+        try:
+            probe(n)
+        except Exception as e:  # keep going: one bad launch configuration should not hide the others
+            print(f"{n:20s} FAILED: {str(e)[-160:]}", flush=True)
