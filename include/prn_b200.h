@@ -161,6 +161,75 @@ int prn_mask_stats(const float* seg, void* mask16, float* area, float* ssum, int
 int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool, int32_t* boxes, int32_t n_inst, int32_t h,
                           int32_t w, int32_t h_out, int32_t w_out, float thr, void* stream);
 
+/* ---- training step: backward of the dense path.  The reference has no hand-written backward; these
+ *      are torch autograd's gradients of the operator call sites cited above, 16-bit NHWC gradients, fp32 weight gradients. */
+
+/* Weight gradient of the convolution a PrnConv with the same geometry describes (nn.Conv2d call sites
+ * models/backbone.py:56-66, models/fpn.py:55,61, planerecnet.py:386-391, 478-495, 593-605):
+ *   dw[n, (ky*ksize + kx)*(c0+c1) + c] += sum_m dy[m, n] * im2col(src)[m, (ky,kx,c)]     m = (image, ho, wo)
+ * Split-K tcgen05 contraction over the output pixels; partial sums are ADDED to dw with fp32 reductions, so the
+ * caller zeroes dw (or keeps accumulating into it).  The input gradient needs no entry point of its own: it is
+ * prn_conv2d_fwd over dy with the spatially flipped, in/out-transposed weights. */
+typedef struct PrnWgrad {
+  const void* src0;        /* forward input(s), NHWC 16-bit, exactly as given to prn_conv2d_fwd */
+  const void* src1;
+  int32_t c0, c1;
+  int32_t ld0, ld1;
+  int32_t batch, h_in, w_in;
+  int32_t upsample;
+  int32_t ksize, stride, pad;
+  int32_t pad_mode;
+  int32_t h_out, w_out;
+  const void* dy;          /* 16-bit [batch*h_out*w_out][ld_dy], first n columns used */
+  int32_t n;               /* output channels */
+  int32_t ld_dy;           /* multiple of 8 */
+  float* dw;               /* fp32 [n][ld_dw], 16-byte aligned */
+  int32_t ld_dw;           /* >= ksize*ksize*(c0+c1), multiple of 4 */
+  int32_t dtype;
+  int32_t flags;           /* 0; bit 0 = swap the LBO/SBO fields of the MN-major operand descriptors (bring-up aid) */
+} PrnWgrad;
+int prn_conv2d_wgrad(const PrnWgrad* desc, void* stream);
+/* out8 = {m_tiles, n_tiles, k_splits, k-blocks per split, 128-row sub-tiles per CTA, stages, grid, atoms}. */
+int prn_conv2d_wgrad_plan(const PrnWgrad* desc, int32_t* out8);
+
+/* nn.BatchNorm2d in training mode (models/backbone.py:57-65, planerecnet.py:518,543 under net.train()):
+ * stats[c*2+{0,1}] = {sum, sumsq} of the conv output over `count` rows (a prn_conv2d_fwd epilogue with stats_cg = 0)
+ * -> mean_invstd[c*2+{0,1}] = {mean, 1/sqrt(biased var + eps)}; running statistics (NULL = leave) are updated with
+ * `momentum` and the unbiased variance like torch. */
+int prn_bn_finalize(const float* stats, float* mean_invstd, float* running_mean, float* running_var, int32_t c, int64_t count,
+                    float eps, float momentum, void* stream);
+/* out = [relu]((x - mean) * invstd * gamma + beta [+ residual]) over 16-bit [rows][c]. */
+int prn_bn_apply(const void* x16, void* out16, const float* mean_invstd, const float* gamma, const float* beta,
+                 const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream);
+/* Per-channel reductions of a gradient: g = dz * (out > 0) (out16 NULL: g = dz);
+ * sums[c*2] += sum g (= dbeta / conv bias gradient), sums[c*2+1] += sum g * (x - mean) * invstd (= dgamma; skipped when
+ * x16 is NULL).  Caller zeroes sums. */
+int prn_chan_reduce(const void* dz16, const void* out16, const void* x16, const float* mean_invstd, float* sums, int64_t rows,
+                    int32_t c, int32_t dtype, void* stream);
+/* BatchNorm backward: dx = gamma * invstd * (g - sums[c][0]/rows - xhat * sums[c][1]/rows); g_out16 (optional) = g. */
+int prn_bn_bwd_apply(const void* dz16, const void* out16, const void* x16, const float* mean_invstd, const float* gamma,
+                     const float* sums, void* dx16, void* g_out16, int64_t rows, int32_t c, int32_t dtype, void* stream);
+/* g = dz * (out > 0). */
+int prn_relu_bwd(const void* dz16, const void* out16, void* g16, int64_t n, int32_t dtype, void* stream);
+/* dst[b, s*i, s*j, :] += src[b, i, j, :]: input gradient of the 1x1 stride-s downsample conv (models/backbone.py:152-167). */
+int prn_add_strided(void* dst16, const void* src16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride, int32_t dtype,
+                    void* stream);
+/* out16 = a32 (+ b16); out16 = a16 + b16: joins of gradient branches. */
+int prn_add_f32(const float* a32, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream);
+int prn_add16(const void* a16, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream);
+/* nn.MaxPool2d(3, 2, 1) backward (models/backbone.py:104): first maximum in scan order takes the gradient, like torch. */
+int prn_maxpool3x3s2_bwd(const void* in16, const void* dout16, void* din16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                         int32_t dtype, void* stream);
+/* Training form of torchvision.ops.deform_conv2d (models/dcn.py:59-66): col16[m, tap*c + ch] = mask * bilinear sample,
+ * m = (image, ho, wo), offmask as for PrnConv.dcn_offmask; the contraction with the weights is a 1x1 prn_conv2d_fwd. */
+int prn_dcn_im2col(const void* x16, const float* offmask, void* col16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                   int32_t stride, int32_t pad, int32_t dtype, void* stream);
+/* Backward of prn_dcn_im2col: dx32 fp32 [batch,h,w,c] (caller zeroes) += scattered input gradient; dpre16 [M][64] =
+ * gradient w.r.t. the pre-activation output of the fused offset/modulator conv (models/dcn.py:53-57: clamp passes where
+ * |offset| < clamp_bound, modulator through d(2*sigmoid)); columns >= 27 are written as 0. */
+int prn_dcn_col2im_bwd(const void* x16, const float* offmask, const void* dcol16, float* dx32, void* dpre16, int32_t batch,
+                       int32_t h, int32_t w, int32_t c, int32_t stride, int32_t pad, float clamp_bound, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,22 @@ class PrnConv(C.Structure):
     ]
 
 
+class PrnWgrad(C.Structure):
+    _fields_ = [
+        ("src0", C.c_void_p), ("src1", C.c_void_p),
+        ("c0", C.c_int32), ("c1", C.c_int32),
+        ("ld0", C.c_int32), ("ld1", C.c_int32),
+        ("batch", C.c_int32), ("h_in", C.c_int32), ("w_in", C.c_int32),
+        ("upsample", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+        ("pad_mode", C.c_int32),
+        ("h_out", C.c_int32), ("w_out", C.c_int32),
+        ("dy", C.c_void_p), ("n", C.c_int32), ("ld_dy", C.c_int32),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int32),
+        ("dtype", C.c_int32), ("flags", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -73,6 +89,9 @@ EXPORTS = [
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
     "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",
     "prn_conv3x3_to1_reflect", "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box",
+    "prn_conv2d_wgrad", "prn_conv2d_wgrad_plan", "prn_bn_finalize", "prn_bn_apply", "prn_chan_reduce", "prn_bn_bwd_apply",
+    "prn_relu_bwd", "prn_add_strided", "prn_add_f32", "prn_add16", "prn_maxpool3x3s2_bwd", "prn_dcn_im2col",
+    "prn_dcn_col2im_bwd",
 ]
 
 

@@ -1,0 +1,529 @@
+// prn_train.cu — HBM-bound passes of the training step (train-mode BatchNorm forward, and the backward of
+// BatchNorm / ReLU / max-pool / strided 1x1 / modulated deformable sampling).  NHWC, 16-bit, 8 channels
+// (16 bytes) per thread; per-channel reductions accumulate in shared memory and leave with one fp32 atomic per
+// (CTA, channel).  The reference has no hand-written backward: these are autograd's formulas for the operator
+// call sites cited per function in include/prn_b200.h.
+#include "prn_pw.cuh"
+
+namespace prn {
+
+// ---------------------------------------------------------------- BatchNorm2d, training mode
+// stats[c*2 + {0,1}] = {sum, sumsq} over `count` rows (accumulated by the conv epilogue, fp32)
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, int C, float count,
+                                   float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[2 * c] / count;
+  const float var = fmaxf(stats[2 * c + 1] / count - mean * mean, 0.f);   // biased: normalisation
+  mean_invstd[2 * c] = mean;
+  mean_invstd[2 * c + 1] = rsqrtf(var + eps);
+  if (running_mean != nullptr) {
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ mean_invstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ res,
+                                long long rows, int C, int relu) {
+  const int cv = C / 8;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    float f[8], r[8];
+    load8(x + m * C + c, f);
+    if (res != nullptr) load8(res + m * C + c, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
+      float v = (f[j] - mean) * inv * __ldg(gamma + c + j) + __ldg(beta + c + j);
+      if (res != nullptr) v += r[j];
+      f[j] = relu ? fmaxf(v, 0.f) : v;
+    }
+    store8(out + m * C + c, f);
+  }
+}
+
+// sums[c*2] += sum_m g, sums[c*2+1] += sum_m g * xhat with g = dz * (out > 0) (out == NULL: g = dz) and
+// xhat = (x - mean) * invstd (x == NULL: second sum skipped).  Total thread count is a multiple of C/8 so that a
+// thread keeps its 8 channels for all of its rows.
+template <typename T>
+__global__ void chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
+                                   const float* __restrict__ mean_invstd, float* __restrict__ sums, long long rows, int C) {
+  extern __shared__ float acc[];   // [C][2]
+  const int cv = C / 8;
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+  const int c = static_cast<int>(gtid % cv) * 8;
+  const long long rstep = tthreads / cv;
+  float mean[8], inv[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = x != nullptr ? __ldg(mean_invstd + 2 * (c + j)) : 0.f;
+    inv[j] = x != nullptr ? __ldg(mean_invstd + 2 * (c + j) + 1) : 0.f;
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  for (long long m = gtid / cv; m < rows; m += rstep) {
+    float g[8], o[8], xv[8];
+    load8(dz + m * C + c, g);
+    if (out != nullptr) {
+      load8(out + m * C + c, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] += g[j];
+    if (x != nullptr) {
+      load8(x + m * C + c, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s2[j] = fmaf(g[j], (xv[j] - mean[j]) * inv[j], s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(acc + 2 * (c + j), s1[j]);
+    atomicAdd(acc + 2 * (c + j) + 1, s2[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(sums + i, acc[i]);
+}
+
+// dx = gamma * invstd * (g - sum_g / count - xhat * sum_gxhat / count); optionally g itself is written too (the
+// gradient of the residual branch of a bottleneck: models/backbone.py:69-70)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
+                                    const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, T* __restrict__ dx, T* __restrict__ g_out, long long rows,
+                                    int C, float inv_count) {
+  const int cv = C / 8;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    float g[8], o[8], xv[8];
+    load8(dz + m * C + c, g);
+    if (out != nullptr) {
+      load8(out + m * C + c, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+    }
+    if (g_out != nullptr) store8(g_out + m * C + c, g);
+    load8(x + m * C + c, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
+      const float xhat = (xv[j] - mean) * inv;
+      const float sg = __ldg(sums + 2 * (c + j)) * inv_count, sgx = __ldg(sums + 2 * (c + j) + 1) * inv_count;
+      xv[j] = __ldg(gamma + c + j) * inv * (g[j] - sg - xhat * sgx);
+    }
+    store8(dx + m * C + c, xv);
+  }
+}
+
+// g = dz * (out > 0): ReLU backward on its own (layers whose normalisation is not a BatchNorm)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dz, const T* __restrict__ out, T* __restrict__ g, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a[8], o[8];
+    load8(dz + i * 8, a);
+    load8(out + i * 8, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = o[j] > 0.f ? a[j] : 0.f;
+    store8(g + i * 8, a);
+  }
+}
+
+// dst[b, s*i, s*j, :] += src[b, i, j, :]: input gradient of a 1x1 stride-s convolution (the bottleneck's downsample
+// branch, models/backbone.py:152-167) joined with the gradient already in dst
+template <typename T>
+__global__ void add_strided_kernel(T* __restrict__ dst, const T* __restrict__ src, int B, int h, int w, int C, int s) {
+  const int cv = C / 8;
+  const long long total = static_cast<long long>(B) * h * w * cv;
+  const int H = h * s, W = w * s;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int x = static_cast<int>(m % w), y = static_cast<int>((m / w) % h);
+    const int b = static_cast<int>(m / (static_cast<long long>(w) * h));
+    T* dp = dst + ((static_cast<long long>(b) * H + y * s) * W + x * s) * C + c;
+    float a[8], q[8];
+    load8(src + m * C + c, a);
+    load8(dp, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += q[j];
+    store8(dp, a);
+  }
+}
+
+// out16 = a32 (+ b16): joins an fp32 scatter buffer with the 16-bit gradient stream
+template <typename T>
+__global__ void add_f32_kernel(const float* __restrict__ a32, const T* __restrict__ b16, T* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(a32) + 2 * i), v = __ldg(reinterpret_cast<const float4*>(a32) + 2 * i + 1);
+    float f[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+    if (b16 != nullptr) {
+      float q[8];
+      load8(b16 + i * 8, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += q[j];
+    }
+    store8(out + i * 8, f);
+  }
+}
+
+// out16 = a16 + b16
+template <typename T>
+__global__ void add16_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float f[8], q[8];
+    load8(a + i * 8, f);
+    load8(b + i * 8, q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += q[j];
+    store8(out + i * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------- MaxPool2d(3, 2, 1) backward (models/backbone.py:104)
+// Gather form, deterministic: an input pixel receives the gradient of every window in which it is the FIRST maximum
+// in (dy, dx) scan order (torch's strict `>` update rule), so ties resolve like the reference.
+template <typename T>
+__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ in, const T* __restrict__ dout, T* __restrict__ din, int B, int H,
+                                      int W, int C) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, cv = C / 8;
+  const long long total = static_cast<long long>(B) * H * W * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const long long m = i / cv;
+    const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
+    const int b = static_cast<int>(m / (static_cast<long long>(W) * H));
+    const T* img = in + static_cast<long long>(b) * H * W * C + c;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int ho_hi = min((y + 1) >> 1, Ho - 1), wo_hi = min((x + 1) >> 1, Wo - 1);
+    for (int ho = y >> 1; ho <= ho_hi; ++ho) {
+      for (int wo = x >> 1; wo <= wo_hi; ++wo) {
+        const int my = (y - (2 * ho - 1)) * 3 + (x - (2 * wo - 1));   // my position in the window's scan order
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = -1; }
+        for (int dy = 0; dy < 3; ++dy) {
+          const int yy = 2 * ho - 1 + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            const int xx = 2 * wo - 1 + dx;
+            if (xx < 0 || xx >= W) continue;
+            float f[8];
+            load8(img + (static_cast<long long>(yy) * W + xx) * C, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (f[j] > best[j]) { best[j] = f[j]; arg[j] = dy * 3 + dx; }
+          }
+        }
+        float g[8];
+        load8(dout + ((static_cast<long long>(b) * Ho + ho) * Wo + wo) * C + c, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += arg[j] == my ? g[j] : 0.f;
+      }
+    }
+    store8(din + m * C + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------- modulated deformable sampling, training form
+// torchvision.ops.deform_conv2d (models/dcn.py:59-66) split into its two halves: the sampled + modulated im2col
+// matrix col[m, tap*C + c] (16-bit, saved for the backward) and a plain contraction with the packed weights.
+struct DcnGeom {
+  int B, H, W, C, Ho, Wo, stride, pad;
+};
+
+__device__ __forceinline__ void dcn_corners(const DcnGeom& g, const float* om, int tap, int ho, int wo, float& mk, bool& inside,
+                                            float& ly, float& lx, int& y0, int& x0) {
+  const int ky = tap / 3, kx = tap - ky * 3;
+  const float py = static_cast<float>(ho * g.stride - g.pad + ky) + __ldg(om + 2 * tap);
+  const float px = static_cast<float>(wo * g.stride - g.pad + kx) + __ldg(om + 2 * tap + 1);
+  mk = __ldg(om + 18 + tap);
+  inside = py > -1.f && py < static_cast<float>(g.H) && px > -1.f && px < static_cast<float>(g.W);
+  const float fy = floorf(py), fx = floorf(px);
+  y0 = static_cast<int>(fy);
+  x0 = static_cast<int>(fx);
+  ly = py - fy;
+  lx = px - fx;
+}
+
+template <typename T>
+__global__ void dcn_im2col_kernel(const T* __restrict__ x, const float* __restrict__ offmask, T* __restrict__ col, DcnGeom g) {
+  const int cv = g.C / 8;
+  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * 9 * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv) * 8;
+    const int tap = static_cast<int>((i / cv) % 9);
+    const long long m = i / (9 * cv);
+    const int wo = static_cast<int>(m % g.Wo), ho = static_cast<int>((m / g.Wo) % g.Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
+    float mk, ly, lx;
+    bool inside;
+    int y0, x0;
+    dcn_corners(g, offmask + m * 32, tap, ho, wo, mk, inside, ly, lx, y0, x0);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (inside) {
+#pragma unroll
+      for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          const int yy = y0 + cy, xx = x0 + cx;
+          if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
+          const float wgt = (cy ? ly : 1.f - ly) * (cx ? lx : 1.f - lx) * mk;
+          float f[8];
+          load8(x + ((static_cast<long long>(b) * g.H + yy) * g.W + xx) * g.C + c, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(wgt, f[j], acc[j]);
+        }
+      }
+    }
+    store8(col + m * (9LL * g.C) + static_cast<long long>(tap) * g.C + c, acc);
+  }
+}
+
+__device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// One warp per output pixel.  dcol = gradient of the im2col matrix.  Produces
+//   dx32 (fp32, zero-initialised by the caller) += mask * bilinear weights * dcol      scattered with vector reductions
+//   dpre16[m, 0:64]: gradient w.r.t. the PRE-activation output of the fused offset/modulator conv: offsets pass
+//   where the clamp is inactive (|off| < bound), modulators through d(2*sigmoid)/dz = m * (1 - m/2); columns >= 27 are 0.
+template <typename T>
+__global__ void dcn_col2im_bwd_kernel(const T* __restrict__ x, const float* __restrict__ offmask, const T* __restrict__ dcol,
+                                      float* __restrict__ dx32, T* __restrict__ dpre16, DcnGeom g, float bound) {
+  const int cv = g.C / 8;
+  const int lane = threadIdx.x & 31;
+  const long long warp_g = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const long long M = static_cast<long long>(g.B) * g.Ho * g.Wo;
+  for (long long m = warp_g; m < M; m += nwarps) {
+    const int wo = static_cast<int>(m % g.Wo), ho = static_cast<int>((m / g.Wo) % g.Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
+    const float* om = offmask + m * 32;
+    float v0 = 0.f, v1 = 0.f;   // the two dpre columns (2*lane, 2*lane+1) this lane writes
+    for (int tap = 0; tap < 9; ++tap) {
+      float mk, ly, lx;
+      bool inside;
+      int y0, x0;
+      dcn_corners(g, om, tap, ho, wo, mk, inside, ly, lx, y0, x0);
+      float s_m = 0.f, s_y = 0.f, s_x = 0.f;
+      if (inside) {
+        for (int ch = lane; ch < cv; ch += 32) {
+          const int c = ch * 8;
+          float gcol[8];
+          load8(dcol + m * (9LL * g.C) + static_cast<long long>(tap) * g.C + c, gcol);
+#pragma unroll
+          for (int cy = 0; cy < 2; ++cy) {
+#pragma unroll
+            for (int cx = 0; cx < 2; ++cx) {
+              const int yy = y0 + cy, xx = x0 + cx;
+              if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
+              const float wy = cy ? ly : 1.f - ly, wxx = cx ? lx : 1.f - lx;
+              const long long pix = ((static_cast<long long>(b) * g.H + yy) * g.W + xx) * g.C + c;
+              float f[8];
+              load8(x + pix, f);
+              float dot = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dot = fmaf(gcol[j], f[j], dot);
+              s_m = fmaf(wy * wxx, dot, s_m);
+              s_y = fmaf((cy ? 1.f : -1.f) * wxx, dot, s_y);
+              s_x = fmaf((cx ? 1.f : -1.f) * wy, dot, s_x);
+              const float wgt = wy * wxx * mk;
+              red_add_v4f(dx32 + pix, wgt * gcol[0], wgt * gcol[1], wgt * gcol[2], wgt * gcol[3]);
+              red_add_v4f(dx32 + pix + 4, wgt * gcol[4], wgt * gcol[5], wgt * gcol[6], wgt * gcol[7]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s_m += __shfl_xor_sync(0xffffffffu, s_m, o);
+        s_y += __shfl_xor_sync(0xffffffffu, s_y, o);
+        s_x += __shfl_xor_sync(0xffffffffu, s_x, o);
+      }
+      const float offy = __ldg(om + 2 * tap), offx = __ldg(om + 2 * tap + 1);
+      const float d_dy = (offy > -bound && offy < bound) ? s_y * mk : 0.f;
+      const float d_dx = (offx > -bound && offx < bound) ? s_x * mk : 0.f;
+      const float d_mk = s_m * mk * (1.f - 0.5f * mk);
+      if (lane == tap) { v0 = d_dy; v1 = d_dx; }
+      if (lane == 9 + (tap >> 1)) { if (tap & 1) v1 = d_mk; else v0 = d_mk; }
+    }
+    reinterpret_cast<uint32_t*>(dpre16 + m * 64)[lane] = Pack2<T>::pack(v0, v1);
+  }
+}
+
+}  // namespace prn
+
+// =================================================================================================== C ABI
+using namespace prn;
+
+static int chan_reduce_grid(long long rows, int cv) {
+  // total threads must be a multiple of cv: grid multiple of cv / gcd(cv, 256)
+  int a = cv, b = kPwThreads;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int g0 = cv / a;
+  long long want = (rows * cv + kPwThreads * 8LL - 1) / (kPwThreads * 8LL);   // ~8 rows per thread
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (want > cap) want = cap;
+  long long grid = want / g0 * g0;
+  if (grid < g0) grid = g0;
+  return static_cast<int>(grid);
+}
+
+extern "C" {
+
+int prn_bn_finalize(const float* stats, float* mean_invstd, float* running_mean, float* running_var, int32_t c, int64_t count,
+                    float eps, float momentum, void* stream) {
+  PRN_REQUIRE(stats && mean_invstd && c > 0 && count > 0 && (running_mean == nullptr) == (running_var == nullptr),
+              "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(stats, mean_invstd, running_mean, running_var, c,
+                                                                                   static_cast<float>(count), eps, momentum);
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_bn_apply(const void* x16, void* out16, const float* mean_invstd, const float* gamma, const float* beta,
+                 const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream) {
+  PRN_REQUIRE(x16 && out16 && mean_invstd && gamma && beta && rows > 0 && c > 0 && c % 8 == 0, "bn_apply: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = rows * (c / 8);
+  PRN_DISPATCH(dtype,
+               (bn_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), static_cast<__nv_bfloat16*>(out16), mean_invstd, gamma, beta, static_cast<const __nv_bfloat16*>(residual16), rows, c, relu)),
+               (bn_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(x16), static_cast<__half*>(out16), mean_invstd, gamma, beta, static_cast<const __half*>(residual16), rows, c, relu)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_chan_reduce(const void* dz16, const void* out16, const void* x16, const float* mean_invstd, float* sums, int64_t rows,
+                    int32_t c, int32_t dtype, void* stream) {
+  PRN_REQUIRE(dz16 && sums && rows > 0 && c > 0 && c % 8 == 0 && c <= 4096 && (x16 == nullptr || mean_invstd != nullptr),
+              "chan_reduce: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = chan_reduce_grid(rows, c / 8);
+  const size_t smem = static_cast<size_t>(c) * 2 * sizeof(float);
+  PRN_DISPATCH(dtype,
+               (chan_reduce_kernel<__nv_bfloat16><<<grid, kPwThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), mean_invstd, sums, rows, c)),
+               (chan_reduce_kernel<__half><<<grid, kPwThreads, smem, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), mean_invstd, sums, rows, c)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_bn_bwd_apply(const void* dz16, const void* out16, const void* x16, const float* mean_invstd, const float* gamma,
+                     const float* sums, void* dx16, void* g_out16, int64_t rows, int32_t c, int32_t dtype, void* stream) {
+  PRN_REQUIRE(dz16 && x16 && mean_invstd && gamma && sums && dx16 && rows > 0 && c > 0 && c % 8 == 0, "bn_bwd_apply: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = rows * (c / 8);
+  const float inv_count = 1.0f / static_cast<float>(rows);
+  PRN_DISPATCH(dtype,
+               (bn_bwd_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), mean_invstd, gamma, sums, static_cast<__nv_bfloat16*>(dx16), static_cast<__nv_bfloat16*>(g_out16), rows, c, inv_count)),
+               (bn_bwd_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), mean_invstd, gamma, sums, static_cast<__half*>(dx16), static_cast<__half*>(g_out16), rows, c, inv_count)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_relu_bwd(const void* dz16, const void* out16, void* g16, int64_t n, int32_t dtype, void* stream) {
+  PRN_REQUIRE(dz16 && out16 && g16 && n > 0 && n % 8 == 0, "relu_bwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (relu_bwd_kernel<__nv_bfloat16><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<__nv_bfloat16*>(g16), n / 8)),
+               (relu_bwd_kernel<__half><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<__half*>(g16), n / 8)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_add_strided(void* dst16, const void* src16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride, int32_t dtype,
+                    void* stream) {
+  PRN_REQUIRE(dst16 && src16 && batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && stride >= 1, "add_strided: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * h * w * (c / 8);
+  PRN_DISPATCH(dtype,
+               (add_strided_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<__nv_bfloat16*>(dst16), static_cast<const __nv_bfloat16*>(src16), batch, h, w, c, stride)),
+               (add_strided_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<__half*>(dst16), static_cast<const __half*>(src16), batch, h, w, c, stride)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_add_f32(const float* a32, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream) {
+  PRN_REQUIRE(a32 && out16 && n > 0 && n % 8 == 0, "add_f32: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (add_f32_kernel<__nv_bfloat16><<<pw_grid(n / 8), kPwThreads, 0, st>>>(a32, static_cast<const __nv_bfloat16*>(b16), static_cast<__nv_bfloat16*>(out16), n / 8)),
+               (add_f32_kernel<__half><<<pw_grid(n / 8), kPwThreads, 0, st>>>(a32, static_cast<const __half*>(b16), static_cast<__half*>(out16), n / 8)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_add16(const void* a16, const void* b16, void* out16, int64_t n, int32_t dtype, void* stream) {
+  PRN_REQUIRE(a16 && b16 && out16 && n > 0 && n % 8 == 0, "add16: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (add16_kernel<__nv_bfloat16><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(a16), static_cast<const __nv_bfloat16*>(b16), static_cast<__nv_bfloat16*>(out16), n / 8)),
+               (add16_kernel<__half><<<pw_grid(n / 8), kPwThreads, 0, st>>>(static_cast<const __half*>(a16), static_cast<const __half*>(b16), static_cast<__half*>(out16), n / 8)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_maxpool3x3s2_bwd(const void* in16, const void* dout16, void* din16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                         int32_t dtype, void* stream) {
+  PRN_REQUIRE(in16 && dout16 && din16 && batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool_bwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * h * w * (c / 8);
+  PRN_DISPATCH(dtype,
+               (maxpool3s2_bwd_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<const __nv_bfloat16*>(dout16), static_cast<__nv_bfloat16*>(din16), batch, h, w, c)),
+               (maxpool3s2_bwd_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<const __half*>(dout16), static_cast<__half*>(din16), batch, h, w, c)));
+  PRN_LAUNCH_CHECK();
+}
+
+static int dcn_geom(DcnGeom* g, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t stride, int32_t pad) {
+  PRN_REQUIRE(batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && stride >= 1 && pad >= 0, "dcn: bad geometry");
+  g->B = batch; g->H = h; g->W = w; g->C = c; g->stride = stride; g->pad = pad;
+  g->Ho = (h + 2 * pad - 3) / stride + 1;
+  g->Wo = (w + 2 * pad - 3) / stride + 1;
+  return PRN_OK;
+}
+
+int prn_dcn_im2col(const void* x16, const float* offmask, void* col16, int32_t batch, int32_t h, int32_t w, int32_t c,
+                   int32_t stride, int32_t pad, int32_t dtype, void* stream) {
+  PRN_REQUIRE(x16 && offmask && col16, "dcn_im2col: NULL argument");
+  DcnGeom g;
+  int rc = dcn_geom(&g, batch, h, w, c, stride, pad);
+  if (rc != PRN_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * g.Ho * g.Wo * 9 * (c / 8);
+  PRN_DISPATCH(dtype,
+               (dcn_im2col_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), offmask, static_cast<__nv_bfloat16*>(col16), g)),
+               (dcn_im2col_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(x16), offmask, static_cast<__half*>(col16), g)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_dcn_col2im_bwd(const void* x16, const float* offmask, const void* dcol16, float* dx32, void* dpre16, int32_t batch,
+                       int32_t h, int32_t w, int32_t c, int32_t stride, int32_t pad, float clamp_bound, int32_t dtype, void* stream) {
+  PRN_REQUIRE(x16 && offmask && dcol16 && dx32 && dpre16, "dcn_col2im_bwd: NULL argument");
+  DcnGeom g;
+  int rc = dcn_geom(&g, batch, h, w, c, stride, pad);
+  if (rc != PRN_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long work = static_cast<long long>(batch) * g.Ho * g.Wo * 32;
+  PRN_DISPATCH(dtype,
+               (dcn_col2im_bwd_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), offmask, static_cast<const __nv_bfloat16*>(dcol16), dx32, static_cast<__nv_bfloat16*>(dpre16), g, clamp_bound)),
+               (dcn_col2im_bwd_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(x16), offmask, static_cast<const __half*>(dcol16), dx32, static_cast<__half*>(dpre16), g, clamp_bound)));
+  PRN_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -89,3 +89,112 @@ def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mod
     else:
         L.check(L.lib().prn_conv2d_fwd(C.byref(d), L.current_stream()), "prn_conv2d_fwd")
     return d
+
+
+# ------------------------------------------------------------------------------------------ training step
+def _vp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def pack_dgrad_weight(w, cout_pad=None, n_pad=None, dtype=L.PRN_BF16):
+    """[Cout, Cin, kh, kw] -> packed weights of the input-gradient convolution: rows = Cin (padded to n_pad),
+    K = (ky, kx, Cout padded), taps flipped.  dX = conv(dY, this, pad = k - 1 - pad) for stride 1."""
+    wt = w.detach().float().flip(2, 3).transpose(0, 1).contiguous()      # [Cin, Cout, kh, kw]
+    cout = w.shape[0]
+    return pack_conv_weight(wt, [(cout, cout_pad or round_up(cout, 64))], n_pad or round_up(w.shape[1], 16), dtype)
+
+
+def conv2d_wgrad(src0, dy, dw, *, batch, h_in, w_in, n, ksize=1, stride=1, pad=0, pad_mode=L.PAD_ZERO, upsample=1,
+                 src1=None, c0=None, c1=None, dtype=L.PRN_BF16, flags=0):
+    """Launch prn_conv2d_wgrad: dw[n, ksize*ksize*(c0+c1)] (fp32, accumulated) += dy^T . im2col(src)."""
+    d = L.PrnWgrad()
+    d.src0 = src0.data_ptr()
+    d.c0 = c0 if c0 is not None else src0.shape[-1]
+    d.src1 = src1.data_ptr() if src1 is not None else None
+    d.c1 = (c1 if c1 is not None else src1.shape[-1]) if src1 is not None else 0
+    d.ld0 = src0.shape[-1] if src0.shape[-1] != d.c0 else 0
+    d.ld1 = (src1.shape[-1] if src1.shape[-1] != d.c1 else 0) if src1 is not None else 0
+    d.batch, d.h_in, d.w_in = batch, h_in, w_in
+    d.upsample = upsample
+    d.ksize, d.stride, d.pad, d.pad_mode = ksize, stride, pad, pad_mode
+    d.h_out = (h_in * upsample + 2 * pad - ksize) // stride + 1
+    d.w_out = (w_in * upsample + 2 * pad - ksize) // stride + 1
+    d.dy = dy.data_ptr()
+    d.n = n
+    d.ld_dy = dy.shape[-1]
+    d.dw = dw.data_ptr()
+    d.ld_dw = dw.shape[-1]
+    d.dtype = dtype
+    d.flags = flags
+    L.check(L.lib().prn_conv2d_wgrad(C.byref(d), L.current_stream()), "prn_conv2d_wgrad")
+    return d
+
+
+def unpack_wgrad(dw, weight_shape, c_splits=None):
+    """fp32 [n_rows, kh*kw*sum(c_pad)] (layout of pack_conv_weight) -> [Cout, Cin, kh, kw] fp32."""
+    cout, cin, kh, kw = weight_shape
+    if c_splits is None:
+        c_splits = [(cin, round_up(cin, 64))]
+    cpad = sum(p for _, p in c_splits)
+    v = dw[:cout].view(cout, kh, kw, cpad)
+    parts, off = [], 0
+    for real, padded in c_splits:
+        parts.append(v[..., off:off + real])
+        off += padded
+    return torch.cat(parts, dim=-1).permute(0, 3, 1, 2).contiguous()
+
+
+def bn_finalize(stats, mean_invstd, running_mean, running_var, count, eps, momentum):
+    L.check(L.lib().prn_bn_finalize(_vp(stats), _vp(mean_invstd), _vp(running_mean), _vp(running_var), stats.numel() // 2,
+                                    C.c_int64(count), C.c_float(eps), C.c_float(momentum), L.current_stream()), "prn_bn_finalize")
+
+
+def bn_apply(x, out, mean_invstd, gamma, beta, residual, relu, dtype):
+    c = x.shape[-1]
+    L.check(L.lib().prn_bn_apply(_vp(x), _vp(out), _vp(mean_invstd), _vp(gamma), _vp(beta), _vp(residual),
+                                 C.c_int64(x.numel() // c), c, 1 if relu else 0, dtype, L.current_stream()), "prn_bn_apply")
+
+
+def chan_reduce(dz, out, x, mean_invstd, sums, dtype):
+    c = dz.shape[-1]
+    L.check(L.lib().prn_chan_reduce(_vp(dz), _vp(out), _vp(x), _vp(mean_invstd), _vp(sums), C.c_int64(dz.numel() // c), c, dtype,
+                                    L.current_stream()), "prn_chan_reduce")
+
+
+def bn_bwd_apply(dz, out, x, mean_invstd, gamma, sums, dx, g_out, dtype):
+    c = dz.shape[-1]
+    L.check(L.lib().prn_bn_bwd_apply(_vp(dz), _vp(out), _vp(x), _vp(mean_invstd), _vp(gamma), _vp(sums), _vp(dx), _vp(g_out),
+                                     C.c_int64(dz.numel() // c), c, dtype, L.current_stream()), "prn_bn_bwd_apply")
+
+
+def relu_bwd(dz, out, g, dtype):
+    L.check(L.lib().prn_relu_bwd(_vp(dz), _vp(out), _vp(g), C.c_int64(dz.numel()), dtype, L.current_stream()), "prn_relu_bwd")
+
+
+def add_strided(dst, src, stride, dtype):
+    b, h, w, c = src.shape
+    L.check(L.lib().prn_add_strided(_vp(dst), _vp(src), b, h, w, c, stride, dtype, L.current_stream()), "prn_add_strided")
+
+
+def add_f32(a32, b16, out16, dtype):
+    L.check(L.lib().prn_add_f32(_vp(a32), _vp(b16), _vp(out16), C.c_int64(a32.numel()), dtype, L.current_stream()), "prn_add_f32")
+
+
+def add16(a, b, out, dtype):
+    L.check(L.lib().prn_add16(_vp(a), _vp(b), _vp(out), C.c_int64(a.numel()), dtype, L.current_stream()), "prn_add16")
+
+
+def maxpool_bwd(x, dout, din, dtype):
+    b, h, w, c = x.shape
+    L.check(L.lib().prn_maxpool3x3s2_bwd(_vp(x), _vp(dout), _vp(din), b, h, w, c, dtype, L.current_stream()), "prn_maxpool3x3s2_bwd")
+
+
+def dcn_im2col(x, offmask, col, stride, pad, dtype):
+    b, h, w, c = x.shape
+    L.check(L.lib().prn_dcn_im2col(_vp(x), _vp(offmask), _vp(col), b, h, w, c, stride, pad, dtype, L.current_stream()), "prn_dcn_im2col")
+
+
+def dcn_col2im_bwd(x, offmask, dcol, dx32, dpre16, stride, pad, bound, dtype):
+    b, h, w, c = x.shape
+    L.check(L.lib().prn_dcn_col2im_bwd(_vp(x), _vp(offmask), _vp(dcol), _vp(dx32), _vp(dpre16), b, h, w, c, stride, pad,
+                                       C.c_float(bound), dtype, L.current_stream()), "prn_dcn_col2im_bwd")
