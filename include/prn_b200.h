@@ -230,6 +230,34 @@ int prn_dcn_im2col(const void* x16, const float* offmask, void* col16, int32_t b
 int prn_dcn_col2im_bwd(const void* x16, const float* offmask, const void* dcol16, float* dx32, void* dpre16, int32_t batch,
                        int32_t h, int32_t w, int32_t c, int32_t stride, int32_t pad, float clamp_bound, int32_t dtype, void* stream);
 
+/* nn.GroupNorm(32, C) + ReLU backward (planerecnet.py:341-342, 420-421, 463-464).  stats as for prn_groupnorm_apply.
+ * Pass 1: g = dz * (out > 0); sums_bc[(b*c + ch)*2 + {0,1}] += {sum_pix g, sum_pix g*xhat} (caller zeroes) and
+ * dgb[ch*2 + {0,1}] += the same over all images (= dbeta, dgamma; levels sharing weights keep accumulating).
+ * Pass 2: dx = rstd * (g*gamma - mean_group(g*gamma) - xhat * mean_group(g*gamma*xhat)). */
+int prn_gn_bwd_reduce(const void* dz16, const void* out16, const void* x16, const float* stats, float* sums_bc, float* dgb,
+                      int32_t batch, int32_t hw, int32_t c, int32_t ch_per_group, float eps, int32_t dtype, void* stream);
+int prn_gn_bwd_apply(const void* dz16, const void* out16, const void* x16, const float* stats, const float* gamma,
+                     const float* sums_bc, void* dx16, int32_t batch, int32_t hw, int32_t c, int32_t ch_per_group, float eps,
+                     int32_t dtype, void* stream);
+/* Backward of prn_avgpool2x2: din [batch,h,w,c] (= or +=) 0.25 * dout[b, y/2, x/2]. */
+int prn_avgpool2x2_bwd(const void* dout16, void* din16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t accumulate,
+                       int32_t dtype, void* stream);
+/* Backward of prn_upsample2x_bilinear: dout [batch,2h,2w,c] -> din [batch,h,w,c]. */
+int prn_upsample2x_bilinear_bwd(const void* dout16, void* din16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype,
+                                void* stream);
+/* Backward of prn_resize_bilinear w.r.t. its c feature channels: dout [batch,h_out,w_out,ld_dout] -> din32 fp32
+ * [batch,h,w,c] += (caller zeroes); the coord channels have no upstream. */
+int prn_resize_bilinear_bwd(const void* dout16, float* din32, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t h_out,
+                            int32_t w_out, int32_t ld_dout, int32_t dtype, void* stream);
+/* Backward of [nn.Upsample(x2 nearest) ->] nn.ReflectionPad2d(1) (planerecnet.py:515-568): dpad16
+ * [batch, h*up+2, w*up+2, ld_dpad] is the gradient w.r.t. the padded tensor (prn_conv2d_fwd over dY with the flipped
+ * weights and zero padding 2); folds mirrored borders and the 2x2 replicas into din16 [batch,h,w,c] (= or +=). */
+int prn_reflect_fold(const void* dpad16, void* din16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t ld_dpad,
+                     int32_t upsample, int32_t accumulate, int32_t dtype, void* stream);
+/* nn.Softplus backward for the single-channel depth head (planerecnet.py:570-573): dpre16[m, 0] = dout[m] *
+ * (1 - exp(-out[m])), columns 1..63 zero (a 64-channel operand row for the head's gradient contractions). */
+int prn_softplus_bwd_pad(const float* dout, const float* out, void* dpre16, int64_t rows, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

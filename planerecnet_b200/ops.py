@@ -198,3 +198,46 @@ def dcn_col2im_bwd(x, offmask, dcol, dx32, dpre16, stride, pad, bound, dtype):
     b, h, w, c = x.shape
     L.check(L.lib().prn_dcn_col2im_bwd(_vp(x), _vp(offmask), _vp(dcol), _vp(dx32), _vp(dpre16), b, h, w, c, stride, pad,
                                        C.c_float(bound), dtype, L.current_stream()), "prn_dcn_col2im_bwd")
+
+
+def gn_bwd_reduce(dz, out, x, stats, sums_bc, dgb, cg, eps, dtype):
+    b, c = dz.shape[0], dz.shape[-1]
+    hw = dz.numel() // (b * c)
+    L.check(L.lib().prn_gn_bwd_reduce(_vp(dz), _vp(out), _vp(x), _vp(stats), _vp(sums_bc), _vp(dgb), b, hw, c, cg, C.c_float(eps),
+                                      dtype, L.current_stream()), "prn_gn_bwd_reduce")
+
+
+def gn_bwd_apply(dz, out, x, stats, gamma, sums_bc, dx, cg, eps, dtype):
+    b, c = dz.shape[0], dz.shape[-1]
+    hw = dz.numel() // (b * c)
+    L.check(L.lib().prn_gn_bwd_apply(_vp(dz), _vp(out), _vp(x), _vp(stats), _vp(gamma), _vp(sums_bc), _vp(dx), b, hw, c, cg,
+                                     C.c_float(eps), dtype, L.current_stream()), "prn_gn_bwd_apply")
+
+
+def avgpool2_bwd(dout, din, accumulate, dtype):
+    b, h, w, c = din.shape
+    L.check(L.lib().prn_avgpool2x2_bwd(_vp(dout), _vp(din), b, h, w, c, 1 if accumulate else 0, dtype, L.current_stream()),
+            "prn_avgpool2x2_bwd")
+
+
+def upsample2x_bwd(dout, din, dtype):
+    b, h, w, c = din.shape
+    L.check(L.lib().prn_upsample2x_bilinear_bwd(_vp(dout), _vp(din), b, h, w, c, dtype, L.current_stream()),
+            "prn_upsample2x_bilinear_bwd")
+
+
+def resize_bilinear_bwd(dout, din32, dtype):
+    b, h, w, c = din32.shape
+    L.check(L.lib().prn_resize_bilinear_bwd(_vp(dout), _vp(din32), b, h, w, c, dout.shape[1], dout.shape[2], dout.shape[3], dtype,
+                                            L.current_stream()), "prn_resize_bilinear_bwd")
+
+
+def reflect_fold(dpad, din, upsample, accumulate, dtype):
+    b, h, w, c = din.shape
+    L.check(L.lib().prn_reflect_fold(_vp(dpad), _vp(din), b, h, w, c, dpad.shape[-1], upsample, 1 if accumulate else 0, dtype,
+                                     L.current_stream()), "prn_reflect_fold")
+
+
+def softplus_bwd_pad(dout32, out32, dpre16, dtype):
+    L.check(L.lib().prn_softplus_bwd_pad(_vp(dout32), _vp(out32), _vp(dpre16), C.c_int64(out32.numel()), dtype, L.current_stream()),
+            "prn_softplus_bwd_pad")

@@ -39,3 +39,25 @@ def test_gradient_joins(cuda_lib):
 @pytest.mark.parametrize("name", list(TC.DCN_CASES))
 def test_dcn_train(cuda_lib, name):
     TC.run_dcn_case(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(Cc=128, HW=777, B=2)])
+def test_groupnorm_bwd(cuda_lib, kw):
+    TC.run_gn_case(**kw)
+
+
+@pytest.mark.gpu
+def test_resample_bwd(cuda_lib):
+    TC.run_resample_bwd_cases()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(up=1), dict(up=2), dict(up=2, accumulate=True), dict(up=1, H=3, W=3)])
+def test_reflect_dgrad(cuda_lib, kw):
+    TC.run_reflect_dgrad_case(**kw)
+
+
+@pytest.mark.gpu
+def test_softplus_bwd(cuda_lib):
+    TC.run_softplus_case()

@@ -292,3 +292,122 @@ def run_dcn_case(name, seed=0):
     r["dpre"] = chk("dpre", dpre[:, :27], pr.grad, 2e-2)
     assert float(dpre[:, 27:].float().abs().max()) == 0.0
     return r
+
+
+def _chk(what, got, ref, tol):
+    scale = ref.abs().max().item() + 1e-6
+    err = (got.float().cpu() - ref).abs().max().item()
+    assert err <= tol * scale, f"{what}: max err {err:.4g} > {tol * scale:.4g} (scale {scale:.3g})"
+    return err / scale
+
+
+def run_gn_case(seed=0, B=3, HW=15 * 20, Cc=256, G=32):
+    """GroupNorm(32)+ReLU backward against autograd of F.group_norm."""
+    g = torch.Generator().manual_seed(seed)
+    tdt, dt = torch.bfloat16, L.PRN_BF16
+    cg = Cc // G
+    x = (torch.randn(B, HW, Cc, generator=g) * 1.5 + 0.3).to(tdt)
+    gamma = torch.rand(Cc, generator=g) + 0.5
+    beta = torch.randn(Cc, generator=g) * 0.2
+    dz = torch.randn(B, HW, Cc, generator=g).to(tdt)
+    eps = 1e-5
+    xr = x.float().clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.group_norm(xr.permute(0, 2, 1), G, gr, br, eps).permute(0, 2, 1).relu()
+    y.backward(dz.float())
+    xd = x.to(DEV)
+    xf = xd.float().reshape(B, HW, G, cg)
+    stats = torch.stack([xf.sum((1, 3)), (xf * xf).sum((1, 3))], -1).reshape(-1).contiguous()
+    out = torch.empty(B, HW, Cc, dtype=tdt, device=DEV)
+    gd, bd = gamma.to(DEV), beta.to(DEV)
+    import ctypes as C
+    L.check(L.lib().prn_groupnorm_apply(C.c_void_p(xd.data_ptr()), C.c_void_p(out.data_ptr()), C.c_void_p(stats.data_ptr()),
+                                        C.c_void_p(gd.data_ptr()), C.c_void_p(bd.data_ptr()), B, HW, Cc, cg, C.c_float(eps), 1, dt,
+                                        L.current_stream()))
+    sums_bc = torch.zeros(B, Cc, 2, device=DEV)
+    dgb = torch.zeros(Cc, 2, device=DEV)
+    dzd = dz.to(DEV)
+    ops.gn_bwd_reduce(dzd, out, xd, stats, sums_bc, dgb, cg, eps, dt)
+    dx = torch.empty(B, HW, Cc, dtype=tdt, device=DEV)
+    ops.gn_bwd_apply(dzd, out, xd, stats, gd, sums_bc, dx, cg, eps, dt)
+    torch.cuda.synchronize()
+    r = {"out": _chk("gn forward", out, y.detach(), 2.0 ** -8 + 2e-3)}
+    r["dx"] = _chk("gn dx", dx, xr.grad, 2.0 ** -8 + 3e-3)
+    r["dgamma"] = _chk("gn dgamma", dgb[:, 1], gr.grad, 3e-3)
+    r["dbeta"] = _chk("gn dbeta", dgb[:, 0], br.grad, 3e-3)
+    return r
+
+
+def run_resample_bwd_cases(seed=0):
+    """2x2 mean, bilinear x2 and arbitrary bilinear resize backward against autograd of F.interpolate."""
+    g = torch.Generator().manual_seed(seed)
+    tdt, dt = torch.bfloat16, L.PRN_BF16
+    r = {}
+    B, H, W, Cc = 2, 12, 16, 64
+    # 2x2 mean
+    dout = torch.randn(B, H // 2, W // 2, Cc, generator=g).to(tdt)
+    xr = torch.zeros(B, Cc, H, W, requires_grad=True)
+    F.interpolate(xr, scale_factor=0.5, mode="bilinear", align_corners=False).backward(dout.float().permute(0, 3, 1, 2))
+    din = torch.empty(B, H, W, Cc, dtype=tdt, device=DEV)
+    ops.avgpool2_bwd(dout.to(DEV), din, False, dt)
+    prev = torch.randn(B, H, W, Cc, generator=g).to(tdt)
+    din2 = prev.to(DEV)
+    ops.avgpool2_bwd(dout.to(DEV), din2, True, dt)
+    torch.cuda.synchronize()
+    ref = xr.grad.permute(0, 2, 3, 1)
+    r["avg"] = _chk("avgpool2 bwd", din, ref, 2.0 ** -8)
+    r["avg_acc"] = _chk("avgpool2 bwd acc", din2, ref + prev.float(), 2.0 ** -7)
+    # bilinear x2
+    dout = torch.randn(B, 2 * H, 2 * W, Cc, generator=g).to(tdt)
+    xr = torch.zeros(B, Cc, H, W, requires_grad=True)
+    F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False).backward(dout.float().permute(0, 3, 1, 2))
+    din = torch.empty(B, H, W, Cc, dtype=tdt, device=DEV)
+    ops.upsample2x_bwd(dout.to(DEV), din, dt)
+    torch.cuda.synchronize()
+    r["up2"] = _chk("upsample2x bwd", din, xr.grad.permute(0, 2, 3, 1), 2.0 ** -7)
+    # arbitrary resize (down 60x80 -> 40x40 style and up 15x20 -> 16x16 style), dout carries 2 extra coord channels
+    for (h, w, S) in ((30, 40, 20), (15, 20, 16), (12, 16, 24)):
+        dout = torch.randn(B, S, S, Cc + 64, generator=g).to(tdt)
+        xr = torch.zeros(B, Cc, h, w, requires_grad=True)
+        F.interpolate(xr, size=(S, S), mode="bilinear", align_corners=False).backward(dout[..., :Cc].float().permute(0, 3, 1, 2))
+        din32 = torch.zeros(B, h, w, Cc, device=DEV)
+        ops.resize_bilinear_bwd(dout.to(DEV), din32, dt)
+        torch.cuda.synchronize()
+        r[f"resize_{h}x{w}_{S}"] = _chk("resize bwd", din32, xr.grad.permute(0, 2, 3, 1), 1e-4)
+    return r
+
+
+def run_reflect_dgrad_case(seed=0, up=1, B=2, H=9, W=12, Cc=64, N=128, accumulate=False):
+    """Input gradient of [nearest x2 ->] ReflectionPad2d(1) -> conv3x3: contraction with zero padding 2, then the fold."""
+    g = torch.Generator().manual_seed(seed)
+    tdt, dt = torch.bfloat16, L.PRN_BF16
+    w = (torch.randn(N, Cc, 3, 3, generator=g) / (N * 9) ** 0.5).to(tdt)
+    He, We = H * up, W * up
+    dy = torch.randn(B, He, We, N, generator=g).to(tdt)
+    prev = torch.randn(B, H, W, Cc, generator=g).to(tdt) if accumulate else None
+    xr = torch.zeros(B, Cc, H, W, requires_grad=True)
+    xi = F.interpolate(xr, scale_factor=2, mode="nearest") if up == 2 else xr
+    F.conv2d(F.pad(xi, (1, 1, 1, 1), mode="reflect"), w.float()).backward(dy.float().permute(0, 3, 1, 2))
+    ref = xr.grad.permute(0, 2, 3, 1)
+    if accumulate:
+        ref = ref + prev.float()
+    wp = ops.pack_dgrad_weight(w.float(), dtype=dt).to(DEV)
+    dpad = torch.empty(B, He + 2, We + 2, wp.shape[0], dtype=tdt, device=DEV)
+    ops.conv2d(dy.to(DEV), wp, batch=B, h_in=He, w_in=We, ksize=3, stride=1, pad=2, out16=dpad, dtype=dt)
+    din = prev.to(DEV) if accumulate else torch.empty(B, H, W, Cc, dtype=tdt, device=DEV)
+    ops.reflect_fold(dpad, din, up, accumulate, dt)
+    torch.cuda.synchronize()
+    return {"err": _chk(f"reflect dgrad up{up}", din, ref, 2.0 ** -6)}
+
+
+def run_softplus_case(seed=0, rows=1000):
+    g = torch.Generator().manual_seed(seed)
+    pre = (torch.randn(rows, generator=g) * 3).requires_grad_(True)
+    out = F.softplus(pre)
+    dout = torch.randn(rows, generator=g)
+    out.backward(dout)
+    dpre = torch.empty(rows, 64, dtype=torch.bfloat16, device=DEV)
+    ops.softplus_bwd_pad(dout.to(DEV), out.detach().to(DEV), dpre, L.PRN_BF16)
+    torch.cuda.synchronize()
+    assert float(dpre[:, 1:].float().abs().max()) == 0.0
+    return {"err": _chk("softplus bwd", dpre[:, 0], pre.grad, 2.0 ** -8 + 1e-4)}

@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 LOG = os.path.join(ROOT, "gpurun_out", "train_selftest.log")
 
-GROUPS = ["wgrad0", "dgrad", "bn", "misc", "dcn"]   # "wgrad1" = swapped LBO/SBO probe (expected to fail)
+GROUPS = ["wgrad0", "dgrad", "bn", "misc", "dcn", "heads"]   # "wgrad1" = swapped LBO/SBO probe (expected to fail)
 
 
 def log(msg):
@@ -39,6 +39,12 @@ def run_group(group):
         jobs = [("maxpool_bwd", TC.run_maxpool_bwd_case), ("adds", TC.run_add_cases)]
     elif group == "dcn":
         jobs = [(n, lambda n=n: TC.run_dcn_case(n)) for n in TC.DCN_CASES]
+    elif group == "heads":
+        jobs = [("gn", TC.run_gn_case), ("gn128", lambda: TC.run_gn_case(Cc=128, HW=777, B=2)),
+                ("resample", TC.run_resample_bwd_cases), ("reflect_up1", lambda: TC.run_reflect_dgrad_case(up=1)),
+                ("reflect_up2", lambda: TC.run_reflect_dgrad_case(up=2)),
+                ("reflect_up2_acc", lambda: TC.run_reflect_dgrad_case(up=2, accumulate=True)),
+                ("reflect_3x3", lambda: TC.run_reflect_dgrad_case(up=1, H=3, W=3)), ("softplus", TC.run_softplus_case)]
     ok = 0
     for name, fn in jobs:
         try:
