@@ -214,8 +214,9 @@ class Oracle:
     # ---- planerecnet.py:586-607
     def depth_decoder(self, cs, mask_pred, kernel_pred):
         B = cs[0].shape[0]
-        flat = torch.cat([k.permute(0, 2, 3, 1).reshape(B, -1, NUM_KERNELS) for k in kernel_pred], 1)
-        attn = torch.cat([F.conv2d(mask_pred[b:b + 1], flat[b].view(-1, NUM_KERNELS, 1, 1)) for b in range(B)], 0).sigmoid()
+        # planerecnet.py:589,592: kernels, masks and the sigmoid attention are detached (no gradient into the heads)
+        flat = torch.cat([k.permute(0, 2, 3, 1).reshape(B, -1, NUM_KERNELS) for k in kernel_pred], 1).detach()
+        attn = torch.cat([F.conv2d(mask_pred[b:b + 1].detach(), flat[b].view(-1, NUM_KERNELS, 1, 1)) for b in range(B)], 0).sigmoid().detach()
         self.taps["ppa_sigmoid"] = attn
         attn = self._conv(attn, "depth_decoder.conv1x1.0")
         attn = F.interpolate(attn, scale_factor=0.25, mode="bilinear", align_corners=False, recompute_scale_factor=False)

@@ -73,6 +73,14 @@ class PlaneRecNet(nn.Module):
             self._engine = Engine()
         return self._engine
 
+    @property
+    def train_engine(self):
+        """Executor of the training branch (bf16 activations/gradients, fp32 weight gradients)."""
+        if getattr(self, "_train_engine", None) is None:
+            from .train_engine import TrainEngine
+            self._train_engine = TrainEngine("bf16")
+        return self._train_engine
+
     def set_precision(self, name):
         """'f16' (default: 10-bit mantissa, ~1e-3 end-to-end) or 'bf16' (~1e-2) storage/operand type of the
         tensor-core path; accumulation is fp32 in TMEM either way."""
@@ -89,11 +97,14 @@ class PlaneRecNet(nn.Module):
     def forward(self, x):
         from .utils import timer
         if self.training:
-            if any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
-                raise NotImplementedError(
-                    "training-mode forward (batch-statistics BatchNorm + autograd through the sm_100a kernels) "
-                    "is the next scope row (SURVEY.md §8 a16); call net.eval() or freeze_bn() + forward_dense()")
-            return self.forward_dense(x)
+            # planerecnet.py:101-103: (mask_pred, cate_pred, kernel_pred, depth_pred), autograd-connected through one
+            # node whose backward replays the sm_100a tape (train_engine.py)
+            from .train_engine import forward_train_autograd
+            if torch.is_grad_enabled():
+                return forward_train_autograd(self, x)
+            outs = self.train_engine.forward_train(self, x)
+            self.train_engine.reset()
+            return outs
         with timer.env("dense forward"):
             st = (self.engine.forward_dense_graph if self.use_cuda_graph else self.engine.forward_dense)(self, x, False)
         with timer.env("Inferencing"):
