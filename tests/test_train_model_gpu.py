@@ -1,0 +1,74 @@
+"""Training step through the public module API against autograd through the CPU oracle.
+
+What is compared and why (tolerances are measured values with ~2x margin, stated per assert):
+  * single bottlenecks with batch-statistics BatchNorm, identical inputs: every gradient, rel-L2;
+  * whole model with frozen (running-statistics) BatchNorm: stable network -> tight gradient cosine; this pins the
+    whole tape (every dgrad / wgrad / resampler / norm backward and every gradient join);
+  * whole model with batch-statistics BatchNorm on a residual-dominant init: outputs and gradient cosine.  (On the
+    plain random init the train-mode network is chaotic in the fp32 oracle itself — see train_cases._build.)
+Gradients of a 16-bit training step are compared by cosine / rel-L2 (SURVEY §7 "hard parts" (c)), not element-wise."""
+import pytest
+import torch
+
+import train_cases as TC
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["bf16", "f16"])
+def test_bottleneck_blocks_train_bn(cuda_lib, prec):
+    net = TC._build("PlaneRecNet_50_config").train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    lim_all, lim_last, lim_out = (0.30, 0.05, 2.5e-2) if prec == "bf16" else (0.20, 8e-3, 4e-3)
+    for (s, b) in ((0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (3, 0), (3, 2)):     # plain / DCN, stride 1 / 2, +- projection
+        r = TC.run_block_check(s, b, prec=prec, net=net, sd=sd)
+        assert r["out"] <= lim_out, (s, b, r)
+        assert r["conv3.weight"] <= lim_last and r["bn3.weight"] <= lim_last, (s, b, r)
+        assert max(r.values()) <= lim_all, (s, b, r)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset,B", [("PlaneRecNet_50_config", 2), ("PlaneRecNet_101_config", 1)])
+def test_model_step_frozen_bn(cuda_lib, preset, B):
+    r = TC.run_model_check(preset, B=B, prec="bf16", bn_mode="frozen", cond=False)
+    assert not r["missing"], r["missing"]
+    assert max(r["outs"]) <= 2.5e-2, r["outs"]                 # bf16 forward, eval-BN: north_star's 1e-2-class bar
+    assert r["all_cos"] >= 0.9995 and r["all_rel"] <= 0.03, (r["all_cos"], r["all_rel"])
+    assert min(c for c, _ in r["fam"].values()) >= 0.985, r["fam"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["bf16", "f16"])
+def test_model_step_train_bn(cuda_lib, prec):
+    r = TC.run_model_check("PlaneRecNet_50_config", prec=prec, bn_mode="train", cond=True)
+    assert not r["missing"], r["missing"]
+    out_lim, cos_lim, bb_lim = (7e-2, 0.995, 0.70) if prec == "bf16" else (1e-2, 0.999, 0.92)
+    assert max(r["outs"]) <= out_lim, r["outs"]
+    assert r["all_cos"] >= cos_lim, r["all_cos"]
+    for f in ("inst_head.cate_tower", "inst_head.kernel_tower", "mask_head.convs_all_levels", "fpn.fpn_convs"):
+        assert r["fam"][f][0] >= 0.985, (f, r["fam"][f])
+    assert r["fam"]["backbone.layers"][1] >= bb_lim, r["fam"]["backbone.layers"]
+    # running statistics follow torch's update rule (momentum, unbiased variance), num_batches_tracked advanced
+    st, sd0 = r["state"], r["sd0"]
+    assert int(st["backbone.bn1.num_batches_tracked"]) == int(sd0["backbone.bn1.num_batches_tracked"]) + 1
+    rm0, rm1 = sd0["backbone.bn1.running_mean"], st["backbone.bn1.running_mean"].cpu()
+    assert float((rm1 - rm0).abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_running_stats_match_torch(cuda_lib):
+    """backbone.bn1 after one training forward == nn.BatchNorm2d's update on the fp32 stem output."""
+    from oracle import prn_oracle as O
+    net = TC._build("PlaneRecNet_50_config").train()
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(3))
+    netc = net.cuda()
+    with torch.no_grad():
+        netc(x.cuda())
+    o = O.Oracle(sd0, "PlaneRecNet_50_config")
+    y = o._conv(x, "backbone.conv1", 2, 3)
+    rm, rv = sd0["backbone.bn1.running_mean"].clone(), sd0["backbone.bn1.running_var"].clone()
+    torch.nn.functional.batch_norm(y, rm, rv, None, None, True, 0.1, 1e-5)
+    got_m, got_v = netc.backbone.bn1.running_mean.cpu(), netc.backbone.bn1.running_var.cpu()
+    assert float((got_m - rm).abs().max()) <= 2e-3 * float(rm.abs().max() + 1)
+    assert float((got_v - rv).abs().max()) <= 5e-3 * float(rv.abs().max())

@@ -411,3 +411,114 @@ def run_softplus_case(seed=0, rows=1000):
     torch.cuda.synchronize()
     assert float(dpre[:, 1:].float().abs().max()) == 0.0
     return {"err": _chk("softplus bwd", dpre[:, 0], pre.grad, 2.0 ** -8 + 1e-4)}
+
+
+# ------------------------------------------------------------------------------------------ whole blocks / whole model
+def _build(preset, cond=False, seed=0):
+    from helpers import build_ours, perturb_
+    torch.manual_seed(seed)
+    net = build_ours(preset)
+    perturb_(net)
+    if cond:
+        # residual-dominant regime (like a trained ResNet).  Train-mode BatchNorm on a random init is chaotic: 1e-3
+        # input noise changes C5 by ~100 % in the fp32 oracle itself, which makes element-wise parity meaningless.
+        with torch.no_grad():
+            for k, v in net.state_dict().items():
+                if k.endswith("bn3.weight"):
+                    v.mul_(0.1)
+    return net
+
+
+def run_block_check(s, b, prec="bf16", preset="PlaneRecNet_50_config", B=2, H=16, W=20, net=None, sd=None):
+    """One bottleneck, batch-statistics BatchNorm, forward + backward, against autograd through the CPU oracle on
+    identical 16-bit-rounded inputs.  Loss = quadratic (its cotangent vanishes where the ReLU output does; random
+    cotangents make the per-channel sums cancellation-dominated and sign flips of near-zero outputs dominate them).
+    Returns {name: rel-L2}."""
+    from helpers import rel_l2
+    from oracle import prn_oracle as O
+    from planerecnet_b200.train_engine import TrainEngine
+    if net is None:
+        net = _build(preset).train()
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        net = net.cuda()
+    eng = TrainEngine(prec)
+    blk = net.backbone.layers[s][b]
+    prefix = f"backbone.layers.{s}.{b}"
+    cin = blk.conv1.in_channels
+    stride = 2 if (b == 0 and s > 0) else 1
+    g = torch.Generator().manual_seed(100 * s + b)
+    x = torch.randn(B, cin, H, W, generator=g).relu().to(eng.tdt).float()
+    o = O.Oracle(sd, preset, bn_train=True)
+    for k, v in o.sd.items():
+        if k.startswith(prefix) and v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = o._bottleneck(xr, prefix, stride, o.flags[s][b], b == 0)
+    wgt = 1.0 / ref[0].numel() ** 0.5
+    (0.5 * wgt * ref * ref).sum().backward()
+    eng.reset()
+    tin = eng.to_nhwc(x.cuda())
+    out = eng.bottleneck_t(tin, blk)
+    eng._set_grad(out, eng.to_nhwc(eng.to_nchw(out, ref.shape[1]) * wgt))
+    grads = eng.backward_keep_inputs(tin)
+    res = {"out": rel_l2(eng.to_nchw(out, ref.shape[1]).cpu(), ref.detach()),
+           "dx": rel_l2(eng.to_nchw(grads["dx"], cin).cpu(), xr.grad)}
+    refg = {n: o.sd[prefix + "." + n].grad for n, _ in blk.named_parameters()}
+    gmax = max(float(v.norm()) for v in refg.values() if v is not None)
+    for n, p in blk.named_parameters():
+        gr = refg[n]
+        if gr is None or float(gr.norm()) < 1e-5 * gmax:      # conv bias in front of a batch-stat BatchNorm: exactly 0
+            continue
+        res[n] = rel_l2(grads["params"][id(p)].cpu(), gr)
+    return res
+
+
+def run_model_check(preset="PlaneRecNet_50_config", B=2, H=128, W=160, prec="bf16", bn_mode="train", cond=True):
+    """Whole training step through net(x) + loss.backward() against autograd through the CPU oracle.
+    Returns dict(outs=[rel-L2 per output], all_cos, all_rel, fam={family: (min cos, mean cos)}, missing=[...])."""
+    from helpers import rel_l2
+    from oracle import prn_oracle as O
+    from planerecnet_b200.train_engine import TrainEngine
+    net = _build(preset, cond=cond).train()
+    if bn_mode == "frozen":       # running statistics, affine parameters still trainable
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, H, W, generator=g)
+    netc = net.cuda()
+    netc._train_engine = TrainEngine(prec)
+    outs_t = netc(x.cuda())
+    outs = [outs_t[0]] + list(outs_t[1]) + list(outs_t[2]) + [outs_t[3]]
+    wts = [1.0 / o[0].numel() ** 0.5 for o in outs]
+    sum((0.5 * c * a * a).sum() for a, c in zip(outs, wts)).backward()
+    torch.cuda.synchronize()
+    ours = {n: p.grad.float().cpu() for n, p in netc.named_parameters() if p.grad is not None}
+    o = O.Oracle(sd0, preset, bn_train=(bn_mode == "train"))
+    for k, v in o.sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+    mask, cate, kern, depth = o.forward_dense(x)
+    flat = [mask] + list(cate) + list(kern) + [depth]
+    sum((0.5 * c * a * a).sum() for a, c in zip(flat, wts)).backward()
+    ref = {k: v.grad for k, v in o.sd.items() if v.is_floating_point() and v.grad is not None}
+    r = {"outs": [rel_l2(a.detach().float().cpu(), b.detach()) for a, b in zip(outs, flat)], "missing": [], "fam": {},
+         "launches": netc.train_engine.launches, "state": netc.state_dict(), "sd0": sd0}
+    gmax = max(float(v.norm()) for v in ref.values())
+    fam, av, bv = {}, [], []
+    for k, gr in ref.items():
+        if float(gr.norm()) < 1e-5 * gmax:
+            continue
+        if k not in ours:
+            r["missing"].append(k)
+            continue
+        a, b = ours[k].double().flatten(), gr.double().flatten()
+        fam.setdefault(".".join(k.split(".")[:2]), []).append(float((a @ b) / (a.norm() * b.norm() + 1e-30)))
+        av.append(a)
+        bv.append(b)
+    a, b = torch.cat(av), torch.cat(bv)
+    r["all_cos"] = float((a @ b) / (a.norm() * b.norm()))
+    r["all_rel"] = float((a - b).norm() / b.norm())
+    r["fam"] = {f: (min(v), sum(v) / len(v)) for f, v in fam.items()}
+    return r
