@@ -144,6 +144,10 @@ int prn_nchw_f32_to_nhwc(const float* src, void* dst16, int32_t batch, int32_t h
 int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, float bias, float* out, int32_t batch, int32_t h,
                             int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream);
 
+/* Same with the bias read from device memory at run time (a captured training step must see the optimizer's updates). */
+int prn_conv3x3_to1_reflect_devbias(const void* in16, const float* weight9c, const float* bias_dev, float* out, int32_t batch,
+                                    int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream);
+
 /* ---- inference bookkeeping (planerecnet.py:106-107, 182-289; models/functions/nms.py:8-12) --------- */
 
 /* scores = point_nms(sigmoid(logits)): logits fp32 [B, total, ld] with rows level-major then (y,x) and the first

@@ -217,20 +217,40 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
       }
     }
   } else if (d.stats != nullptr) {
-    // BatchNorm batch statistics: per-channel sums over all rows
+    // BatchNorm batch statistics: per-channel {sum, sumsq} over the warp's 32 rows.  Butterfly reduce-scatter over
+    // the lanes (W-1 shuffles per quantity instead of 5*W): after the halving steps lane l holds the total of column
+    // bits(l), and every lane issues one atomic per quantity.
+    float s1[W], s2[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      float s1 = valid ? x[j] : 0.f;
-      float s2 = s1 * s1;
+      s1[j] = valid ? x[j] : 0.f;
+      s2[j] = s1[j] * s1[j];
+    }
+    int col = 0;
+    int off = 16;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int n = W; n > 1; n >>= 1) {
+      const bool hi = (lane & off) != 0;
+      const int h = n >> 1;
+#pragma unroll
+      for (int i = 0; i < W / 2; ++i) {
+        if (i < h) {
+          const float k1 = hi ? s1[h + i] : s1[i], t1 = hi ? s1[i] : s1[h + i];
+          const float k2 = hi ? s2[h + i] : s2[i], t2 = hi ? s2[i] : s2[h + i];
+          s1[i] = k1 + __shfl_xor_sync(0xffffffffu, t1, off);
+          s2[i] = k2 + __shfl_xor_sync(0xffffffffu, t2, off);
+        }
       }
-      if (lane == 0) {
-        atomicAdd(d.stats + static_cast<size_t>(col0 + j) * 2, s1);
-        atomicAdd(d.stats + static_cast<size_t>(col0 + j) * 2 + 1, s2);
-      }
+      col += hi ? h : 0;
+      off >>= 1;
+    }
+    if constexpr (W == 16) {        // 16 columns over 32 lanes: lane pairs hold the two halves of a column's total
+      s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+      s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+    }
+    if (W == 32 || (lane & 1) == 0) {
+      atomicAdd(d.stats + static_cast<size_t>(col0 + col) * 2, s1[0]);
+      atomicAdd(d.stats + static_cast<size_t>(col0 + col) * 2 + 1, s2[0]);
     }
   }
   act_apply<W>(x, d.act, d.act_param, col0);

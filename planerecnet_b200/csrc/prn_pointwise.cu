@@ -477,7 +477,7 @@ constexpr int kD1Tile = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(kD1Tile * kD1Tile)
-conv3x3_to1_kernel(const T* __restrict__ in, const float* __restrict__ wgt /*[9][C] fp32*/, float bias,
+conv3x3_to1_kernel(const T* __restrict__ in, const float* __restrict__ wgt /*[9][C] fp32*/, float bias_host, const float* __restrict__ bias_dev,
                    float* __restrict__ out, int B, int H, int W, int C, int softplus) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int pstride = C * 2 + 16;                          // bytes per staged pixel
@@ -516,7 +516,7 @@ conv3x3_to1_kernel(const T* __restrict__ in, const float* __restrict__ wgt /*[9]
     }
   }
   if (oy < H && ox < W) {
-    float v = acc + bias;
+    float v = acc + (bias_dev != nullptr ? __ldg(bias_dev) : bias_host);
     if (softplus) v = v > 20.f ? v : log1pf(expf(v));
     out[(static_cast<long long>(b) * H + oy) * W + ox] = v;
   }
@@ -524,8 +524,8 @@ conv3x3_to1_kernel(const T* __restrict__ in, const float* __restrict__ wgt /*[9]
 
 }  // namespace prn
 
-extern "C" int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, float bias, float* out, int32_t batch,
-                                       int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream) {
+static int conv3x3_to1_launch(const void* in16, const float* weight9c, float bias, const float* bias_dev, float* out, int32_t batch,
+                              int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream) {
   PRN_REQUIRE(in16 && weight9c && out && batch > 0 && h > 1 && w > 1 && c > 0 && c % 8 == 0 && c <= 128,
               "conv3x3_to1_reflect: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -534,13 +534,25 @@ extern "C" int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, 
   if (dtype == PRN_BF16) {
     static bool cfg = false;
     if (!cfg) { PRN_CUDA(cudaFuncSetAttribute(conv3x3_to1_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; }
-    conv3x3_to1_kernel<__nv_bfloat16><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __nv_bfloat16*>(in16), weight9c, bias, out, batch, h, w, c, softplus);
+    conv3x3_to1_kernel<__nv_bfloat16><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __nv_bfloat16*>(in16), weight9c, bias, bias_dev, out, batch, h, w, c, softplus);
   } else if (dtype == PRN_F16) {
     static bool cfg = false;
     if (!cfg) { PRN_CUDA(cudaFuncSetAttribute(conv3x3_to1_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); cfg = true; }
-    conv3x3_to1_kernel<__half><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __half*>(in16), weight9c, bias, out, batch, h, w, c, softplus);
+    conv3x3_to1_kernel<__half><<<grid, kD1Tile * kD1Tile, smem, st>>>(static_cast<const __half*>(in16), weight9c, bias, bias_dev, out, batch, h, w, c, softplus);
   } else {
     return set_error(PRN_ERR_INVALID, "conv3x3_to1_reflect: bad dtype");
   }
   PRN_LAUNCH_CHECK();
+}
+
+extern "C" int prn_conv3x3_to1_reflect(const void* in16, const float* weight9c, float bias, float* out, int32_t batch,
+                                       int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype, void* stream) {
+  return conv3x3_to1_launch(in16, weight9c, bias, nullptr, out, batch, h, w, c, softplus, dtype, stream);
+}
+
+extern "C" int prn_conv3x3_to1_reflect_devbias(const void* in16, const float* weight9c, const float* bias_dev, float* out,
+                                               int32_t batch, int32_t h, int32_t w, int32_t c, int32_t softplus, int32_t dtype,
+                                               void* stream) {
+  if (!bias_dev) return set_error(PRN_ERR_INVALID, "conv3x3_to1_reflect_devbias: NULL bias");
+  return conv3x3_to1_launch(in16, weight9c, 0.f, bias_dev, out, batch, h, w, c, softplus, dtype, stream);
 }

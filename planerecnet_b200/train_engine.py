@@ -35,6 +35,10 @@ class TrainEngine(Engine):
         self.pgrads = {}       # id(param) -> fp32 gradient in the parameter's shape
         self.pfinal = []       # closures that turn accumulators into parameter gradients after the tape
         self._keep = []        # keeps tokens / tensors alive while their ids are used as keys
+        self._arena = None
+        self._arena_off = 0
+        self._arena_hi = 0
+        self._graphs_t = {}
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
@@ -67,10 +71,29 @@ class TrainEngine(Engine):
         if p is None or not p.requires_grad:
             return
         cur = self.pgrads.get(id(p))
-        self.pgrads[id(p)] = g if cur is None else cur.add_(g)
+        if cur is None:
+            self.pgrads[id(p)] = g                      # may be a view of an accumulator: copied only if joined
+        else:
+            self.pgrads[id(p)] = cur + g
+
+    _ARENA_FLOATS = 4 << 20      # 16 MB of fp32 for the many small zero-initialised accumulators of one step
+    _ARENA_MAX_ITEM = 1 << 16
 
     def _zeros(self, *shape, dtype=torch.float32):
-        return torch.zeros(*shape, dtype=dtype, device="cuda")
+        """Zero-initialised buffer.  Small fp32 accumulators (statistics, per-channel sums) are carved out of one
+        arena that is cleared with a single memset at the start of a step instead of one fill kernel each."""
+        n = 1
+        for d in shape:
+            n *= d
+        if dtype != torch.float32 or n > self._ARENA_MAX_ITEM or self._arena is None:
+            return torch.zeros(*shape, dtype=dtype, device="cuda")
+        n_al = (n + 31) // 32 * 32
+        if self._arena_off + n_al > self._ARENA_FLOATS:
+            return torch.zeros(*shape, dtype=dtype, device="cuda")
+        t = self._arena[self._arena_off:self._arena_off + n].view(*shape)
+        self._arena_off += n_al
+        self._arena_hi = max(self._arena_hi, self._arena_off)
+        return t
 
     # ------------------------------------------------------------------ packed parameters (no BatchNorm folding)
     def _pack_conv_train(self, conv, c_splits, n_pad=None):
@@ -140,7 +163,7 @@ class TrainEngine(Engine):
                 sums = self._zeros(ldy, 2)
                 ops.chan_reduce(dy, None, None, None, sums, self.dt)
                 self.launches += 1
-                self._padd(conv.bias, sums[:cout, 0].clone())
+                self._padd(conv.bias, sums[:cout, 0])
             if conv.weight.requires_grad:
                 dw = self._wbuf(conv, c_splits)
                 with self._timed(f"wgrad{k}x{k}", flops):
@@ -267,8 +290,8 @@ class TrainEngine(Engine):
                 ops.chan_reduce(dz, out if relu else None, y, mi, sums, self.dt)
                 self.launches += 1
             if need_param:
-                self._padd(gamma, sums[:nreal, 1].clone())
-                self._padd(beta, sums[:nreal, 0].clone())
+                self._padd(gamma, sums[:nreal, 1])
+                self._padd(beta, sums[:nreal, 0])
             if not train_stats:
                 sums = self._zeros(Cc, 2)      # frozen statistics: dx = gamma * invstd * g
             dx = self._empty(*y.shape)
@@ -311,8 +334,8 @@ class TrainEngine(Engine):
                 dgb = self.wbufs[key] = self._zeros(Cc, 2)
 
                 def fin():
-                    self._padd(gamma, dgb[:, 1].clone())
-                    self._padd(beta, dgb[:, 0].clone())
+                    self._padd(gamma, dgb[:, 1])
+                    self._padd(beta, dgb[:, 0])
 
                 self.pfinal.append(fin)
             sums_bc = self._zeros(B, Cc, 2)
@@ -375,7 +398,7 @@ class TrainEngine(Engine):
             if reg.bias is not None and reg.bias.requires_grad:
                 sums = self._zeros(n_pad, 2)
                 ops.chan_reduce(dy, None, None, None, sums, self.dt)
-                self._padd(reg.bias, sums[:N, 0].clone())
+                self._padd(reg.bias, sums[:N, 0])
             dw = self._zeros(ops.round_up(N, 4), 9 * Cc)
             with self._timed("wgrad_dcn", flops):
                 ops.conv2d_wgrad(col, dy, dw, batch=B, h_in=Ho, w_in=Wo, n=N, ksize=1, dtype=self.dt)
@@ -389,8 +412,8 @@ class TrainEngine(Engine):
             # offset / modulator conv: bias, weight and input gradients
             sums = self._zeros(64, 2)
             ops.chan_reduce(dpre, None, None, None, sums, self.dt)
-            self._padd(m.offset_conv.bias, sums[:18, 0].clone())
-            self._padd(m.modulator_conv.bias, sums[18:27, 0].clone())
+            self._padd(m.offset_conv.bias, sums[:18, 0])
+            self._padd(m.modulator_conv.bias, sums[18:27, 0])
             dwom = self._zeros(28, 9 * Cc)
             ops.conv2d_wgrad(x, dpre, dwom, batch=B, h_in=H, w_in=W, n=27, ksize=3, stride=stride, pad=pad, dtype=self.dt)
             g27 = ops.unpack_wgrad(dwom, (27, m.offset_conv.in_channels, 3, 3), [(m.offset_conv.in_channels, Cc)])
@@ -670,13 +693,13 @@ class TrainEngine(Engine):
             x = self._rconv_t(skips[k], getattr(dec, f"deconv{k}"), src1=x)
         # depth head 64 -> 1 (+ softplus) on the CUDA cores; its backward goes through the generic contractions
         dconv = dec.depth_pred[1]
-        w9c = self._pack((id(dconv), "to1"), [dconv.weight, dconv.bias],
+        w9c = self._pack((id(dconv), "to1_train"), [dconv.weight, dconv.bias],
                          lambda: (dconv.weight.detach().float()[0].permute(1, 2, 0).reshape(9, -1).contiguous().cuda(),
-                                  float(dconv.bias.detach().float()[0])))
+                                  dconv.bias.detach().float().reshape(1).contiguous().cuda()))
         Bx, Hx, Wx, Cx = x.shape
         d32 = self._empty(Bx, Hx, Wx, 1, dtype=torch.float32)
-        self._call(self.lib.prn_conv3x3_to1_reflect, C.c_void_p(x.data_ptr()), C.c_void_p(w9c[0].data_ptr()), C.c_float(w9c[1]),
-                   C.c_void_p(d32.data_ptr()), Bx, Hx, Wx, Cx, 1, self.dt, self._st())
+        self._call(self.lib.prn_conv3x3_to1_reflect_devbias, C.c_void_p(x.data_ptr()), C.c_void_p(w9c[0].data_ptr()),
+                   C.c_void_p(w9c[1].data_ptr()), C.c_void_p(d32.data_ptr()), Bx, Hx, Wx, Cx, 1, self.dt, self._st())
         xin = x
         tok = object()
         self._keep.append(tok)
@@ -689,7 +712,7 @@ class TrainEngine(Engine):
             ops.softplus_bwd_pad(dout, d32, dpre, self.dt)
             sums = self._zeros(64, 2)
             ops.chan_reduce(dpre, None, None, None, sums, self.dt)
-            self._padd(dconv.bias, sums[:1, 0].clone())
+            self._padd(dconv.bias, sums[:1, 0])
             dw = self._zeros(4, 9 * Cx)
             ops.conv2d_wgrad(xin, dpre, dw, batch=Bx, h_in=Hx, w_in=Wx, n=1, ksize=3, stride=1, pad=1, pad_mode=L.PAD_REFLECT,
                              dtype=self.dt)
@@ -717,7 +740,14 @@ class TrainEngine(Engine):
         return (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
 
     def reset(self):
+        """Start of a step: drop the previous tape and clear the accumulator arena (one memset)."""
         self.tape, self.grads, self.wbufs, self.pgrads, self.pfinal, self._keep = [], {}, {}, {}, [], []
+        if self._arena is None:
+            self._arena = torch.zeros(self._ARENA_FLOATS, dtype=torch.float32, device="cuda")
+            self._arena_hi = 0
+        elif self._arena_hi > 0:
+            self._arena[:self._arena_hi].zero_()
+        self._arena_off = 0
 
     def seed_output_grads(self, d_mask, d_cates, d_kerns, d_depth):
         """Cotangents of the training outputs (NCHW fp32 or None) -> NHWC 16-bit gradients of the dense tensors."""
@@ -755,13 +785,87 @@ class TrainEngine(Engine):
         return grads
 
 
+class GraphedStep:
+    """Forward and backward of one training step captured as two CUDA graphs sharing a memory pool (the ~1300 launches
+    of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
+    optimizer's in-place parameter updates; parameters must keep their storage (true for torch optimizers)."""
+
+    def __init__(self, eng, net, x, pack_in_graph=True):
+        self.eng, self.net = eng, net
+        self.sx = torch.empty_like(x)
+        self.sx.copy_(x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # eager warm-up: function attributes, allocator, first packs
+            outs = eng.forward_train(net, self.sx)
+            eng.seed_output_grads(torch.zeros_like(outs[0]), [torch.zeros_like(c) for c in outs[1]],
+                                  [torch.zeros_like(k) for k in outs[2]], torch.zeros_like(outs[3]))
+            eng.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats]
+        self.g_fwd = torch.cuda.CUDAGraph()
+        n0 = eng.launches
+        with torch.cuda.graph(self.g_fwd):
+            if pack_in_graph:
+                eng._packed.clear()
+            self.outs = eng.forward_train(net, self.sx)
+        self.fwd_launches = eng.launches - n0
+        m, cs, ks, d = self.outs
+        self.cots = (torch.zeros_like(m), [torch.zeros_like(c) for c in cs], [torch.zeros_like(k) for k in ks], torch.zeros_like(d))
+        self.g_bwd = torch.cuda.CUDAGraph()
+        n0 = eng.launches
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+            eng.seed_output_grads(*self.cots)
+            self.grads = eng.backward()
+        self.bwd_launches = eng.launches - n0
+
+    def forward(self, x):
+        self.sx.copy_(x, non_blocking=True)
+        self.g_fwd.replay()
+        self.eng.launches += self.fwd_launches
+        for bn in self.bns:      # the replay updated the running statistics through raw pointers
+            torch.autograd.graph.increment_version(bn.running_mean)
+            torch.autograd.graph.increment_version(bn.running_var)
+        return self.outs
+
+    def backward(self, d_mask, d_cates, d_kerns, d_depth):
+        def put(dst, src):
+            if src is None:
+                dst.zero_()
+            else:
+                dst.copy_(src, non_blocking=True)
+
+        put(self.cots[0], d_mask)
+        for dst, src in zip(self.cots[1], d_cates):
+            put(dst, src)
+        for dst, src in zip(self.cots[2], d_kerns):
+            put(dst, src)
+        put(self.cots[3], d_depth)
+        self.g_bwd.replay()
+        self.eng.launches += self.bwd_launches
+        return self.grads
+
+
 class _DenseTrainFn(torch.autograd.Function):
     """Autograd boundary of the training branch: one node whose backward runs the sm_100a tape."""
 
     @staticmethod
     def forward(ctx, net, x, *params):
         eng = net.train_engine
-        mask, cates, kerns, depth = eng.forward_train(net, x)
+        ctx.step = None
+        if getattr(net, "use_train_graph", False):
+            key = (id(net), tuple(x.shape), tuple(p.requires_grad for p in params),
+                   tuple(m.training for m in net.modules() if isinstance(m, nn.BatchNorm2d)))
+            step = eng._graphs_t.get(key)
+            if step is None:
+                step = eng._graphs_t[key] = GraphedStep(eng, net, x)
+            mask, cates, kerns, depth = step.forward(x)
+            # the graph's static buffers are overwritten by the next step: hand out copies
+            mask, cates, kerns, depth = mask.clone(), [c.clone() for c in cates], [k.clone() for k in kerns], depth.clone()
+            ctx.step = step
+        else:
+            mask, cates, kerns, depth = eng.forward_train(net, x)
         ctx.eng, ctx.params = eng, params
         ctx.nl = len(cates)
         return (mask, *cates, *kerns, depth)
@@ -769,12 +873,17 @@ class _DenseTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *cots):
         eng, nl = ctx.eng, ctx.nl
-        eng.seed_output_grads(cots[0], cots[1:1 + nl], cots[1 + nl:1 + 2 * nl], cots[1 + 2 * nl])
-        g = eng.backward()
+        args = (cots[0], cots[1:1 + nl], cots[1 + nl:1 + 2 * nl], cots[1 + 2 * nl])
+        if ctx.step is not None:
+            g = ctx.step.backward(*args)
+        else:
+            eng.seed_output_grads(*args)
+            g = eng.backward()
         out = []
         for p in ctx.params:
             gp = g.get(id(p))
-            out.append(gp.to(p.dtype) if gp is not None and p.requires_grad else None)
+            # copies: the accumulators (and, when graphed, the static buffers) are reused by the next step
+            out.append(gp.to(p.dtype, copy=True).contiguous() if gp is not None and p.requires_grad else None)
         return (None, None, *out)
 
 

@@ -72,3 +72,45 @@ def test_running_stats_match_torch(cuda_lib):
     got_m, got_v = netc.backbone.bn1.running_mean.cpu(), netc.backbone.bn1.running_var.cpu()
     assert float((got_m - rm).abs().max()) <= 2e-3 * float(rm.abs().max() + 1)
     assert float((got_v - rv).abs().max()) <= 5e-3 * float(rv.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bn_mode", ["frozen", "train"])
+def test_graphed_step_matches_eager_and_follows_optimizer(cuda_lib, bn_mode):
+    """The two-graph replay of a step gives the eager step's gradients, and — because weight packing is captured too —
+    keeps doing so after an in-place optimizer update.  With frozen statistics the network is stable and the two agree to
+    fp32-atomics noise; with batch statistics run-to-run noise (atomic order -> 16-bit rounding flips, amplified by the
+    train-mode network) is measured on the eager path itself and bounds the comparison."""
+    from helpers import rel_l2
+    net = TC._build("PlaneRecNet_50_config", cond=True).train()
+    if bn_mode == "frozen":
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+    net = net.cuda()
+    x = torch.randn(2, 3, 128, 160, generator=torch.Generator().manual_seed(5)).cuda()
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        m, cs, ks, d = net(x)
+        outs = [m] + list(cs) + list(ks) + [d]
+        sum((0.5 * a * a).sum() / a[0].numel() ** 0.5 for a in outs).backward()
+        return torch.cat([p.grad.flatten().float() for p in net.parameters() if p.grad is not None]).clone()
+
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    net.use_train_graph = False
+    g_eager0 = step()
+    noise = rel_l2(step(), g_eager0)          # run-to-run noise floor of the eager path
+    opt.step()
+    g_eager1 = step()
+    net.load_state_dict(state)
+    net.use_train_graph = True
+    g_graph0 = step()          # captures
+    opt.step()
+    g_graph1 = step()          # replays with the updated parameters
+    tol = max(3 * noise, 1e-4 if bn_mode == "frozen" else 1e-3)
+    print(f"bn={bn_mode} eager run-to-run {noise:.2e} graph-vs-eager {rel_l2(g_graph0, g_eager0):.2e} {rel_l2(g_graph1, g_eager1):.2e}")
+    assert rel_l2(g_graph0, g_eager0) <= tol, (rel_l2(g_graph0, g_eager0), noise)
+    assert rel_l2(g_graph1, g_eager1) <= tol, (rel_l2(g_graph1, g_eager1), noise)
+    assert rel_l2(g_eager1, g_eager0) > 3 * tol or bn_mode == "train"      # the update did change the gradients
