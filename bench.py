@@ -27,6 +27,10 @@ METRIC = "images/sec 480x640 ResNet101-DCN dense forward"
 H_IMG, W_IMG = 480, 640
 # algorithmic GFLOP per image of the conv-like contractions as the reference executes them
 ALGO_GF = {"PlaneRecNet_101_config": 294.31, "PlaneRecNet_50_config": 249.30}
+# training step fwd+bwd: as the reference executes it / as we execute it (the plane-prior attention is
+# evaluated only at the pixels its x0.25 resize reads, forward and weight gradient alike)
+ALGO_GF_TRAIN = {"PlaneRecNet_101_config": 808.2, "PlaneRecNet_50_config": 673.2}
+EXEC_GF_TRAIN = {"PlaneRecNet_101_config": 725.7, "PlaneRecNet_50_config": 590.7}
 
 
 def parse():
@@ -39,6 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--precision", default="f16", choices=["f16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (fwd+bwd) measurement")
     return ap.parse_args()
 
 
@@ -245,6 +250,66 @@ def main():
                                 "tflops": round(v[0] / (v[1] / 1e3) / 1e12, 1) if v[1] > 0 else None}
                             for k, v in sorted(by.items())}}
 
+    # ---------------------------------------------------------------- training step: fwd + bwd (+ gradient all-reduce)
+    # net.train() (batch-statistics BatchNorm), model forward + backward driven by fixed seeded
+    # cotangents of the 10 output tensors, bf16 activations/gradients, fp32 weight gradients; the step replays two
+    # captured CUDA graphs (weight packing included).  With N > 1 ranks every step ends with ONE NCCL all-reduce (mean)
+    # over the flat gradient buffer (§8e).
+    train = None
+    if not a.no_train:
+        from planerecnet_b200.train_engine import GraphedStep
+        torch.manual_seed(0)
+        tnet = perturb_(PlaneRecNet(cfg)).train().cuda()
+        teng = tnet.train_engine
+        step = GraphedStep(teng, tnet, x_dev)
+        gen = torch.Generator(device="cuda").manual_seed(1 + rank)
+
+        def mk(t):
+            return torch.randn(t.shape, device="cuda", generator=gen) / t[0].numel() ** 0.5
+
+        m_, cs_, ks_, d_ = step.outs
+        cots = (mk(m_), [mk(c) for c in cs_], [mk(k) for k in ks_], mk(d_))
+        params = [p for p in tnet.parameters() if p.requires_grad]
+
+        def train_step():
+            step.forward(x_dev)
+            g = step.backward(*cots)
+            if world > 1:
+                flat = torch.cat([g[id(p)].reshape(-1) for p in params if id(p) in g])
+                dist.all_reduce(flat)
+                flat.div_(world)
+            return g
+
+        for _ in range(3):
+            train_step()
+        sync_all()
+        t_steps = max(3, min(a.steps, 10))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(t_steps):
+            train_step()
+        ev[1].record()
+        sync_all()
+        t_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / t_steps
+        ev[0].record()
+        step.forward(x_dev)
+        ev[1].record()
+        step.backward(*cots)
+        ev[2].record()
+        torch.cuda.synchronize()
+        peak, _, how = peaks()
+        ex = EXEC_GF_TRAIN.get(a.preset)
+        train = {"value": round(world * B / (t_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(t_ms, 3),
+                 "fwd_ms": round(ev[0].elapsed_time(ev[1]), 3), "bwd_ms": round(ev[1].elapsed_time(ev[2]), 3), "steps": t_steps,
+                 "dtype": "bf16", "gpu_launches_per_step": step.fwd_launches + step.bwd_launches,
+                 "grad_allreduce": "nccl, 1 flat fp32 buffer / step" if world > 1 else None,
+                 "algorithmic_gflop_per_image": ALGO_GF_TRAIN.get(a.preset), "executed_gflop_per_image": ex,
+                 "tensor_frac_of_peak": round(ex * B / t_ms / peak, 4) if ex else None,
+                 "workload": f"{a.preset} net.train() fwd+bwd bs={B}/GPU 480x640, fixed seeded cotangents (kernel-only step, "
+                             f"no loss/optimizer), 2 CUDA graphs incl. weight packing"}
+        del step, tnet
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r = cpu_reference(a.preset, 2, 1)
@@ -263,7 +328,7 @@ def main():
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": d2h, "steps": e_steps,
                         "path": "net(x) eval: pinned host input -> H2D -> graph forward -> inference bookkeeping -> D2H"},
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "train_step": train}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -25,25 +25,34 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   }
 }
 
+// Channel-stationary threads: a thread keeps its 8 channels (scale/shift in registers) and walks rows with a stride of
+// (total threads / (C/8)); total thread count is a multiple of C/8 (chan_grid).  One 16-byte load per operand and row.
 template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ out, const float* __restrict__ mean_invstd,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, const T* __restrict__ res,
-                                long long rows, int C, int relu) {
+__global__ void __launch_bounds__(kPwThreads) bn_apply_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                            const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const T* __restrict__ res,
+                                                            long long rows, int C, int relu) {
   const int cv = C / 8;
-  const long long total = rows * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
+  const int c = static_cast<int>(gtid % cv) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(mean_invstd + 2 * (c + j) + 1) * __ldg(gamma + c + j);
+    sh[j] = __ldg(beta + c + j) - __ldg(mean_invstd + 2 * (c + j)) * sc[j];
+  }
+  const float lo = relu ? 0.f : -INFINITY;
+  for (long long m = gtid / cv; m < rows; m += rstep) {
     float f[8], r[8];
     load8(x + m * C + c, f);
-    if (res != nullptr) load8(res + m * C + c, r);
+    if (res != nullptr) {
+      load8(res + m * C + c, r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
-      float v = (f[j] - mean) * inv * __ldg(gamma + c + j) + __ldg(beta + c + j);
-      if (res != nullptr) v += r[j];
-      f[j] = relu ? fmaxf(v, 0.f) : v;
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]) + r[j], lo);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), lo);
     }
     store8(out + m * C + c, f);
   }
@@ -53,8 +62,20 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, T* __restrict__ out, co
 // xhat = (x - mean) * invstd (x == NULL: second sum skipped).  Total thread count is a multiple of C/8 so that a
 // thread keeps its 8 channels for all of its rows.
 template <typename T>
-__global__ void chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
-                                   const float* __restrict__ mean_invstd, float* __restrict__ sums, long long rows, int C) {
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = Pack2<T>::unpack(w[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPwThreads) chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out,
+                                                               const T* __restrict__ x, const float* __restrict__ mean_invstd,
+                                                               float* __restrict__ sums, long long rows, int C) {
   extern __shared__ float acc[];   // [C][2]
   const int cv = C / 8;
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
@@ -63,34 +84,69 @@ __global__ void chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict
   const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const int c = static_cast<int>(gtid % cv) * 8;
   const long long rstep = tthreads / cv;
-  float mean[8], inv[8], s1[8], s2[8];
+  // s2 accumulates sum g * x; the normalisation is applied once at the end: sum g*xhat = inv * (s2 - mean * s1)
+  float s1[8], s2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    mean[j] = x != nullptr ? __ldg(mean_invstd + 2 * (c + j)) : 0.f;
-    inv[j] = x != nullptr ? __ldg(mean_invstd + 2 * (c + j) + 1) : 0.f;
-    s1[j] = 0.f;
-    s2[j] = 0.f;
-  }
-  for (long long m = gtid / cv; m < rows; m += rstep) {
-    float g[8], o[8], xv[8];
-    load8(dz + m * C + c, g);
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  // two rows per iteration, all loads issued before the first use (the pass is latency-bound otherwise)
+  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+    const long long m2 = m + rstep;
+    const bool two = m2 < rows;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(dz + m * C + c));
+    const uint4 a1 = two ? __ldg(reinterpret_cast<const uint4*>(dz + m2 * C + c)) : zero4;
+    uint4 b0 = zero4, b1 = zero4, c0 = zero4, c1 = zero4;
     if (out != nullptr) {
-      load8(out + m * C + c, o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      b0 = __ldg(reinterpret_cast<const uint4*>(out + m * C + c));
+      if (two) b1 = __ldg(reinterpret_cast<const uint4*>(out + m2 * C + c));
+    }
+    if (x != nullptr) {
+      c0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
+      if (two) c1 = __ldg(reinterpret_cast<const uint4*>(x + m2 * C + c));
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s1[j] += g[j];
-    if (x != nullptr) {
-      load8(x + m * C + c, xv);
+    for (int r = 0; r < 2; ++r) {
+      float g[8], o[8], xv[8];
+      unpack8<T>(r ? a1 : a0, g);
+      if (out != nullptr) {
+        unpack8<T>(r ? b1 : b0, o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s2[j] = fmaf(g[j], (xv[j] - mean[j]) * inv[j], s2[j]);
+        for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      }
+      unpack8<T>(r ? c1 : c0, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += g[j];
+        s2[j] = fmaf(g[j], xv[j], s2[j]);
+      }
     }
   }
+  if (x != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(acc + 2 * (c + j), s1[j]);
-    atomicAdd(acc + 2 * (c + j) + 1, s2[j]);
+    for (int j = 0; j < 8; ++j) {
+      const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
+      s2[j] = inv * (s2[j] - mean * s1[j]);
+    }
+  }
+  // lanes l, l + cv, l + 2 cv, ... of a warp hold the same channels when cv divides 32: fold them with shuffles first
+  const int lane = threadIdx.x & 31;
+  bool writer = true;
+  if (cv < 32 && (32 % cv) == 0 && (blockDim.x % 32) == 0) {
+    for (int off = 16; off >= cv; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+      }
+    }
+    writer = lane < cv;
+  }
+  if (writer) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(acc + 2 * (c + j), s1[j]);
+      atomicAdd(acc + 2 * (c + j) + 1, s2[j]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(sums + i, acc[i]);
@@ -99,32 +155,37 @@ __global__ void chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict
 // dx = gamma * invstd * (g - sum_g / count - xhat * sum_gxhat / count); optionally g itself is written too (the
 // gradient of the residual branch of a bottleneck: models/backbone.py:69-70)
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
-                                    const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums, T* __restrict__ dx, T* __restrict__ g_out, long long rows,
-                                    int C, float inv_count) {
+__global__ void __launch_bounds__(kPwThreads) bn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ out,
+                                                                const T* __restrict__ x, const float* __restrict__ mean_invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ sums,
+                                                                T* __restrict__ dx, T* __restrict__ g_out, long long rows, int C,
+                                                                float inv_count) {
   const int cv = C / 8;
-  const long long total = rows * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
+  const int c = static_cast<int>(gtid % cv) * 8;
+  // dx = a * g + b * x + k  with  a = gamma*invstd,  b = -a*invstd*sgx,  k = -a*sg - b*mean
+  float ka[8], kb[8], kk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
+    const float sg = __ldg(sums + 2 * (c + j)) * inv_count, sgx = __ldg(sums + 2 * (c + j) + 1) * inv_count;
+    ka[j] = __ldg(gamma + c + j) * inv;
+    kb[j] = -ka[j] * inv * sgx;
+    kk[j] = -ka[j] * sg - kb[j] * mean;
+  }
+  for (long long m = gtid / cv; m < rows; m += rstep) {
     float g[8], o[8], xv[8];
     load8(dz + m * C + c, g);
+    load8(x + m * C + c, xv);
     if (out != nullptr) {
       load8(out + m * C + c, o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
     }
     if (g_out != nullptr) store8(g_out + m * C + c, g);
-    load8(x + m * C + c, xv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float mean = __ldg(mean_invstd + 2 * (c + j)), inv = __ldg(mean_invstd + 2 * (c + j) + 1);
-      const float xhat = (xv[j] - mean) * inv;
-      const float sg = __ldg(sums + 2 * (c + j)) * inv_count, sgx = __ldg(sums + 2 * (c + j) + 1) * inv_count;
-      xv[j] = __ldg(gamma + c + j) * inv * (g[j] - sg - xhat * sgx);
-    }
+    for (int j = 0; j < 8; ++j) xv[j] = fmaf(ka[j], g[j], fmaf(kb[j], xv[j], kk[j]));
     store8(dx + m * C + c, xv);
   }
 }
@@ -381,12 +442,12 @@ __global__ void dcn_col2im_bwd_kernel(const T* __restrict__ x, const float* __re
 // =================================================================================================== C ABI
 using namespace prn;
 
-static int chan_reduce_grid(long long rows, int cv) {
+static int chan_reduce_grid(long long rows, int cv, int rows_per_thread = 8) {
   // total threads must be a multiple of cv: grid multiple of cv / gcd(cv, 256)
   int a = cv, b = kPwThreads;
   while (b) { const int t = a % b; a = b; b = t; }
   const int g0 = cv / a;
-  long long want = (rows * cv + kPwThreads * 8LL - 1) / (kPwThreads * 8LL);   // ~8 rows per thread
+  long long want = (rows * cv + kPwThreads * static_cast<long long>(rows_per_thread) - 1) / (kPwThreads * static_cast<long long>(rows_per_thread));
   const long long cap = static_cast<long long>(sm_count()) * 8;
   if (want > cap) want = cap;
   long long grid = want / g0 * g0;
@@ -409,10 +470,10 @@ int prn_bn_apply(const void* x16, void* out16, const float* mean_invstd, const f
                  const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream) {
   PRN_REQUIRE(x16 && out16 && mean_invstd && gamma && beta && rows > 0 && c > 0 && c % 8 == 0, "bn_apply: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long work = rows * (c / 8);
+  const int grid = chan_reduce_grid(rows, c / 8, 4);
   PRN_DISPATCH(dtype,
-               (bn_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), static_cast<__nv_bfloat16*>(out16), mean_invstd, gamma, beta, static_cast<const __nv_bfloat16*>(residual16), rows, c, relu)),
-               (bn_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(x16), static_cast<__half*>(out16), mean_invstd, gamma, beta, static_cast<const __half*>(residual16), rows, c, relu)));
+               (bn_apply_kernel<__nv_bfloat16><<<grid, kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), static_cast<__nv_bfloat16*>(out16), mean_invstd, gamma, beta, static_cast<const __nv_bfloat16*>(residual16), rows, c, relu)),
+               (bn_apply_kernel<__half><<<grid, kPwThreads, 0, st>>>(static_cast<const __half*>(x16), static_cast<__half*>(out16), mean_invstd, gamma, beta, static_cast<const __half*>(residual16), rows, c, relu)));
   PRN_LAUNCH_CHECK();
 }
 
@@ -433,11 +494,11 @@ int prn_bn_bwd_apply(const void* dz16, const void* out16, const void* x16, const
                      const float* sums, void* dx16, void* g_out16, int64_t rows, int32_t c, int32_t dtype, void* stream) {
   PRN_REQUIRE(dz16 && x16 && mean_invstd && gamma && sums && dx16 && rows > 0 && c > 0 && c % 8 == 0, "bn_bwd_apply: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long work = rows * (c / 8);
+  const int grid = chan_reduce_grid(rows, c / 8, 4);
   const float inv_count = 1.0f / static_cast<float>(rows);
   PRN_DISPATCH(dtype,
-               (bn_bwd_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), mean_invstd, gamma, sums, static_cast<__nv_bfloat16*>(dx16), static_cast<__nv_bfloat16*>(g_out16), rows, c, inv_count)),
-               (bn_bwd_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), mean_invstd, gamma, sums, static_cast<__half*>(dx16), static_cast<__half*>(g_out16), rows, c, inv_count)));
+               (bn_bwd_apply_kernel<__nv_bfloat16><<<grid, kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), mean_invstd, gamma, sums, static_cast<__nv_bfloat16*>(dx16), static_cast<__nv_bfloat16*>(g_out16), rows, c, inv_count)),
+               (bn_bwd_apply_kernel<__half><<<grid, kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), mean_invstd, gamma, sums, static_cast<__half*>(dx16), static_cast<__half*>(g_out16), rows, c, inv_count)));
   PRN_LAUNCH_CHECK();
 }
 

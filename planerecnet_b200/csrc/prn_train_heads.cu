@@ -72,40 +72,45 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restri
   }
 }
 
-// pass 2: dx = rstd * (g*gamma - mean_grp(g*gamma) - xhat * mean_grp(g*gamma*xhat)), group means from sums_bc
+// pass 2: dx = rstd * (g*gamma - mean_grp(g*gamma) - xhat * mean_grp(g*gamma*xhat)), group means from sums_bc.
+// Channel-stationary threads per image (blockIdx.y): dx = a*g + b*x + k with per-(image, channel) constants in registers.
 template <typename T>
-__global__ void gn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
-                                    const float* __restrict__ stats, const float* __restrict__ gamma,
-                                    const float* __restrict__ sums_bc, T* __restrict__ dx, int B, int HW, int C, int cg, float eps) {
+__global__ void __launch_bounds__(kPwThreads) gn_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ out,
+                                                                const T* __restrict__ x, const float* __restrict__ stats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ sums_bc,
+                                                                T* __restrict__ dx, int B, int HW, int C, int cg, float eps) {
   const int cv = C / 8, G = C / cg;
+  const int b = blockIdx.y;
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
-  const long long total = static_cast<long long>(B) * HW * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int b = static_cast<int>(m / HW);
-    float g[8], o[8], xv[8];
-    load8(dz + m * C + c, g);
-    load8(out + m * C + c, o);
-    load8(x + m * C + c, xv);
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
+  const int c = static_cast<int>(gtid % cv) * 8;
+  float ka[8], kb[8], kk[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int grp = (c + j) / cg;
-      const float m1 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2) * inv_cnt;
-      const float m2 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2 + 1) * inv_cnt;
-      const float rstd = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + eps);
-      float ga = 0.f, gb = 0.f;      // sum over the group's channels of gamma * {a, bq}
-      for (int cc = grp * cg; cc < (grp + 1) * cg; ++cc) {
-        const float gm = __ldg(gamma + cc);
-        ga = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2), ga);
-        gb = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2 + 1), gb);
-      }
-      const float gg = o[j] > 0.f ? g[j] : 0.f;
-      const float xhat = (xv[j] - m1) * rstd;
-      xv[j] = rstd * (gg * __ldg(gamma + c + j) - ga * inv_cnt - xhat * gb * inv_cnt);
+  for (int j = 0; j < 8; ++j) {
+    const int grp = (c + j) / cg;
+    const float m1 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2) * inv_cnt;
+    const float m2 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2 + 1) * inv_cnt;
+    const float rstd = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + eps);
+    float ga = 0.f, gb = 0.f;      // sum over the group's channels of gamma * {a, bq}
+    for (int cc = grp * cg; cc < (grp + 1) * cg; ++cc) {
+      const float gm = __ldg(gamma + cc);
+      ga = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2), ga);
+      gb = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2 + 1), gb);
     }
-    store8(dx + m * C + c, xv);
+    ka[j] = rstd * __ldg(gamma + c + j);
+    kb[j] = -rstd * rstd * gb * inv_cnt;
+    kk[j] = -rstd * ga * inv_cnt - kb[j] * m1;
+  }
+  const long long img = static_cast<long long>(b) * HW;
+  for (long long m = gtid / cv; m < HW; m += rstep) {
+    float g[8], o[8], xv[8];
+    load8(dz + (img + m) * C + c, g);
+    load8(out + (img + m) * C + c, o);
+    load8(x + (img + m) * C + c, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = fmaf(ka[j], o[j] > 0.f ? g[j] : 0.f, fmaf(kb[j], xv[j], kk[j]));
+    store8(dx + (img + m) * C + c, xv);
   }
 }
 
@@ -303,10 +308,19 @@ int prn_gn_bwd_apply(const void* dz16, const void* out16, const void* x16, const
   PRN_REQUIRE(dz16 && out16 && x16 && stats && gamma && sums_bc && dx16 && batch > 0 && hw > 0 && c > 0 && c % 8 == 0 &&
                   ch_per_group > 0 && c % ch_per_group == 0, "gn_bwd_apply: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long work = static_cast<long long>(batch) * hw * (c / 8);
+  const int cv = c / 8;
+  int a = cv, b = kPwThreads;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int g0 = cv / a;
+  long long want = (static_cast<long long>(hw) * cv + kPwThreads * 4LL - 1) / (kPwThreads * 4LL);
+  const long long cap = static_cast<long long>(sm_count()) * 16 / batch + 1;
+  if (want > cap) want = cap;
+  long long gx = want / g0 * g0;
+  if (gx < g0) gx = g0;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(batch));
   PRN_DISPATCH(dtype,
-               (gn_bwd_apply_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), stats, gamma, sums_bc, static_cast<__nv_bfloat16*>(dx16), batch, hw, c, ch_per_group, eps)),
-               (gn_bwd_apply_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), stats, gamma, sums_bc, static_cast<__half*>(dx16), batch, hw, c, ch_per_group, eps)));
+               (gn_bwd_apply_kernel<__nv_bfloat16><<<grid, kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), stats, gamma, sums_bc, static_cast<__nv_bfloat16*>(dx16), batch, hw, c, ch_per_group, eps)),
+               (gn_bwd_apply_kernel<__half><<<grid, kPwThreads, 0, st>>>(static_cast<const __half*>(dz16), static_cast<const __half*>(out16), static_cast<const __half*>(x16), stats, gamma, sums_bc, static_cast<__half*>(dx16), batch, hw, c, ch_per_group, eps)));
   PRN_LAUNCH_CHECK();
 }
 

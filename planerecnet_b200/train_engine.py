@@ -35,6 +35,10 @@ class TrainEngine(Engine):
         self.pgrads = {}       # id(param) -> fp32 gradient in the parameter's shape
         self.pfinal = []       # closures that turn accumulators into parameter gradients after the tape
         self._keep = []        # keeps tokens / tensors alive while their ids are used as keys
+        self.side_wgrad = True
+        self._wg_streams = None
+        self._wg_rr = 0
+        self._wg_used = set()
         self._arena = None
         self._arena_off = 0
         self._arena_hi = 0
@@ -166,9 +170,8 @@ class TrainEngine(Engine):
                 self._padd(conv.bias, sums[:cout, 0])
             if conv.weight.requires_grad:
                 dw = self._wbuf(conv, c_splits)
-                with self._timed(f"wgrad{k}x{k}", flops):
-                    ops.conv2d_wgrad(x, dy, dw, batch=B, h_in=H, w_in=W, n=cout, ksize=k, stride=stride, pad=pad,
-                                     pad_mode=pad_mode, upsample=upsample, src1=src1, c0=c0, dtype=self.dt)
+                self._wgrad(f"wgrad{k}x{k}", flops, x, dy, dw, batch=B, h_in=H, w_in=W, n=cout, ksize=k, stride=stride, pad=pad,
+                            pad_mode=pad_mode, upsample=upsample, src1=src1, c0=c0, dtype=self.dt)
             if need_dx:
                 assert ldy % 64 == 0, "input-gradient contraction needs dY rows padded to a multiple of 64 channels"
                 lo = 0
@@ -178,6 +181,38 @@ class TrainEngine(Engine):
 
         self.tape.append(bwd)
         return out
+
+    def _wgrad(self, name, flops, src0, dy, dw, **kw):
+        """Weight-gradient contraction.  It depends on (activation, dY) only and nothing in the backward chain depends
+        on it, so it goes to a side stream where its CTAs fill the SMs that the (often sub-wave) input-gradient and
+        normalisation kernels of the main stream leave idle; joined before the accumulators are unpacked."""
+        if not self.side_wgrad or self.profile is not None:
+            with self._timed(name, flops):
+                ops.conv2d_wgrad(src0, dy, dw, **kw)
+            return
+        main = torch.cuda.current_stream()
+        if self._wg_streams is None:
+            self._wg_streams = [torch.cuda.Stream() for _ in range(2)]
+        st = self._wg_streams[self._wg_rr % len(self._wg_streams)]
+        self._wg_rr += 1
+        ev = torch.cuda.Event()
+        ev.record(main)
+        st.wait_event(ev)
+        with torch.cuda.stream(st):
+            ops.conv2d_wgrad(src0, dy, dw, **kw)
+        for t in (src0, dy, dw, kw.get("src1")):
+            if t is not None:
+                t.record_stream(st)
+        self._wg_used.add(st)
+        self.launches += 1
+
+    def _join_wgrad(self):
+        main = torch.cuda.current_stream()
+        for st in self._wg_used:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        self._wg_used = set()
 
     def _wbuf(self, conv, c_splits):
         key = (id(conv), str(c_splits))
@@ -400,9 +435,8 @@ class TrainEngine(Engine):
                 ops.chan_reduce(dy, None, None, None, sums, self.dt)
                 self._padd(reg.bias, sums[:N, 0])
             dw = self._zeros(ops.round_up(N, 4), 9 * Cc)
-            with self._timed("wgrad_dcn", flops):
-                ops.conv2d_wgrad(col, dy, dw, batch=B, h_in=Ho, w_in=Wo, n=N, ksize=1, dtype=self.dt)
-            self._padd(reg.weight, ops.unpack_wgrad(dw, tuple(reg.weight.shape), [(reg.in_channels, Cc)]))
+            self._wgrad("wgrad_dcn", flops, col, dy, dw, batch=B, h_in=Ho, w_in=Wo, n=N, ksize=1, dtype=self.dt)
+            self.pfinal.append(lambda: self._padd(reg.weight, ops.unpack_wgrad(dw, tuple(reg.weight.shape), [(reg.in_channels, Cc)])))
             dcol = self._empty(B, Ho, Wo, 9 * Cc)
             with self._timed("dgrad_dcn", flops):
                 ops.conv2d(dy, wreg_t, batch=B, h_in=Ho, w_in=Wo, ksize=1, c0=N, out16=dcol, dtype=self.dt)
@@ -415,10 +449,15 @@ class TrainEngine(Engine):
             self._padd(m.offset_conv.bias, sums[:18, 0])
             self._padd(m.modulator_conv.bias, sums[18:27, 0])
             dwom = self._zeros(28, 9 * Cc)
-            ops.conv2d_wgrad(x, dpre, dwom, batch=B, h_in=H, w_in=W, n=27, ksize=3, stride=stride, pad=pad, dtype=self.dt)
-            g27 = ops.unpack_wgrad(dwom, (27, m.offset_conv.in_channels, 3, 3), [(m.offset_conv.in_channels, Cc)])
-            self._padd(m.offset_conv.weight, g27[:18].contiguous())
-            self._padd(m.modulator_conv.weight, g27[18:27].contiguous())
+            self._wgrad("wgrad3x3", 2.0 * B * Ho * Wo * 27 * Cc * 9, x, dpre, dwom, batch=B, h_in=H, w_in=W, n=27, ksize=3,
+                        stride=stride, pad=pad, dtype=self.dt)
+
+            def fin_om():
+                g27 = ops.unpack_wgrad(dwom, (27, m.offset_conv.in_channels, 3, 3), [(m.offset_conv.in_channels, Cc)])
+                self._padd(m.offset_conv.weight, g27[:18])
+                self._padd(m.modulator_conv.weight, g27[18:27])
+
+            self.pfinal.append(fin_om)
             if stride == 1:
                 u = dpre
             else:   # transposed stride-2 conv = stride-1 conv over the zero-inserted gradient
@@ -558,9 +597,8 @@ class TrainEngine(Engine):
             if dy is None or not conv1.weight.requires_grad:
                 return
             dw = self._zeros(64, 192)
-            with self._timed("wgrad7x7", flops):
-                ops.conv2d_wgrad(a, dy, dw, batch=B, h_in=H // 2, w_in=W // 2, n=64, ksize=1, dtype=self.dt)
-            self._padd(conv1.weight, dw[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous())
+            self._wgrad("wgrad7x7", flops, a, dy, dw, batch=B, h_in=H // 2, w_in=W // 2, n=64, ksize=1, dtype=self.dt)
+            self.pfinal.append(lambda: self._padd(conv1.weight, dw[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()))
 
         self.tape.append(bwd)
         t = self.maxpool_t(self.t_bn(y, bb.bn1, True))
@@ -714,9 +752,9 @@ class TrainEngine(Engine):
             ops.chan_reduce(dpre, None, None, None, sums, self.dt)
             self._padd(dconv.bias, sums[:1, 0])
             dw = self._zeros(4, 9 * Cx)
-            ops.conv2d_wgrad(xin, dpre, dw, batch=Bx, h_in=Hx, w_in=Wx, n=1, ksize=3, stride=1, pad=1, pad_mode=L.PAD_REFLECT,
-                             dtype=self.dt)
-            self._padd(dconv.weight, ops.unpack_wgrad(dw, tuple(dconv.weight.shape), [(Cx, Cx)]))
+            self._wgrad("wgrad3x3", 2.0 * Bx * Hx * Wx * Cx * 9, xin, dpre, dw, batch=Bx, h_in=Hx, w_in=Wx, n=1, ksize=3, stride=1,
+                        pad=1, pad_mode=L.PAD_REFLECT, dtype=self.dt)
+            self.pfinal.append(lambda: self._padd(dconv.weight, ops.unpack_wgrad(dw, tuple(dconv.weight.shape), [(Cx, Cx)])))
             self.launches += 3
             self._dgrad(xin, dconv, dpre, 0, Cx, Cx, 3, 1, 1, L.PAD_REFLECT, 1, (Bx, Hx, Wx), 2.0 * Bx * Hx * Wx * Cx * 9)
 
@@ -767,6 +805,7 @@ class TrainEngine(Engine):
         """Like backward(), for partial graphs (tests, per-module use): also returns the gradient of `inputs`."""
         for fn in reversed(self.tape):
             fn()
+        self._join_wgrad()
         for fn in self.pfinal:
             fn()
         dxs = [self._take(t) for t in inputs]
@@ -778,6 +817,7 @@ class TrainEngine(Engine):
         """Replay the tape in reverse; returns {id(param): fp32 gradient}."""
         for fn in reversed(self.tape):
             fn()
+        self._join_wgrad()
         for fn in self.pfinal:
             fn()
         grads = self.pgrads

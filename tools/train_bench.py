@@ -57,10 +57,11 @@ def main():
               "img_per_s": B * 1000.0 / (fwd + bwd), "launches": step.fwd_launches + step.bwd_launches, "capture_s": cap_s,
               "mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}))
         return
-    for it in range(steps + 2):
+    warm = int(os.environ.get('PRN_WARMUP', '2'))
+    for it in range(steps + warm):
         torch.cuda.synchronize()
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        if prof and it == steps + 1:
+        if prof and it == steps + warm - 1:
             eng.profile = []
         l0 = eng.launches
         e0.record()
@@ -74,7 +75,7 @@ def main():
         grads = eng.backward()
         e2.record()
         torch.cuda.synchronize()
-        if it >= 2:
+        if it >= warm:
             times.append((e0.elapsed_time(e1), e1.elapsed_time(e2)))
         nl = eng.launches - l0
         del grads
