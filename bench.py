@@ -275,9 +275,7 @@ def main():
             step.forward(x_dev)
             g = step.backward(*cots)
             if world > 1:
-                flat = torch.cat([g[id(p)].reshape(-1) for p in params if id(p) in g])
-                dist.all_reduce(flat)
-                flat.div_(world)
+                D.allreduce_mean_grads(g, params)      # one NCCL all-reduce over the flat gradient buffer (gloo-tested on CPU)
             return g
 
         for _ in range(3):

@@ -44,3 +44,20 @@ def throughput(images_per_rank_step, steps, elapsed_ms_local, device="cpu"):
     """Whole-job images/s: all ranks' images over the slowest rank's device time."""
     total = sum_over_ranks(images_per_rank_step * steps, device)
     return total / (max_over_ranks(elapsed_ms_local, device) / 1e3)
+
+
+def allreduce_mean_grads(grads, params):
+    """exactly ONE all-reduce (sum, then / world) per training step over the flat gradient buffer.
+    grads: {id(param): tensor}; params: parameters in a fixed (rank-independent) order.  Returns the averaged flat
+    buffer and a {id(param): view} dict into it (identity copy when not initialised / world 1)."""
+    order = [p for p in params if id(p) in grads]
+    flat = torch.cat([grads[id(p)].reshape(-1).float() for p in order])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+        flat.div_(dist.get_world_size())
+    views, off = {}, 0
+    for p in order:
+        n = grads[id(p)].numel()
+        views[id(p)] = flat[off:off + n].view(grads[id(p)].shape)
+        off += n
+    return flat, views

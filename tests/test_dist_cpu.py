@@ -25,7 +25,13 @@ def _worker(rank, world, port, out):
     D.barrier()
     ms = D.max_over_ranks(10.0 + 5.0 * rank)          # slowest rank defines the step time
     thr = D.throughput(8, 4, 100.0 * (rank + 1))       # 2 ranks x 8 images x 4 steps over 200 ms
-    out.put((rank, lo, hi, ms, thr))
+    # the training step's single gradient all-reduce (mean over ranks) on a toy parameter set
+    params = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(1))]
+    grads = {id(params[0]): torch.full((3, 2), float(rank + 1)), id(params[1]): torch.arange(5.0) * (rank + 1)}   # params[2]: no grad
+    flat, views = D.allreduce_mean_grads(grads, params)
+    ok = (flat.numel() == 11 and torch.allclose(views[id(params[0])], torch.full((3, 2), 1.5)) and
+          torch.allclose(views[id(params[1])], torch.arange(5.0) * 1.5) and id(params[2]) not in views)
+    out.put((rank, lo, hi, ms, thr, bool(ok)))
     dist.destroy_process_group()
 
 
@@ -40,7 +46,8 @@ def test_two_rank_sharding_and_timing():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, lo0, hi0, ms0, thr0), (_, lo1, hi1, ms1, thr1) = res
+    assert all(r[5] for r in res)
+    (_, lo0, hi0, ms0, thr0, _), (_, lo1, hi1, ms1, thr1, _) = res
     assert (lo0, hi0, lo1, hi1) == (0, 9, 9, 17)          # contiguous, covers everything, sizes differ by <= 1
     assert ms0 == ms1 == 15.0
     assert abs(thr0 - 320.0) < 1e-9 and thr0 == thr1      # 64 images / 0.2 s
