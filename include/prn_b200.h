@@ -165,6 +165,12 @@ int prn_mask_stats(const float* seg, void* mask16, float* area, float* ssum, int
 int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool, int32_t* boxes, int32_t n_inst, int32_t h,
                           int32_t w, int32_t h_out, int32_t w_out, float thr, void* stream);
 
+/* Greedy mask-NMS (models/functions/nms.py:53-80, selected by nms_type == 'mask', planerecnet.py:249-252) over the
+ * score-sorted candidates of each image: inter fp32 [B][n][n] = mask intersections, area fp32 [B][n], labels int64 [B][n],
+ * valid/keep uint8 [B][n].  keep[j] = valid[j] and no kept earlier candidate of the same label has IoU > thr with j. */
+int prn_mask_nms_greedy(const float* inter, const float* area, const int64_t* labels, const uint8_t* valid, uint8_t* keep,
+                        int32_t batch, int32_t n, float thr, void* stream);
+
 /* ---- training step: backward of the dense path.  The reference has no hand-written backward; these
  *      are torch autograd's gradients of the operator call sites cited above, 16-bit NHWC gradients, fp32 weight gradients. */
 

@@ -289,6 +289,29 @@ def matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=2.0, kernel
     return cate_scores * coef
 
 
+def mask_nms(cate_labels, seg_masks, sum_masks, cate_scores, nms_thr=0.5):
+    """nms.py:53-80: greedy O(n^2) suppression over the score-sorted candidates; returns the bool keep vector."""
+    n = len(cate_scores)
+    if n == 0:
+        return []
+    keep = torch.ones(n, dtype=torch.bool)
+    m = seg_masks.reshape(n, -1).float()
+    for i in range(n - 1):
+        if not keep[i]:
+            continue
+        for j in range(i + 1, n):
+            if not keep[j] or cate_labels[i] != cate_labels[j]:
+                continue
+            inter = (m[i] * m[j]).sum()
+            union = sum_masks[i] + sum_masks[j] - inter
+            if union > 0:
+                if inter / union > nms_thr:
+                    keep[j] = False
+            else:
+                keep[j] = False
+    return keep
+
+
 def inference_single(seg_preds, cate_preds, kernel_preds, depth_pred, ori_size, p=INFER):
     """planerecnet.py:182-289, one image.  seg_preds [1,128,h,w]; cate_preds [3728,2]; kernel_preds [3728,128]."""
     result = {"pred_masks": None, "pred_boxes": None, "pred_classes": None, "pred_scores": None, "pred_depth": None}
@@ -338,8 +361,11 @@ def bookkeeping(seg, cate_scores, cate_labels, strides, p=INFER):
     order = torch.argsort(cate_scores, descending=True)[:p["nms_pre"]]
     seg_masks, seg, sum_masks = seg_masks[order], seg[order], sum_masks[order]
     cate_scores, cate_labels, cand = cate_scores[order], cate_labels[order], cand[order]
-    cate_scores = matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=p["sigma"], kernel=p["kernel"])
-    keep = cate_scores >= p["update_thr"]
+    if p.get("nms_type", "matrix") == "mask":      # planerecnet.py:249-252
+        keep = mask_nms(cate_labels, seg_masks, sum_masks, cate_scores, nms_thr=p["mask_thr"])
+    else:
+        cate_scores = matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=p["sigma"], kernel=p["kernel"])
+        keep = cate_scores >= p["update_thr"]
     if keep.sum() == 0:
         return None
     seg, cate_scores, cate_labels, cand = seg[keep], cate_scores[keep], cate_labels[keep], cand[keep]

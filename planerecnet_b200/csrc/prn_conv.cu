@@ -915,7 +915,7 @@ static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   const uint64_t rows = d.w_rows_total > 0 ? static_cast<uint64_t>(d.w_rows_total) : static_cast<uint64_t>(d.n_pad);
   rc = encode_tmap_2d_sw128(&tm, d.weight, rows, kdim, static_cast<uint32_t>(p.n_tile / p.cluster), d.dtype);
   if (rc != PRN_OK) return rc;
-  const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  const int grid = launch_grid(p);
   CUtensorMap tmo = tm;
   if (p.tma_store) {
     rc = encode_tmap_2d_sw128(&tmo, d.out16, static_cast<uint64_t>(p.m_group), static_cast<uint64_t>(d.n_pad), 32, d.dtype,

@@ -171,3 +171,50 @@ int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- greedy mask-NMS (nms.py:53-80, nms_type == 'mask')
+// One CTA per image over the score-sorted candidates.  inter [B][n][n] fp32 = exact mask intersections (Gram matrix of
+// the 0/1 masks); candidate i, if still kept, removes every later kept j of the same label whose IoU
+// inter/(area_i + area_j - inter) exceeds thr (or whose union is 0), in the reference's i-then-j order.
+namespace prn {
+__global__ void mask_nms_greedy_kernel(const float* __restrict__ inter, const float* __restrict__ area,
+                                       const long long* __restrict__ labels, const unsigned char* __restrict__ valid,
+                                       unsigned char* __restrict__ keep, int n, float thr) {
+  extern __shared__ unsigned char kp[];
+  const int b = blockIdx.x;
+  const float* I = inter + static_cast<long long>(b) * n * n;
+  const float* A = area + static_cast<long long>(b) * n;
+  const long long* Lb = labels + static_cast<long long>(b) * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) kp[j] = valid[static_cast<long long>(b) * n + j];
+  __syncthreads();
+  for (int i = 0; i + 1 < n; ++i) {
+    if (kp[i]) {                      // uniform across the CTA (read after the barrier)
+      const float ai = A[i];
+      const long long li = Lb[i];
+      for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+        if (!kp[j] || Lb[j] != li) continue;
+        const float in = I[static_cast<long long>(i) * n + j];
+        const float un = ai + A[j] - in;
+        if (un > 0.f) {
+          if (in / un > thr) kp[j] = 0;
+        } else {
+          kp[j] = 0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < n; j += blockDim.x) keep[static_cast<long long>(b) * n + j] = kp[j];
+}
+}  // namespace prn
+
+extern "C" int prn_mask_nms_greedy(const float* inter, const float* area, const int64_t* labels, const uint8_t* valid,
+                                   uint8_t* keep, int32_t batch, int32_t n, float thr, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(inter && area && labels && valid && keep && batch > 0 && n > 0 && n <= 48 * 1024, "mask_nms_greedy: bad arguments");
+  mask_nms_greedy_kernel<<<batch, 256, n, static_cast<cudaStream_t>(stream)>>>(inter, area, reinterpret_cast<const long long*>(labels),
+                                                                               valid, keep, n, thr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(PRN_ERR_CUDA, "mask_nms_greedy launch: %s", cudaGetErrorString(e));
+  return PRN_OK;
+}

@@ -104,8 +104,18 @@ def select(scores, seg_fn, strides_all, nc, p):
     a1 = area.gather(1, order)
     l1 = labels.gather(1, order)
     inter1 = gram_fn(order, n_pre)                                # intersections of the sorted survivors only
-    s2 = _decay(inter1, a1, l1, s1, v1, p["sigma"], p["kernel"])  # nms.py
-    keep2 = v1 & (s2 >= p["update_thr"])
+    if p.get("nms_type", "matrix") == "mask":                     # planerecnet.py:249-252: greedy, scores unchanged
+        keep_u8 = torch.empty(B, n_pre, dtype=torch.uint8, device=dev)
+        v1_u8 = v1.to(torch.uint8).contiguous()
+        a1c, l1c = a1.contiguous(), l1.contiguous()
+        L.check(L.lib().prn_mask_nms_greedy(C.c_void_p(inter1.data_ptr()), C.c_void_p(a1c.data_ptr()), C.c_void_p(l1c.data_ptr()),
+                                            C.c_void_p(v1_u8.data_ptr()), C.c_void_p(keep_u8.data_ptr()), B, n_pre,
+                                            C.c_float(p["mask_thr"]), L.current_stream()), "prn_mask_nms_greedy")
+        s2 = s1
+        keep2 = keep_u8.bool()
+    else:
+        s2 = _decay(inter1, a1, l1, s1, v1, p["sigma"], p["kernel"])  # nms.py
+        keep2 = v1 & (s2 >= p["update_thr"])
     key2 = torch.where(keep2, s2, torch.full_like(s2, -1.0))
     order2 = torch.argsort(key2, dim=1, descending=True)[:, :p["top_k"]]
     fin_valid = keep2.gather(1, order2)
@@ -134,9 +144,10 @@ def inference(eng, net, st, x):
     total = inst["cate32"].shape[1]
     lib = eng.lib
     p = dict(score_thr=net.score_threshold, mask_thr=net.mask_threshold, update_thr=net.update_threshold,
-             nms_pre=net.max_before_nms, top_k=net.max_per_img, sigma=net.nms_sigma, kernel=net.nms_kernel)
-    if net.nms_type != "matrix":
-        raise NotImplementedError("nms_type %r (only 'matrix', the presets' default, is implemented)" % net.nms_type)
+             nms_pre=net.max_before_nms, top_k=net.max_per_img, sigma=net.nms_sigma, kernel=net.nms_kernel,
+             nms_type=net.nms_type)
+    if net.nms_type not in ("matrix", "mask"):
+        raise NotImplementedError          # planerecnet.py:253-254
 
     grids = eng._zero_pool.get(("grids", tuple(net.num_grids)))
     if grids is None:

@@ -45,6 +45,22 @@ def test_conv_descriptor_struct_matches_header_layout():
     assert names == [f[0] for f in _lib.PrnConv._fields_]
 
 
+def test_wgrad_descriptor_struct_matches_header_layout():
+    from planerecnet_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "prn_b200.h")).read()
+    body = hdr[hdr.index("typedef struct PrnWgrad {") + len("typedef struct PrnWgrad {"):hdr.index("} PrnWgrad;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        m = re.match(r"(?:const\s+)?(?:void|float|int32_t)\s*\*?\s*(.+)$", decl.strip())
+        if m:
+            names += [n.strip().lstrip("*") for n in m.group(1).split(",")]
+    assert names == [f[0] for f in _lib.PrnWgrad._fields_]
+    d = _lib.PrnWgrad()
+    out8 = (ctypes.c_int32 * 8)()
+    assert _lib.lib().prn_conv2d_wgrad_plan(ctypes.byref(d), out8) == -1      # rejected on the host, no GPU needed
+
+
 def test_invalid_descriptor_is_rejected_without_gpu():
     from planerecnet_b200 import _lib
     l = _lib.lib()
@@ -124,10 +140,26 @@ def test_forward_without_gpu_fails_loudly():
     assert "CUDA" in str(ei.value) or "cuda" in str(ei.value)
 
 
-def test_training_mode_is_explicitly_unsupported():
+def test_training_mode_has_no_cpu_path_either():
+    """net.train() routes to the sm_100a training executor; like the eval path it fails loudly on a CPU tensor."""
+    from planerecnet_b200 import _lib
     net = H.build_ours("PlaneRecNet_50_config").train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises((_lib.PrnError, RuntimeError, AssertionError)):
         net(torch.zeros(1, 3, 64, 64))
+
+
+def test_dgrad_weight_packing_layout():
+    """Input-gradient weights: rows = input channels, K = (ky, kx, cout padded) with the taps flipped."""
+    from planerecnet_b200 import ops, _lib
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)          # [Cout=2, Cin=3, 3, 3]
+    p = ops.pack_dgrad_weight(w, cout_pad=64, n_pad=16, dtype=_lib.PRN_F16)
+    assert p.shape == (16, 9 * 64)
+    # row c, k = (ky*3 + kx)*64 + o holds w[o, c, 2-ky, 2-kx]
+    assert float(p[1, (0 * 3 + 2) * 64 + 1]) == float(w[1, 1, 2, 0])
+    assert p[3:].abs().sum() == 0 and float(p[0, 2]) == 0
+    g = torch.arange(4 * 9 * 64, dtype=torch.float32).reshape(4, 9 * 64)
+    u = ops.unpack_wgrad(g, (2, 3, 3, 3), [(3, 64)])
+    assert u.shape == (2, 3, 3, 3) and float(u[1, 2, 1, 0]) == float(g[1, (1 * 3 + 0) * 64 + 2])
 
 
 def test_weight_packing_layout():

@@ -134,3 +134,15 @@ def test_inference_early_outs_return_none_fields():
     cate[5, 0] = 0.9
     r = O.inference_single(seg - 10.0, cate, torch.ones(3728, 128), depth, (32, 32))
     assert r["pred_scores"] is None
+
+
+def test_mask_nms_matches_reference_golden():
+    """oracle.mask_nms (nms.py:53-80 restated) against the keep vectors of the unmodified reference function
+    (tests/golden/mask_nms.pt, generated by tests/golden/make_mask_nms_golden.py)."""
+    import os
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mask_nms.pt"))
+    assert len(cases) == 6
+    for c in cases:
+        keep = O.mask_nms(c["labels"], c["masks"], c["sums"], c["scores"], nms_thr=c["thr"])
+        assert torch.equal(keep, c["keep"])
+    assert O.mask_nms(torch.zeros(0), torch.zeros(0, 4, 4), torch.zeros(0), torch.zeros(0)) == []

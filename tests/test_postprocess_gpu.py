@@ -138,3 +138,70 @@ def test_upsample_mask_box_kernel(cuda_lib):
     for i in range(3):
         ys, xs = torch.where(got[i])
         assert boxes[i].tolist() == [int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())]
+
+
+def test_mask_nms_kernel_matches_reference_golden(cuda_lib):
+    """prn_mask_nms_greedy on the Gram matrix of the golden masks == the unmodified reference's keep vector."""
+    import os
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mask_nms.pt"))
+    for c in cases:
+        n = c["masks"].shape[0]
+        m = c["masks"].reshape(n, -1).float().cuda()
+        inter = (m @ m.t()).contiguous()[None]
+        keep = torch.empty(1, n, dtype=torch.uint8, device="cuda")
+        valid = torch.ones(1, n, dtype=torch.uint8, device="cuda")
+        L.check(L.lib().prn_mask_nms_greedy(C.c_void_p(inter.data_ptr()), C.c_void_p(c["sums"].cuda().data_ptr()),
+                                            C.c_void_p(c["labels"].long().cuda().data_ptr()), C.c_void_p(valid.data_ptr()),
+                                            C.c_void_p(keep.data_ptr()), 1, n, C.c_float(c["thr"]), L.current_stream()))
+        assert torch.equal(keep[0].bool().cpu(), c["keep"])
+
+
+@pytest.mark.parametrize("seed,n_cand", [(0, 40), (1, 150)])
+def test_selection_with_mask_nms_matches_oracle_exactly(cuda_lib, seed, n_cand):
+    """nms_type == 'mask' (planerecnet.py:249-252) through the batched device selection vs the oracle, same inputs."""
+    B, h, w = 2, 16, 20
+    P = h * w
+    scores, seg_table = _synthetic(B, h, w, seed, n_cand)
+    strides_all = torch.tensor([s for gsz, s in zip(GRIDS, O.INSTANCE_STRIDES) for _ in range(gsz * gsz)], dtype=torch.float32)
+    pm = dict(O.INFER, nms_type="mask")
+    exp = []
+    for b in range(B):
+        cate = scores[b]
+        inds = cate > pm["score_thr"]
+        nz = inds.nonzero(as_tuple=False)
+        seg = seg_table[b, nz[:, 0]].reshape(-1, h, w)
+        det = O.bookkeeping(seg, cate[inds], nz[:, 1], strides_all[nz[:, 0]], p=pm)
+        exp.append(None if det is None else (det[1], det[2], det[0]))
+    from planerecnet_b200.engine import Engine
+    eng = Engine("f16")
+    tab = seg_table.cuda()
+
+    def seg_fn(rows, valid, n):
+        seg32 = tab.gather(1, rows[:, :, None].expand(-1, -1, P)).reshape(B * n, P).contiguous()
+        m16 = torch.empty(B * n, P, dtype=eng.tdt, device="cuda")
+        area = torch.empty(B * n, device="cuda")
+        ssum = torch.empty(B * n, device="cuda")
+        eng._call(eng.lib.prn_mask_stats, C.c_void_p(seg32.data_ptr()), C.c_void_p(m16.data_ptr()), C.c_void_p(area.data_ptr()),
+                  C.c_void_p(ssum.data_ptr()), B * n, P, C.c_float(pm["mask_thr"]), eng.dt, eng._st())
+
+        def gram_fn(order, n1):
+            msel = m16.view(B, n, P).gather(1, order[:, :, None].expand(-1, -1, P))
+            inter = torch.empty(B, n1, n1, device="cuda")
+            ops.conv2d(msel.view(B, n1, 1, P), msel.view(B * n1, P), batch=B, h_in=n1, w_in=1, ksize=1, out32=inter,
+                       ld_out32=n1, n_pad=n1, w_group_rows=n1, dtype=eng.dt)
+            return inter
+
+        return seg32, m16, area, ssum, gram_fn
+
+    p = dict(score_thr=0.1, mask_thr=0.1, update_thr=0.15, nms_pre=500, top_k=100, sigma=2.0, kernel="gaussian", nms_type="mask")
+    dets, seg32 = PP.select(scores.cuda(), seg_fn, strides_all.cuda(), 2, p)
+    for b in range(B):
+        rows, sc, lab = dets[b]
+        if exp[b] is None:
+            assert rows is None
+            continue
+        e_sc, e_lab, e_seg = exp[b]
+        assert rows is not None and rows.numel() == e_sc.numel(), "detection count differs"
+        assert torch.equal(lab.cpu(), e_lab)
+        assert torch.allclose(sc.cpu(), e_sc, rtol=1e-5, atol=1e-6)
+        assert torch.equal(seg32[rows].cpu(), e_seg.reshape(-1, P))
