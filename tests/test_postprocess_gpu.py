@@ -150,10 +150,12 @@ def test_mask_nms_kernel_matches_reference_golden(cuda_lib):
         inter = (m @ m.t()).contiguous()[None]
         keep = torch.empty(1, n, dtype=torch.uint8, device="cuda")
         valid = torch.ones(1, n, dtype=torch.uint8, device="cuda")
-        L.check(L.lib().prn_mask_nms_greedy(C.c_void_p(inter.data_ptr()), C.c_void_p(c["sums"].cuda().data_ptr()),
-                                            C.c_void_p(c["labels"].long().cuda().data_ptr()), C.c_void_p(valid.data_ptr()),
+        sums, labels = c["sums"].cuda(), c["labels"].long().cuda()       # named: the pointers must outlive the call
+        L.check(L.lib().prn_mask_nms_greedy(C.c_void_p(inter.data_ptr()), C.c_void_p(sums.data_ptr()),
+                                            C.c_void_p(labels.data_ptr()), C.c_void_p(valid.data_ptr()),
                                             C.c_void_p(keep.data_ptr()), 1, n, C.c_float(c["thr"]), L.current_stream()))
-        assert torch.equal(keep[0].bool().cpu(), c["keep"])
+        torch.cuda.synchronize()
+        assert torch.equal(keep[0].bool().cpu(), c["keep"]), (n, c["thr"], keep[0].tolist(), c["keep"].tolist())
 
 
 @pytest.mark.parametrize("seed,n_cand", [(0, 40), (1, 150)])
