@@ -187,8 +187,22 @@ def main():
     value = world * B * a.steps / (ms / 1e3)
 
     # ---------------------------------------------------------------- end to end through the public API
-    def e2e_step():
-        xb = x_host.cuda(non_blocking=True)
+    # Serving loop with a double-buffered input: the H2D copy of step i+1 (pinned host memory, copy stream) runs while
+    # step i computes; every step's copy, compute, bookkeeping and D2H lie inside the timed region.
+    copy_stream = torch.cuda.Stream()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            xb = x_host.cuda(non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return xb, ev
+
+    def e2e_step(cur):
+        nxt = prefetch()
+        xb, ev = cur
+        torch.cuda.current_stream().wait_event(ev)
+        xb.record_stream(torch.cuda.current_stream())
         res = net(xb)
         out_bytes = 0
         # device -> host read of the step's result: detections (scores, classes, boxes) and depth maps of all images,
@@ -198,11 +212,12 @@ def main():
             if parts:
                 t = torch.cat(parts).cpu()
                 out_bytes += t.numel() * t.element_size()
-        return out_bytes
+        return out_bytes, nxt
 
     with torch.no_grad():
+        cur = prefetch()
         for _ in range(3):
-            e2e_step()
+            _, cur = e2e_step(cur)
         sync_all()
         e_steps = max(3, min(a.steps, 10))
         t0 = torch.cuda.Event(enable_timing=True)
@@ -210,7 +225,7 @@ def main():
         t0.record()
         d2h = 0
         for _ in range(e_steps):
-            d2h = e2e_step()
+            d2h, cur = e2e_step(cur)
         t1.record()
         sync_all()
         e2e_ms = max_over_ranks(t0.elapsed_time(t1))
@@ -325,7 +340,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": d2h, "steps": e_steps,
-                        "path": "net(x) eval: pinned host input -> H2D -> graph forward -> inference bookkeeping -> D2H"},
+                        "path": "net(x) eval: pinned host input -> H2D (double-buffered on a copy stream) -> graph forward -> inference bookkeeping -> D2H"},
                 "roofline": roof, "cpu_baseline": cpu, "train_step": train}
         print(json.dumps(line))
     if world > 1:
