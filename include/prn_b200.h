@@ -268,6 +268,16 @@ int prn_reflect_fold(const void* dpad16, void* din16, int32_t batch, int32_t h, 
  * (1 - exp(-out[m])), columns 1..63 zero (a 64-channel operand row for the head's gradient contractions). */
 int prn_softplus_bwd_pad(const float* dout, const float* out, void* dpre16, int64_t rows, int32_t dtype, void* stream);
 
+/* Operand packing for the training step (the optimizer rewrites every weight each step): w = fp32 [cout][cin][k][k]
+ * (nn.Conv2d.weight).  Forward / weight-gradient operand: out16[n_pad][k*k*(pad[0]+pad[1])], column (tap, off_s + c) =
+ * w[n][lo[s] + c][tap] for c < real[s], zero padding elsewhere (the layout PrnConv.weight expects; two splits = the two
+ * channel-concatenated sources).  Input-gradient operand: out16[rows_pad][k*k*cout_pad], column (tap, o) of row r =
+ * w[o][lo + r][k*k - 1 - tap] (taps flipped, in/out transposed). */
+int prn_pack_conv_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t n_pad, int32_t nsplit,
+                         const int32_t* lo, const int32_t* real, const int32_t* pad, int32_t dtype, void* stream);
+int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t lo, int32_t hi,
+                          int32_t rows_pad, int32_t cout_pad, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -588,3 +588,86 @@ int prn_dcn_col2im_bwd(const void* x16, const float* offmask, const void* dcol16
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- weight packing (fp32 OIHW parameters -> 16-bit operands)
+// A training step re-packs every weight (the optimizer changed it): one launch per operand instead of a chain of
+// permute / pad / cast kernels.  One CTA per output row, the row's source elements staged through shared memory.
+namespace prn {
+
+struct PackSplit { int lo, real, pad; };
+
+// forward operand: out[n][tap][off_s + c] = w[n][lo_s + c][tap] (c < real_s), zero elsewhere; rows n >= cout are zero
+template <typename T>
+__global__ void pack_fwd_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kk, int cpad_tot,
+                                int nsplit, PackSplit s0, PackSplit s1) {
+  extern __shared__ float row[];   // [cin][kk]
+  const int n = blockIdx.x;
+  T* o = out + static_cast<long long>(n) * kk * cpad_tot;
+  if (n >= cout) {
+    for (int i = threadIdx.x; i < kk * cpad_tot; i += blockDim.x) o[i] = static_cast<T>(0.f);
+    return;
+  }
+  const float* src = w + static_cast<long long>(n) * cin * kk;
+  for (int i = threadIdx.x; i < cin * kk; i += blockDim.x) row[i] = __ldg(src + i);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kk * cpad_tot; i += blockDim.x) {
+    const int tap = i / cpad_tot, c = i - tap * cpad_tot;
+    float v = 0.f;
+    if (c < s0.pad) {
+      if (c < s0.real) v = row[(s0.lo + c) * kk + tap];
+    } else if (nsplit > 1) {
+      const int c1 = c - s0.pad;
+      if (c1 < s1.real) v = row[(s1.lo + c1) * kk + tap];
+    }
+    o[i] = static_cast<T>(v);
+  }
+}
+
+// input-gradient operand: out[r][tap'][o] = w[o][lo + r][kk - 1 - tap'] (o < cout, r < hi - lo), zero elsewhere
+template <typename T>
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ out, int cout, int cin, int kk, int lo, int nreal,
+                                  int cout_pad) {
+  const int r = blockIdx.x;
+  T* o = out + static_cast<long long>(r) * kk * cout_pad;
+  for (int i = threadIdx.x; i < kk * cout_pad; i += blockDim.x) {
+    const int tap = i / cout_pad, oc = i - tap * cout_pad;
+    float v = 0.f;
+    if (r < nreal && oc < cout) v = __ldg(w + (static_cast<long long>(oc) * cin + lo + r) * kk + (kk - 1 - tap));
+    o[i] = static_cast<T>(v);
+  }
+}
+
+}  // namespace prn
+
+extern "C" int prn_pack_conv_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t n_pad,
+                                    int32_t nsplit, const int32_t* lo, const int32_t* real, const int32_t* pad, int32_t dtype,
+                                    void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(w && out16 && lo && real && pad && cout > 0 && cin > 0 && ksize >= 1 && ksize <= 7 && n_pad >= cout &&
+                  (nsplit == 1 || nsplit == 2), "pack_conv_weight: bad arguments");
+  PackSplit s0{lo[0], real[0], pad[0]}, s1{0, 0, 0};
+  if (nsplit == 2) s1 = PackSplit{lo[1], real[1], pad[1]};
+  PRN_REQUIRE(s0.lo >= 0 && s0.real >= 0 && s0.pad >= s0.real && s0.lo + s0.real <= cin && s1.lo + s1.real <= cin && s1.pad >= s1.real,
+              "pack_conv_weight: bad channel split");
+  const int kk = ksize * ksize, cpad_tot = s0.pad + s1.pad;
+  const size_t smem = static_cast<size_t>(cin) * kk * sizeof(float);
+  PRN_REQUIRE(smem <= 48 * 1024, "pack_conv_weight: cin*k*k too large (%d x %d)", cin, kk);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (pack_fwd_kernel<__nv_bfloat16><<<n_pad, 256, smem, st>>>(w, static_cast<__nv_bfloat16*>(out16), cout, cin, kk, cpad_tot, nsplit, s0, s1)),
+               (pack_fwd_kernel<__half><<<n_pad, 256, smem, st>>>(w, static_cast<__half*>(out16), cout, cin, kk, cpad_tot, nsplit, s0, s1)));
+  PRN_LAUNCH_CHECK();
+}
+
+extern "C" int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t lo, int32_t hi,
+                                     int32_t rows_pad, int32_t cout_pad, int32_t dtype, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(w && out16 && cout > 0 && cin > 0 && ksize >= 1 && ksize <= 7 && lo >= 0 && hi > lo && hi <= cin &&
+                  rows_pad >= hi - lo && cout_pad >= cout, "pack_dgrad_weight: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int kk = ksize * ksize;
+  PRN_DISPATCH(dtype,
+               (pack_dgrad_kernel<__nv_bfloat16><<<rows_pad, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(out16), cout, cin, kk, lo, hi - lo, cout_pad)),
+               (pack_dgrad_kernel<__half><<<rows_pad, 256, 0, st>>>(w, static_cast<__half*>(out16), cout, cin, kk, lo, hi - lo, cout_pad)));
+  PRN_LAUNCH_CHECK();
+}

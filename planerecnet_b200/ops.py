@@ -241,3 +241,30 @@ def reflect_fold(dpad, din, upsample, accumulate, dtype):
 def softplus_bwd_pad(dout32, out32, dpre16, dtype):
     L.check(L.lib().prn_softplus_bwd_pad(_vp(dout32), _vp(out32), _vp(dpre16), C.c_int64(out32.numel()), dtype, L.current_stream()),
             "prn_softplus_bwd_pad")
+
+
+def pack_conv_weight_dev(w, c_splits, n_pad, dtype):
+    """prn_pack_conv_weight: same result as pack_conv_weight, one launch, for a CUDA fp32 [Cout,Cin,k,k] parameter."""
+    cout, cin, k, _ = w.shape
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and 1 <= len(c_splits) <= 2
+    los, off = [], 0
+    for real, _ in c_splits:
+        los.append(off)
+        off += real
+    assert off == cin
+    arr = C.c_int32 * len(c_splits)
+    out = torch.empty(n_pad, k * k * sum(p for _, p in c_splits), dtype=torch_dtype(dtype), device="cuda")
+    L.check(L.lib().prn_pack_conv_weight(_vp(w), _vp(out), cout, cin, k, n_pad, len(c_splits), arr(*los),
+                                         arr(*[r for r, _ in c_splits]), arr(*[p for _, p in c_splits]), dtype,
+                                         L.current_stream()), "prn_pack_conv_weight")
+    return out
+
+
+def pack_dgrad_weight_dev(w, lo, hi, rows_pad, cout_pad, dtype):
+    """prn_pack_dgrad_weight: == pack_dgrad_weight(w[:, lo:hi], cout_pad, rows_pad), one launch."""
+    cout, cin, k, _ = w.shape
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    out = torch.empty(rows_pad, k * k * cout_pad, dtype=torch_dtype(dtype), device="cuda")
+    L.check(L.lib().prn_pack_dgrad_weight(_vp(w), _vp(out), cout, cin, k, lo, hi, rows_pad, cout_pad, dtype, L.current_stream()),
+            "prn_pack_dgrad_weight")
+    return out

@@ -43,6 +43,7 @@ class TrainEngine(Engine):
         self._arena_off = 0
         self._arena_hi = 0
         self._graphs_t = {}
+        self._nbt = []
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
@@ -102,9 +103,13 @@ class TrainEngine(Engine):
     # ------------------------------------------------------------------ packed parameters (no BatchNorm folding)
     def _pack_conv_train(self, conv, c_splits, n_pad=None):
         def build():
-            w = conv.weight.detach().float()
+            w = conv.weight.detach()
             npad = n_pad or ops.round_up(w.shape[0], 16)
-            wp = ops.pack_conv_weight(w, c_splits, npad, self.dt).cuda()
+            if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] * w.shape[2] * w.shape[3] * 4 <= 48 * 1024:
+                wp = ops.pack_conv_weight_dev(w, c_splits, npad, self.dt)
+                self.launches += 1
+            else:
+                wp = ops.pack_conv_weight(w.float(), c_splits, npad, self.dt).cuda()
             bp = ops.pad_vec(conv.bias.detach().float(), npad).cuda() if conv.bias is not None else None
             return wp, bp
 
@@ -114,8 +119,11 @@ class TrainEngine(Engine):
         """Weights of the input-gradient contraction for input channels [real_lo, real_hi) padded to rows_pad rows;
         K = (ky, kx, cout padded to cout_pad), taps flipped."""
         def build():
-            w = conv.weight.detach().float()[:, real_lo:real_hi]
-            return ops.pack_dgrad_weight(w, cout_pad=cout_pad, n_pad=rows_pad, dtype=self.dt).cuda()
+            w = conv.weight.detach()
+            if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
+                self.launches += 1
+                return ops.pack_dgrad_weight_dev(w, real_lo, real_hi, rows_pad, cout_pad, self.dt)
+            return ops.pack_dgrad_weight(w.float()[:, real_lo:real_hi], cout_pad=cout_pad, n_pad=rows_pad, dtype=self.dt).cuda()
 
         return self._pack((id(conv), "dgrad", real_lo, real_hi, rows_pad, cout_pad), [conv.weight], build)
 
@@ -300,7 +308,7 @@ class TrainEngine(Engine):
             mom = bn.momentum if bn.momentum is not None else 0.1
             ops.bn_finalize(y._prn_stats, mi, rm, rv, rows, bn.eps, mom)
             if bn.track_running_stats:
-                bn.num_batches_tracked.add_(1)
+                self._nbt.append(bn.num_batches_tracked)      # advanced with one multi-tensor add at the end of the forward
                 # the kernel wrote through raw pointers: bump the version counters the weight caches key on
                 torch.autograd.graph.increment_version(bn.running_mean)
                 torch.autograd.graph.increment_version(bn.running_var)
@@ -774,11 +782,18 @@ class TrainEngine(Engine):
         mask16 = self.mask_head_t(ps, net.mask_head)
         d32, dtok = self.depth_decoder_t([cs_all[i] for i in net.depth_decoder_indices], mask16, inst["kern16"], net.depth_decoder)
         cates, kerns = self.inst_outputs_nchw(inst, net.inst_head)
+        self._flush_nbt()
         self._out = {"mask16": mask16, "ktok": inst["ktok"], "ctok": inst["ctok"], "dtok": dtok}
         return (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
 
+    def _flush_nbt(self):
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)
+            self._nbt = []
+
     def reset(self):
         """Start of a step: drop the previous tape and clear the accumulator arena (one memset)."""
+        self._nbt = []
         self.tape, self.grads, self.wbufs, self.pgrads, self.pfinal, self._keep = [], {}, {}, {}, [], []
         if self._arena is None:
             self._arena = torch.zeros(self._ARENA_FLOATS, dtype=torch.float32, device="cuda")

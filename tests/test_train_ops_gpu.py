@@ -61,3 +61,8 @@ def test_reflect_dgrad(cuda_lib, kw):
 @pytest.mark.gpu
 def test_softplus_bwd(cuda_lib):
     TC.run_softplus_case()
+
+
+@pytest.mark.gpu
+def test_weight_pack_kernels(cuda_lib):
+    TC.run_pack_cases()

@@ -522,3 +522,24 @@ def run_model_check(preset="PlaneRecNet_50_config", B=2, H=128, W=160, prec="bf1
     r["all_rel"] = float((a - b).norm() / b.norm())
     r["fam"] = {f: (min(v), sum(v) / len(v)) for f, v in fam.items()}
     return r
+
+
+def run_pack_cases():
+    """prn_pack_conv_weight / prn_pack_dgrad_weight == the torch reference packers, bit for bit."""
+    g = torch.Generator().manual_seed(0)
+    for (cout, cin, k, splits, dt) in ((64, 64, 1, [(64, 64)], L.PRN_BF16), (256, 258, 3, [(258, 320)], L.PRN_BF16),
+                                       (128, 384, 3, [(256, 256), (128, 128)], L.PRN_BF16), (2, 256, 3, [(256, 256)], L.PRN_F16),
+                                       (256, 3728, 1, [(3728, 3776)], L.PRN_BF16), (27, 128, 3, [(128, 128)], L.PRN_BF16)):
+        w = torch.randn(cout, cin, k, k, generator=g)
+        n_pad = ops.round_up(cout, 16)
+        ref = ops.pack_conv_weight(w, splits, n_pad, dt)
+        got = ops.pack_conv_weight_dev(w.cuda(), splits, n_pad, dt)
+        assert torch.equal(got.cpu().view(torch.int16), ref.view(torch.int16)), ("fwd pack", cout, cin, k)
+        lo = 0
+        for real, pad in splits:
+            cp = ops.round_up(cout, 64)
+            refd = ops.pack_dgrad_weight(w[:, lo:lo + real], cout_pad=cp, n_pad=pad, dtype=dt)
+            gotd = ops.pack_dgrad_weight_dev(w.cuda(), lo, lo + real, pad, cp, dt)
+            assert torch.equal(gotd.cpu().view(torch.int16), refd.view(torch.int16)), ("dgrad pack", cout, cin, k, lo)
+            lo += real
+    return {}
