@@ -187,23 +187,10 @@ def main():
     value = world * B * a.steps / (ms / 1e3)
 
     # ---------------------------------------------------------------- end to end through the public API
-    # Serving loop with a double-buffered input: the H2D copy of step i+1 (pinned host memory, copy stream) runs while
-    # step i computes; every step's copy, compute, bookkeeping and D2H lie inside the timed region.
-    copy_stream = torch.cuda.Stream()
-
-    def prefetch():
-        with torch.cuda.stream(copy_stream):
-            xb = x_host.cuda(non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return xb, ev
-
-    def e2e_step(cur):
-        nxt = prefetch()
-        xb, ev = cur
-        torch.cuda.current_stream().wait_event(ev)
-        xb.record_stream(torch.cuda.current_stream())
-        res = net(xb)
+    # Serving loop through the public API `net.infer_pipelined(batches)`: every batch goes pinned host memory -> H2D
+    # (copy stream) -> dense forward (graph replay) -> inference bookkeeping -> D2H of the detections + depth maps, all
+    # inside the timed region; batch k+1's copy and forward overlap batch k's bookkeeping (two graph slots).
+    def d2h(res):
         out_bytes = 0
         # device -> host read of the step's result: detections (scores, classes, boxes) and depth maps of all images,
         # concatenated per field so that the step issues 4 copies instead of 4 per image
@@ -212,23 +199,24 @@ def main():
             if parts:
                 t = torch.cat(parts).cpu()
                 out_bytes += t.numel() * t.element_size()
-        return out_bytes, nxt
+        return out_bytes
 
-    with torch.no_grad():
-        cur = prefetch()
-        for _ in range(3):
-            _, cur = e2e_step(cur)
-        sync_all()
-        e_steps = max(3, min(a.steps, 10))
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        d2h = 0
-        for _ in range(e_steps):
-            d2h, cur = e2e_step(cur)
-        t1.record()
-        sync_all()
-        e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e_steps = max(3, min(a.steps, 10))
+    e_warm = 4
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    d2h_bytes = 0
+    # steady state at both ends of the timed window: t0 / t1 are recorded right after a result has been delivered while the
+    # next batch's forward is already in flight; one extra batch is fed so that the last timed step still overlaps one
+    for i, res in enumerate(net.infer_pipelined(x_host for _ in range(e_warm + e_steps + 1))):
+        d2h_bytes = d2h(res)
+        if i == e_warm - 1:
+            t0.record()
+        if i == e_warm + e_steps - 1:
+            t1.record()
+    sync_all()
+    d2h = d2h_bytes
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * e_steps / (e2e_ms / 1e3)
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
@@ -340,7 +328,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                         "d2h_bytes_per_step": d2h, "steps": e_steps,
-                        "path": "net(x) eval: pinned host input -> H2D (double-buffered on a copy stream) -> graph forward -> inference bookkeeping -> D2H"},
+                        "path": "net.infer_pipelined(batches): pinned host input -> H2D (copy stream) -> graph forward -> inference bookkeeping -> D2H; batch k+1's copy + forward overlap batch k's bookkeeping"},
                 "roofline": roof, "cpu_baseline": cpu, "train_step": train}
         print(json.dumps(line))
     if world > 1:

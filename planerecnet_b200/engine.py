@@ -469,11 +469,12 @@ class Engine:
             st["outputs"] = (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
         return st
 
-    def forward_dense_graph(self, net, x, want_nchw=True):
+    def forward_dense_graph(self, net, x, want_nchw=True, slot=0):
         """Same as forward_dense, replayed from a CUDA graph captured per (model, input shape, weight
         version): several hundred kernel launches become one graph launch.  The returned tensors are the
-        graph's static buffers: consume them before the next call."""
-        key = (id(net), tuple(x.shape), want_nchw)
+        graph's static buffers: consume them before the next call with the same `slot` (a pipelined caller
+        alternates two slots so that one batch's bookkeeping can overlap the next batch's forward)."""
+        key = (id(net), tuple(x.shape), want_nchw, slot)
         ent = self._graphs.get(key)
         # the graph bakes in pointers to the packed weights: any in-place parameter / buffer update (optimizer step,
         # load_state_dict, BN statistics) bumps a tensor version and forces a re-pack + re-capture

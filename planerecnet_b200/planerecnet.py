@@ -110,6 +110,50 @@ class PlaneRecNet(nn.Module):
         with timer.env("Inferencing"):
             return self.engine.inference(self, st, x)
 
+    def infer_pipelined(self, batches):
+        """Serving loop over an iterable of equally shaped input batches (pinned host or device tensors): yields, in
+        order, exactly what `net(x)` returns for each batch.  Batch k+1's host-to-device copy (copy stream) and dense
+        forward (forward stream, second graph slot) run while batch k's inference bookkeeping — which has to wait for
+        the host at its data-dependent steps (planerecnet.py:189-269) — runs on the caller's stream."""
+        assert not self.training, "infer_pipelined is an eval-mode loop"
+        eng = self.engine
+        if getattr(self, "_pipe_streams", None) is None:
+            self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        s_copy, s_fwd = self._pipe_streams
+        done = [None, None]          # per graph slot: the bookkeeping that read its static buffers has been enqueued
+        prev = None
+
+        def finish(p):
+            st, xb, ev_f, slot = p
+            main = torch.cuda.current_stream()
+            main.wait_event(ev_f)
+            res = eng.inference(self, st, xb)
+            e = torch.cuda.Event()
+            e.record(main)
+            done[slot] = e
+            return res
+
+        with torch.no_grad():
+            for k, xh in enumerate(batches):
+                slot = k & 1
+                with torch.cuda.stream(s_copy):
+                    xb = xh if xh.is_cuda else xh.cuda(non_blocking=True)
+                    ev_c = torch.cuda.Event()
+                    ev_c.record(s_copy)
+                s_fwd.wait_event(ev_c)
+                if done[slot] is not None:
+                    s_fwd.wait_event(done[slot])
+                with torch.cuda.stream(s_fwd):
+                    st = eng.forward_dense_graph(self, xb, False, slot=slot)
+                    ev_f = torch.cuda.Event()
+                    ev_f.record(s_fwd)
+                xb.record_stream(s_fwd)
+                if prev is not None:
+                    yield finish(prev)
+                prev = (st, xb, ev_f, slot)
+            if prev is not None:
+                yield finish(prev)
+
     @staticmethod
     def split_feats(feats):
         """(x0.5 bilinear of P2, P3, P4, P5): planerecnet.py:113-118 — NCHW fp32 in/out, computed on the engine."""

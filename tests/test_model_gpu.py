@@ -157,3 +157,39 @@ def test_eval_forward_detections_close_to_oracle(cuda_lib):
             assert abs(float(r["pred_scores"][0]) - float(o["pred_scores"][0])) < 5e-3
             m0, o0 = r["pred_masks"][0].cpu(), o["pred_masks"][0]
             assert (m0 & o0).sum() / (m0 | o0).sum() > 0.98
+
+
+def test_infer_pipelined_equals_sequential_calls():
+    """net.infer_pipelined(batches) (two graph slots, forward of batch k+1 overlapping the bookkeeping of batch k)
+    must deliver what net(x) delivers, batch by batch, in order.  The dense forward is not bit-reproducible run to run
+    (GroupNorm sums use fp32 atomics), so dense values are compared to 16-bit-rounding tolerance and the detections
+    loosely where they sit on hard thresholds."""
+    net = H.perturb_(H.build_ours("PlaneRecNet_50_config")).eval().cuda()
+    xs = [H.make_input(2, 128, 160, seed=s) for s in (0, 1, 2, 3, 4)]
+    with torch.no_grad():
+        ref = [net(x.cuda()) for x in xs]
+        ref = [[{k: (None if v is None else v.clone()) for k, v in r.items()} for r in batch] for batch in ref]
+    got = list(net.infer_pipelined(x.pin_memory() for x in xs))
+    assert len(got) == len(ref)
+    n_det = 0
+    for bi, (gb, rb) in enumerate(zip(got, ref)):
+        assert len(gb) == len(rb)
+        for g, r in zip(gb, rb):
+            assert list(g.keys()) == list(r.keys())
+            assert H.rel_l2(g["pred_depth"], r["pred_depth"]) < 2e-3, bi
+            if r["pred_scores"] is None:
+                assert g["pred_scores"] is None or g["pred_scores"].numel() <= 2
+                continue
+            # detections sit on hard thresholds (score_thr / update_thr) and near-tied scores: run-to-run noise of the
+            # dense forward may add / drop a borderline one or swap neighbours -> compare counts loosely, the best ones tightly
+            if g["pred_scores"] is None:
+                assert r["pred_scores"].numel() <= 2
+                continue
+            assert abs(g["pred_scores"].numel() - r["pred_scores"].numel()) <= 2, bi
+            k = min(5, g["pred_scores"].numel(), r["pred_scores"].numel())
+            gs, rs = g["pred_scores"].sort(descending=True).values[:k], r["pred_scores"].sort(descending=True).values[:k]
+            assert torch.allclose(gs, rs, rtol=2e-2, atol=1e-3), (gs, rs)
+            n_det += r["pred_scores"].numel()
+    assert n_det > 0
+    # a different batch order must change the answers accordingly (the slots really carry different batches)
+    assert H.rel_l2(got[0][0]["pred_depth"], got[1][0]["pred_depth"]) > 1e-2
