@@ -116,11 +116,12 @@ __device__ __forceinline__ void load_res(uint4* r, const void* ptr, bool on) {
 // kFull = false is the lean instantiation used by most layers (bias, residual, none/ReLU, 16-bit output): the
 // generic one (statistics, sigmoid/softplus/DCN activations, fp32 output, row averaging) is ~10x more code and
 // thrashes the instruction cache when it sits inside the per-chunk loop.
-template <typename T, int W, bool kFull>
+template <typename T, int W, int kEpi>
 __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const uint4* res, bool has_res,
                                           const float* bias_s, int col0, bool valid, bool img_uniform, int img,
                                           int lane, size_t orow, uint32_t stage_row, int jbase) {
   const PrnConv& d = p.d;
+  constexpr bool kFull = kEpi != 0;      // kEpi: 0 lean | 1 full | 2 full + BatchNorm batch statistics (training step only)
   if (bias_s != nullptr) {
 #pragma unroll
     for (int j = 0; j < W / 4; ++j) {
@@ -216,7 +217,7 @@ __device__ __forceinline__ void epi_chunk(const ConvKParams& p, float* x, const 
         }
       }
     }
-  } else if (d.stats != nullptr) {
+  } else if (kEpi == 2 && d.stats != nullptr) {
     // BatchNorm batch statistics: per-channel {sum, sumsq} over the warp's 32 rows.  Butterfly reduce-scatter over
     // the lanes (W-1 shuffles per quantity instead of 5*W): after the halving steps lane l holds the total of column
     // bits(l), and every lane issues one atomic per quantity.
@@ -299,10 +300,11 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <typename T, bool kDCN, bool kFull, int kCl>
+template <typename T, bool kDCN, int kEpi, int kCl>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                  const __grid_constant__ ConvKParams p) {
+  constexpr bool kFull = kEpi != 0;
   constexpr int kEpiGroups = kDCN ? 1 : 2;              // epilogue warpgroups
   constexpr int kProdWarps = kDCN ? 8 : 4;              // A-producer warps
   constexpr int kRows = kDCN ? 4 : 8;                   // A rows per producer thread
@@ -678,10 +680,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
         const uint32_t srow = p.tma_store ? stg_tile + static_cast<uint32_t>(lane) * 128u : 0u;
         if (!kFull || ci < n32)
-          epi_chunk<T, 32, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+          epi_chunk<T, 32, kEpi>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
                                   img, lane, orow, srow, (ci & 1) * 4);
         else
-          epi_chunk<T, 16, kFull>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
+          epi_chunk<T, 16, kEpi>(p, x, rc, has_res, d.bias ? bias_s + ci * 32 : nullptr, n0 + ci * 32, valid, img_uniform,
                                   img, lane, orow, srow, (ci & 1) * 4);
         if (p.tma_store && ((ci & 1) == 1 || ci + 1 == ntot)) {
           fence_proxy_async_smem();
@@ -791,7 +793,7 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   p->n_tiles = ceil_div(d.n_pad, n_tile);
   p->total_tiles = p->groups * p->m_tiles * p->n_tiles;
   // CTA pairs sharing the weight stream pay off when the weight k-blocks dominate the L2->SM traffic
-  p->cluster = (cluster_enabled() && !d.dcn_offmask && n_tile >= 128 && n_tile % 32 == 0 && p->m_tiles >= 2 && kb >= 4) ? 2 : 1;
+  p->cluster = (cluster_enabled() && !d.dcn_offmask && !(d.stats != nullptr && d.stats_cg == 0) && n_tile >= 128 && n_tile % 32 == 0 && p->m_tiles >= 2 && kb >= 4) ? 2 : 1;
   p->m_ptiles = ceil_div(p->m_tiles, p->cluster);
   p->total_ptiles = p->groups * p->m_ptiles * p->n_tiles;
   int cols = 32;
@@ -833,12 +835,12 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
-template <typename T, bool kDCN, bool kFull, int kCl>
+template <typename T, bool kDCN, int kEpi, int kCl>
 static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKParams& p, int grid, size_t smem,
                   cudaStream_t st) {
   static bool configured = false;  // per instantiation
   if (!configured) {
-    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kFull, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    PRN_CUDA(cudaFuncSetAttribute(conv_umma_kernel<T, kDCN, kEpi, kCl>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -862,7 +864,7 @@ static int launch(const CUtensorMap& tm, const CUtensorMap& tmo, const ConvKPara
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  PRN_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, kDCN, kFull, kCl>, tm, tmo, p));
+  PRN_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<T, kDCN, kEpi, kCl>, tm, tmo, p));
   return PRN_OK;
 }
 
@@ -926,11 +928,17 @@ static int conv_launch(const PrnConv* desc, void* stream, long long* dbg) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool dcn = d.dcn_offmask != nullptr;
   const bool full = !p.lean_epi;
+  const bool bnstats = d.stats != nullptr && d.stats_cg == 0;     // training step: separate instantiation keeps the
+  if (bnstats) {                                                   // statistics code out of the inference kernels
+    if (dcn) return set_error(PRN_ERR_UNSUPPORTED, "conv: BatchNorm statistics are not available with deformable sampling");
+    if (d.dtype == PRN_BF16) return launch<__nv_bfloat16, false, 2, 1>(tm, tmo, p, grid, smem, st);
+    return launch<__half, false, 2, 1>(tm, tmo, p, grid, smem, st);
+  }
 #define PRN_LAUNCH(T)                                                                                                  \
-  (dcn ? (full ? launch<T, true, true, 1>(tm, tmo, p, grid, smem, st) : launch<T, true, false, 1>(tm, tmo, p, grid, smem, st)) \
+  (dcn ? (full ? launch<T, true, 1, 1>(tm, tmo, p, grid, smem, st) : launch<T, true, 0, 1>(tm, tmo, p, grid, smem, st)) \
        : (p.cluster == 2                                                                                               \
-              ? (full ? launch<T, false, true, 2>(tm, tmo, p, grid, smem, st) : launch<T, false, false, 2>(tm, tmo, p, grid, smem, st)) \
-              : (full ? launch<T, false, true, 1>(tm, tmo, p, grid, smem, st) : launch<T, false, false, 1>(tm, tmo, p, grid, smem, st))))
+              ? (full ? launch<T, false, 1, 2>(tm, tmo, p, grid, smem, st) : launch<T, false, 0, 2>(tm, tmo, p, grid, smem, st)) \
+              : (full ? launch<T, false, 1, 1>(tm, tmo, p, grid, smem, st) : launch<T, false, 0, 1>(tm, tmo, p, grid, smem, st))))
   if (d.dtype == PRN_BF16) return PRN_LAUNCH(__nv_bfloat16);
   return PRN_LAUNCH(__half);
 #undef PRN_LAUNCH

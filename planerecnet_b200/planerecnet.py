@@ -120,7 +120,9 @@ class PlaneRecNet(nn.Module):
         if getattr(self, "_pipe_streams", None) is None:
             self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream())
         s_copy, s_fwd = self._pipe_streams
-        done = [None, None]          # per graph slot: the bookkeeping that read its static buffers has been enqueued
+        start = torch.cuda.Event()   # work already queued on the caller's stream may still read the slots' static buffers
+        start.record(torch.cuda.current_stream())
+        done = [start, start]        # per graph slot: the bookkeeping that read its static buffers has been enqueued
         prev = None
 
         def finish(p):
