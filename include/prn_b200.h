@@ -278,6 +278,14 @@ int prn_pack_conv_weight(const float* w, void* out16, int32_t cout, int32_t cin,
 int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t lo, int32_t hi,
                           int32_t rows_pad, int32_t cout_pad, int32_t dtype, void* stream);
 
+/* torch.optim.Adam over all parameters in one launch (train.py:251-256: betas (0.9, 0.999), eps 1e-8, no weight decay, one
+ * learning rate per parameter group).  table int64 [n][5] = {param, grad, exp_avg, exp_avg_sq device pointers (fp32), grad
+ * element stride}; numel int64 [n]; lr fp32 [n]; chunks int32 [n_chunks][2] = {tensor, chunk} with 65536 elements per chunk;
+ * state3 fp32 device {step, 1 - beta1^step, sqrt(1 - beta2^step)}: advanced by the call itself, so the update can be
+ * replayed from a CUDA graph.  Gradients are divided by grad_scale. */
+int prn_adam_multi(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
+                   float* state3, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

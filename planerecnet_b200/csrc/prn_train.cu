@@ -671,3 +671,59 @@ extern "C" int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, 
                (pack_dgrad_kernel<__half><<<rows_pad, 256, 0, st>>>(w, static_cast<__half*>(out16), cout, cin, kk, lo, hi - lo, cout_pad)));
   PRN_LAUNCH_CHECK();
 }
+
+// ---------------------------------------------------------------- Adam over many tensors in one launch (train.py:251-256)
+// torch.optim.Adam semantics (betas, eps, no weight decay, no amsgrad), one learning rate per tensor.  The step counter
+// and bias corrections live in device memory so that the update can be replayed from a CUDA graph.
+namespace prn {
+
+__global__ void adam_advance_kernel(float* state, float beta1, float beta2) {
+  // state = {step, 1 - beta1^step, sqrt(1 - beta2^step)}
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[1] = 1.f - powf(beta1, step);
+  state[2] = sqrtf(1.f - powf(beta2, step));
+}
+
+constexpr int kAdamChunk = 1 << 16;
+
+// table[t] = {param, grad, exp_avg, exp_avg_sq, grad stride (elements)}; chunks[c] = {tensor, chunk index}
+__global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __restrict__ table, const long long* __restrict__ numel,
+                                                       const float* __restrict__ lr, const int* __restrict__ chunks,
+                                                       const float* __restrict__ state, float beta1, float beta2, float eps,
+                                                       float inv_grad_scale) {
+  const int t = chunks[2 * blockIdx.x], ck = chunks[2 * blockIdx.x + 1];
+  float* p = reinterpret_cast<float*>(table[5 * t]);
+  const float* g = reinterpret_cast<const float*>(table[5 * t + 1]);
+  float* m = reinterpret_cast<float*>(table[5 * t + 2]);
+  float* v = reinterpret_cast<float*>(table[5 * t + 3]);
+  const long long gs = table[5 * t + 4];
+  const long long n = numel[t];
+  const float step_size = __ldg(lr + t) / state[1];
+  const float inv_bc2_sqrt = 1.f / state[2];
+  const long long lo = static_cast<long long>(ck) * kAdamChunk;
+  const long long hi = lo + kAdamChunk < n ? lo + kAdamChunk : n;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float gi = g[i * gs] * inv_grad_scale;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_bc2_sqrt + eps);
+  }
+}
+
+}  // namespace prn
+
+extern "C" int prn_adam_multi(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
+                              float* state3, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(table && numel && lr && chunks && state3 && n_chunks > 0 && grad_scale > 0.f, "adam_multi: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_advance_kernel<<<1, 1, 0, st>>>(state3, beta1, beta2);
+  adam_multi_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const long long*>(table), reinterpret_cast<const long long*>(numel), lr,
+                                              chunks, state3, beta1, beta2, eps, 1.0f / grad_scale);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(PRN_ERR_CUDA, "adam_multi launch: %s", cudaGetErrorString(e));
+  return PRN_OK;
+}

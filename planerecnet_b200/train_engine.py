@@ -845,7 +845,9 @@ class GraphedStep:
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
     optimizer's in-place parameter updates; parameters must keep their storage (true for torch optimizers)."""
 
-    def __init__(self, eng, net, x, pack_in_graph=True):
+    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1):
+        """optimizer: a planerecnet_b200.optim.FusedAdam over net's parameters -> `optimizer_step()` replays the update
+        from a third graph (after the gradient all-reduce when world > 1)."""
         self.eng, self.net = eng, net
         self.sx = torch.empty_like(x)
         self.sx.copy_(x)
@@ -874,6 +876,43 @@ class GraphedStep:
             eng.seed_output_grads(*self.cots)
             self.grads = eng.backward()
         self.bwd_launches = eng.launches - n0
+        self.optimizer, self.world = optimizer, world
+        self.g_opt = self.g_flat = None
+        if optimizer is not None:
+            params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
+            src = self.grads
+            if world > 1:
+                # one flat fp32 buffer for the NCCL all-reduce; the optimizer reads the averaged views
+                self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
+                views, off = {}, 0
+                for p in params:
+                    views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+                    off += p.numel()
+                self.g_flat = torch.cuda.CUDAGraph()
+                dst = [views[id(p)] for p in params]
+                srcs = [self.grads[id(p)].reshape(p.shape) for p in params]
+                torch.cuda.synchronize()
+                with torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
+                    torch._foreach_copy_(dst, srcs)
+                src = views
+            optimizer.prepare(src)
+            torch.cuda.synchronize()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
+                optimizer.step(src)
+            # the capture executed nothing, but step() bumped versions / the warm-up above ran one real forward+backward:
+            # parameters are untouched; optimizer state starts at step 0
+
+    def optimizer_step(self):
+        """(all-reduce the gradients of the last backward over the ranks and) apply the optimizer, from graphs."""
+        if self.g_flat is not None:
+            import torch.distributed as dist
+            self.g_flat.replay()
+            dist.all_reduce(self.flat)
+            self.flat.div_(self.world)
+        self.g_opt.replay()
+        for p in self.net.parameters():
+            torch.autograd.graph.increment_version(p)
 
     def forward(self, x):
         self.sx.copy_(x, non_blocking=True)

@@ -114,3 +114,87 @@ def test_graphed_step_matches_eager_and_follows_optimizer(cuda_lib, bn_mode):
     assert rel_l2(g_graph0, g_eager0) <= tol, (rel_l2(g_graph0, g_eager0), noise)
     assert rel_l2(g_graph1, g_eager1) <= tol, (rel_l2(g_graph1, g_eager1), noise)
     assert rel_l2(g_eager1, g_eager0) > 3 * tol or bn_mode == "train"      # the update did change the gradients
+
+
+@pytest.mark.gpu
+def test_fused_adam_matches_torch_adam(cuda_lib):
+    """prn_adam_multi == torch.optim.Adam (train.py:251-256: parameter groups with their own learning rates), 4 steps,
+    contiguous and 1-D strided gradients, tensors spanning several 65536-element chunks."""
+    from planerecnet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(300, 17, 3, 3), (70000,), (5,), (64, 64, 1, 1), (131072 + 7,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    groups = lambda ps: [{"params": ps[:2], "lr": 5e-3}, {"params": ps[2:], "lr": 1e-3}]      # noqa: E731
+    ref = torch.optim.Adam(groups(ref_p), lr=1e-3)
+    ours = FusedAdam(groups(our_p), lr=1e-3)
+    for it in range(4):
+        grads = [torch.randn(s, generator=g).cuda() * (1 + it) for s in shapes]
+        strided = torch.stack([grads[2], torch.zeros_like(grads[2])], 1)            # a [C,2] accumulator: column 0 is the gradient
+        for p, gr in zip(ref_p, grads):
+            p.grad = gr.clone()
+        ref.step()
+        gd = {id(p): gr for p, gr in zip(our_p, grads)}
+        gd[id(our_p[2])] = strided[:, 0]
+        ours.step(gd)
+    torch.cuda.synchronize()
+    for a, b in zip(our_p, ref_p):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
+    assert float(ours._state3[0]) == 4.0
+
+
+@pytest.mark.gpu
+def test_graphed_training_iteration_with_fused_adam(cuda_lib):
+    """Forward, backward and the Adam update replayed from graphs track an eager torch.optim.Adam run on a twin model
+    (frozen BatchNorm statistics: stable network).  Adam's first steps move every weight by ~lr * sign(gradient), so the
+    comparison is on the distribution of parameter differences in units of lr."""
+    from planerecnet_b200.optim import FusedAdam
+    from planerecnet_b200.train_engine import GraphedStep
+
+    def make():
+        net = TC._build("PlaneRecNet_50_config", cond=False).train()
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+        return net.cuda()
+
+    x = torch.randn(2, 3, 128, 160, generator=torch.Generator().manual_seed(5)).cuda()
+    lr = 1e-4
+
+    def groups(net):
+        return [{"params": list(net.backbone.parameters()), "lr": 5 * lr}, {"params": list(net.fpn.parameters()), "lr": lr},
+                {"params": list(net.inst_head.parameters()), "lr": lr}, {"params": list(net.mask_head.parameters()), "lr": lr},
+                {"params": list(net.depth_decoder.parameters()), "lr": 2 * lr}]
+
+    def cots_of(outs):
+        m, cs, ks, d = outs
+        flat = [m] + list(cs) + list(ks) + [d]
+        c = [a.detach() / a[0].numel() ** 0.5 for a in flat]
+        return c[0], c[1:1 + len(cs)], c[1 + len(cs):1 + 2 * len(cs)], c[-1]
+
+    ref = make()
+    opt_ref = torch.optim.Adam(groups(ref), lr=lr)
+    for _ in range(3):
+        opt_ref.zero_grad(set_to_none=True)
+        m, cs, ks, d = ref(x)
+        sum((0.5 * a * a).sum() / a[0].numel() ** 0.5 for a in [m] + list(cs) + list(ks) + [d]).backward()
+        opt_ref.step()
+
+    ours = make()
+    p0 = [p.detach().clone() for p in ours.parameters()]
+    opt = FusedAdam(groups(ours), lr=lr)
+    step = GraphedStep(ours.train_engine, ours, x, optimizer=opt)
+    for _ in range(3):
+        outs = step.forward(x)
+        step.backward(*cots_of(outs))
+        step.optimizer_step()
+    torch.cuda.synchronize()
+    assert float(opt._state3[0]) == 3.0
+    moved = torch.cat([(a.detach() - b).flatten() for a, b in zip(ours.parameters(), p0)])
+    diff = torch.cat([(a.detach() - b.detach()).flatten() for a, b in zip(ours.parameters(), ref.parameters())])
+    moved_ref = torch.cat([(a.detach() - b).flatten() for a, b in zip(ref.parameters(), p0)])
+    cos = float((moved @ moved_ref) / (moved.norm() * moved_ref.norm()))
+    print(f"adam: mean |update| {float(moved.abs().mean()):.3e}, mean |ours - torch| {float(diff.abs().mean()):.3e}, cosine {cos:.4f}")
+    assert float(moved.abs().mean()) > 0.5 * lr                      # the graphs did update the weights
+    # weights whose gradient is below the 16-bit noise floor get a +-lr step of arbitrary sign from Adam's normalisation
+    assert cos > 0.9 and float(diff.abs().mean()) < 0.25 * float(moved.abs().mean()), (cos, float(diff.abs().mean()))
