@@ -20,6 +20,7 @@ class FusedAdam:
         self.state = {}
         self._state3 = None
         self._key = None
+        self._lr_key = None
         self._tabs = None
 
     def _params(self):
@@ -27,9 +28,14 @@ class FusedAdam:
 
     def _build(self, grads):
         items = [(p, grp, grads[id(p)]) for p, grp in self._params() if id(p) in grads and grads[id(p)] is not None]
-        key = tuple((p.data_ptr(), g.data_ptr(), tuple(g.stride())) for p, _, g in items) + tuple(grp["lr"] for _, grp, _ in items)
+        key = tuple((p.data_ptr(), g.data_ptr(), tuple(g.stride())) for p, _, g in items)
+        lr_key = tuple(float(grp["lr"]) for _, grp, _ in items)
         if key == self._key:
+            if lr_key != self._lr_key:      # set_lr (train.py:415-420): refresh the table in place, captured graphs keep seeing it
+                self._tabs[2].copy_(torch.tensor(lr_key, dtype=torch.float32))
+                self._lr_key = lr_key
             return
+        self._lr_key = lr_key
         dev = items[0][0].device
         table, numel, lrs, chunks = [], [], [], []
         for t, (p, grp, g) in enumerate(items):

@@ -131,6 +131,11 @@ def test_fused_adam_matches_torch_adam(cuda_lib):
     for it in range(4):
         grads = [torch.randn(s, generator=g).cuda() * (1 + it) for s in shapes]
         strided = torch.stack([grads[2], torch.zeros_like(grads[2])], 1)            # a [C,2] accumulator: column 0 is the gradient
+        if it == 2:                       # set_lr (train.py:415-420) between steps
+            for grp in ref.param_groups:
+                grp["lr"] *= 0.5
+            for grp in ours.param_groups:
+                grp["lr"] *= 0.5
         for p, gr in zip(ref_p, grads):
             p.grad = gr.clone()
         ref.step()
