@@ -81,6 +81,15 @@ class PlaneRecNet(nn.Module):
             self._train_engine = TrainEngine("bf16")
         return self._train_engine
 
+    def set_train_precision(self, name, grad_scale=1.0):
+        """'bf16' (default) or 'f16' activations / gradients for the training step.  f16 carries 3 more mantissa bits
+        (gradient cosine vs fp32 autograd 0.9998 instead of 0.9987 on the parity model) but needs `grad_scale` (loss
+        scaling) once gradients fall below ~6e-8."""
+        from .train_engine import TrainEngine
+        self._train_engine = TrainEngine(name)
+        self._train_engine.grad_scale = float(grad_scale)
+        return self
+
     def set_precision(self, name):
         """'f16' (default: 10-bit mantissa, ~1e-3 end-to-end) or 'bf16' (~1e-2) storage/operand type of the
         tensor-core path; accumulation is fp32 in TMEM either way."""

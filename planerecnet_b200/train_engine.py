@@ -36,6 +36,9 @@ class TrainEngine(Engine):
         self.pfinal = []       # closures that turn accumulators into parameter gradients after the tape
         self._keep = []        # keeps tokens / tensors alive while their ids are used as keys
         self.side_wgrad = True
+        # Loss scaling for 16-bit gradients (needed with f16, whose range ends at 6e-8): cotangents are multiplied by
+        # grad_scale on entry; the autograd boundary (and FusedAdam(grad_scale=...)) divide the parameter gradients again.
+        self.grad_scale = 1.0
         self._wg_streams = None
         self._wg_rr = 0
         self._wg_used = set()
@@ -130,7 +133,7 @@ class TrainEngine(Engine):
     # ------------------------------------------------------------------ convolution with tape
     def t_conv(self, x, conv, *, src1=None, c0=None, c_splits=None, stride=None, pad=None, pad_mode=L.PAD_ZERO, upsample=1,
                act=L.ACT_NONE, residual=None, stats=None, stats_cg=0, out16_buf=None, out32_buf=None, out_img_rows=0,
-               need_dx=True, token=None, name="conv"):
+               need_dx=True, token=None):
         """conv (+bias) (+residual) (+ReLU); returns the 16-bit output (or `token` when the output lives in a caller
         buffer).  Gradient of the output is looked up under the returned object."""
         assert act in (L.ACT_NONE, L.ACT_RELU)
@@ -805,6 +808,12 @@ class TrainEngine(Engine):
     def seed_output_grads(self, d_mask, d_cates, d_kerns, d_depth):
         """Cotangents of the training outputs (NCHW fp32 or None) -> NHWC 16-bit gradients of the dense tensors."""
         o = self._out
+        if self.grad_scale != 1.0:
+            sc = self.grad_scale
+            d_mask = None if d_mask is None else d_mask * sc
+            d_cates = [None if d is None else d * sc for d in d_cates]
+            d_kerns = [None if d is None else d * sc for d in d_kerns]
+            d_depth = None if d_depth is None else d_depth * sc
         if d_mask is not None:
             self._set_grad(o["mask16"], self.to_nhwc(d_mask, c_pad=o["mask16"].shape[-1]))
         for tok, d in zip(o["ktok"], d_kerns):
@@ -977,7 +986,12 @@ class _DenseTrainFn(torch.autograd.Function):
         for p in ctx.params:
             gp = g.get(id(p))
             # copies: the accumulators (and, when graphed, the static buffers) are reused by the next step
-            out.append(gp.to(p.dtype, copy=True).contiguous() if gp is not None and p.requires_grad else None)
+            if gp is None or not p.requires_grad:
+                out.append(None)
+            elif eng.grad_scale != 1.0:
+                out.append((gp / eng.grad_scale).to(p.dtype).contiguous())
+            else:
+                out.append(gp.to(p.dtype, copy=True).contiguous())
         return (None, None, *out)
 
 

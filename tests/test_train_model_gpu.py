@@ -203,3 +203,29 @@ def test_graphed_training_iteration_with_fused_adam(cuda_lib):
     assert float(moved.abs().mean()) > 0.5 * lr                      # the graphs did update the weights
     # weights whose gradient is below the 16-bit noise floor get a +-lr step of arbitrary sign from Adam's normalisation
     assert cos > 0.9 and float(diff.abs().mean()) < 0.25 * float(moved.abs().mean()), (cos, float(diff.abs().mean()))
+
+
+@pytest.mark.gpu
+def test_f16_training_with_loss_scaling(cuda_lib):
+    """set_train_precision('f16', grad_scale): tiny cotangents (5e-8-scale, below the f16 subnormal range after the first
+    contraction) survive thanks to the scale, and the returned gradients are unscaled again."""
+    from helpers import rel_l2
+    net = TC._build("PlaneRecNet_50_config", cond=False).train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    net = net.cuda()
+    x = torch.randn(1, 3, 128, 160, generator=torch.Generator().manual_seed(7)).cuda()
+
+    def grads(scale_loss):
+        net.zero_grad(set_to_none=True)
+        m, cs, ks, d = net(x)
+        outs = [m] + list(cs) + list(ks) + [d]
+        (scale_loss * sum((0.5 * a * a).sum() / a[0].numel() ** 0.5 for a in outs)).backward()
+        return torch.cat([p.grad.flatten() for p in net.parameters() if p.grad is not None]).clone()
+
+    net.set_train_precision("f16")
+    g_ref = grads(1.0)
+    net.set_train_precision("f16", grad_scale=2.0 ** 20)
+    g_small = grads(1e-6)                   # a 1e-6-scaled loss: unscaled f16 gradients would underflow
+    assert rel_l2(g_small, g_ref * 1e-6) < 5e-3, rel_l2(g_small, g_ref * 1e-6)
