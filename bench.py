@@ -260,78 +260,87 @@ def main():
     # over the flat gradient buffer (§8e).
     train = None
     if not a.no_train:
-        from planerecnet_b200.train_engine import GraphedStep
-        torch.manual_seed(0)
-        tnet = perturb_(PlaneRecNet(cfg)).train().cuda()
-        teng = tnet.train_engine
-        from planerecnet_b200.optim import FusedAdam
-        lr = 1e-4          # train.py:251-256: Adam, five parameter groups
-        opt = FusedAdam([{"params": list(tnet.backbone.parameters()), "lr": 5 * lr}, {"params": list(tnet.fpn.parameters()), "lr": lr},
-                         {"params": list(tnet.inst_head.parameters()), "lr": lr}, {"params": list(tnet.mask_head.parameters()), "lr": lr},
-                         {"params": list(tnet.depth_decoder.parameters()), "lr": 2 * lr}], lr=lr)
-        step = GraphedStep(teng, tnet, x_dev, optimizer=opt, world=world)
-        gen = torch.Generator(device="cuda").manual_seed(1 + rank)
+        try:
+            from planerecnet_b200.train_engine import GraphedStep
+            torch.manual_seed(0)
+            tnet = perturb_(PlaneRecNet(cfg)).train().cuda()
+            teng = tnet.train_engine
+            from planerecnet_b200.optim import FusedAdam
+            lr = 1e-4          # train.py:251-256: Adam, five parameter groups
+            opt = FusedAdam([{"params": list(tnet.backbone.parameters()), "lr": 5 * lr}, {"params": list(tnet.fpn.parameters()), "lr": lr},
+                             {"params": list(tnet.inst_head.parameters()), "lr": lr}, {"params": list(tnet.mask_head.parameters()), "lr": lr},
+                             {"params": list(tnet.depth_decoder.parameters()), "lr": 2 * lr}], lr=lr)
+            step = GraphedStep(teng, tnet, x_dev, optimizer=opt, world=world)
+            gen = torch.Generator(device="cuda").manual_seed(1 + rank)
 
-        def mk(t):
-            return torch.randn(t.shape, device="cuda", generator=gen) / t[0].numel() ** 0.5
+            def mk(t):
+                return torch.randn(t.shape, device="cuda", generator=gen) / t[0].numel() ** 0.5
 
-        m_, cs_, ks_, d_ = step.outs
-        cots = (mk(m_), [mk(c) for c in cs_], [mk(k) for k in ks_], mk(d_))
-        params = [p for p in tnet.parameters() if p.requires_grad]
+            m_, cs_, ks_, d_ = step.outs
+            cots = (mk(m_), [mk(c) for c in cs_], [mk(k) for k in ks_], mk(d_))
+            params = [p for p in tnet.parameters() if p.requires_grad]
 
-        def train_step():
+            def train_step():
+                step.forward(x_dev)
+                g = step.backward(*cots)
+                if world > 1:
+                    D.allreduce_mean_grads(g, params)      # one NCCL all-reduce over the flat gradient buffer (gloo-tested on CPU)
+                return g
+
+            for _ in range(3):
+                train_step()
+            sync_all()
+            t_steps = max(3, min(a.steps, 10))
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            for _ in range(t_steps):
+                train_step()
+            ev[1].record()
+            sync_all()
+            t_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / t_steps
+            ev[0].record()
             step.forward(x_dev)
-            g = step.backward(*cots)
-            if world > 1:
-                D.allreduce_mean_grads(g, params)      # one NCCL all-reduce over the flat gradient buffer (gloo-tested on CPU)
-            return g
-
-        for _ in range(3):
-            train_step()
-        sync_all()
-        t_steps = max(3, min(a.steps, 10))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ev[0].record()
-        for _ in range(t_steps):
-            train_step()
-        ev[1].record()
-        sync_all()
-        t_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / t_steps
-        ev[0].record()
-        step.forward(x_dev)
-        ev[1].record()
-        step.backward(*cots)
-        ev[2].record()
-        torch.cuda.synchronize()
-        # full iteration: forward + backward + (gradient all-reduce) + Adam update, all replayed from graphs
-        for _ in range(2):
-            step.forward(x_dev)
+            ev[1].record()
             step.backward(*cots)
-            step.optimizer_step()
-        sync_all()
-        ev[0].record()
-        for _ in range(t_steps):
-            step.forward(x_dev)
-            step.backward(*cots)
-            step.optimizer_step()
-        ev[1].record()
-        sync_all()
-        it_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / t_steps
-        peak, _, how = peaks()
-        ex = EXEC_GF_TRAIN.get(a.preset)
-        train = {"value": round(world * B / (t_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(t_ms, 3),
-                 "fwd_ms": round(ev[0].elapsed_time(ev[1]), 3), "bwd_ms": round(ev[1].elapsed_time(ev[2]), 3), "steps": t_steps,
-                 "dtype": "bf16", "gpu_launches_per_step": step.fwd_launches + step.bwd_launches,
-                 "grad_allreduce": "nccl, 1 flat fp32 buffer / step" if world > 1 else None,
-                 "algorithmic_gflop_per_image": ALGO_GF_TRAIN.get(a.preset), "executed_gflop_per_image": ex,
-                 "tensor_frac_of_peak": round(ex * B / t_ms / peak, 4) if ex else None,
-                 "full_iteration": {"value": round(world * B / (it_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(it_ms, 3),
-                                    "what": "fwd + bwd + " + ("NCCL all-reduce of the flat gradient buffer + " if world > 1 else "") +
-                                            "fused Adam over 5 parameter groups (prn_adam_multi), 3 graph replays"},
-                 "workload": f"{a.preset} net.train() fwd+bwd bs={B}/GPU 480x640, fixed seeded cotangents (kernel-only step, "
-                             f"no loss/optimizer), 2 CUDA graphs incl. weight packing"}
-        del step, tnet
-        torch.cuda.empty_cache()
+            ev[2].record()
+            torch.cuda.synchronize()
+            # full iteration: forward + backward + (gradient all-reduce) + Adam update, all replayed from graphs
+            it_ms, it_err = None, None
+            try:
+                for _ in range(2):
+                    step.forward(x_dev)
+                    step.backward(*cots)
+                    step.optimizer_step()
+                sync_all()
+                ev[0].record()
+                for _ in range(t_steps):
+                    step.forward(x_dev)
+                    step.backward(*cots)
+                    step.optimizer_step()
+                ev[1].record()
+                sync_all()
+                it_ms = max_over_ranks(ev[0].elapsed_time(ev[1])) / t_steps
+            except Exception as exc:
+                it_err = f"{type(exc).__name__}: {exc}"[:300]
+            peak, _, how = peaks()
+            ex = EXEC_GF_TRAIN.get(a.preset)
+            train = {"value": round(world * B / (t_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(t_ms, 3),
+                     "fwd_ms": round(ev[0].elapsed_time(ev[1]), 3), "bwd_ms": round(ev[1].elapsed_time(ev[2]), 3), "steps": t_steps,
+                     "dtype": "bf16", "gpu_launches_per_step": step.fwd_launches + step.bwd_launches,
+                     "grad_allreduce": "nccl, 1 flat fp32 buffer / step" if world > 1 else None,
+                     "algorithmic_gflop_per_image": ALGO_GF_TRAIN.get(a.preset), "executed_gflop_per_image": ex,
+                     "tensor_frac_of_peak": round(ex * B / t_ms / peak, 4) if ex else None,
+                     "full_iteration": ({"error": it_err} if it_ms is None else
+                                        {"value": round(world * B / (it_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(it_ms, 3),
+                                         "what": "fwd + bwd + " + ("NCCL all-reduce of the flat gradient buffer + " if world > 1 else "") +
+                                                 "fused Adam over 5 parameter groups (prn_adam_multi), 3 graph replays"}),
+                     "workload": f"{a.preset} net.train() fwd+bwd bs={B}/GPU 480x640, fixed seeded cotangents (kernel-only step, "
+                                 f"no loss/optimizer), 2 CUDA graphs incl. weight packing"}
+            del step, tnet
+            torch.cuda.empty_cache()
+
+        except Exception as exc:      # never lose the headline line to the secondary measurement
+            train = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
