@@ -304,6 +304,7 @@ def main():
             step.backward(*cots)
             ev[2].record()
             torch.cuda.synchronize()
+            fwd_ms, bwd_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
             # full iteration: forward + backward + (gradient all-reduce) + Adam update, all replayed from graphs
             it_ms, it_err = None, None
             try:
@@ -325,7 +326,7 @@ def main():
             peak, _, how = peaks()
             ex = EXEC_GF_TRAIN.get(a.preset)
             train = {"value": round(world * B / (t_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(t_ms, 3),
-                     "fwd_ms": round(ev[0].elapsed_time(ev[1]), 3), "bwd_ms": round(ev[1].elapsed_time(ev[2]), 3), "steps": t_steps,
+                     "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3), "steps": t_steps,
                      "dtype": "bf16", "gpu_launches_per_step": step.fwd_launches + step.bwd_launches,
                      "grad_allreduce": "nccl, 1 flat fp32 buffer / step" if world > 1 else None,
                      "algorithmic_gflop_per_image": ALGO_GF_TRAIN.get(a.preset), "executed_gflop_per_image": ex,
