@@ -1,4 +1,4 @@
-from planerecnet_b200.postprocess import matrix_nms as _matrix_nms, point_nms  # noqa: F401
+from planerecnet_b200.postprocess import mask_nms, matrix_nms as _matrix_nms, point_nms  # noqa: F401
 
 
 def matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=2.0, kernel="gaussian"):

@@ -365,10 +365,6 @@ __global__ void dcn_im2col_kernel(const T* __restrict__ x, const float* __restri
   }
 }
 
-__device__ __forceinline__ void red_add_v4f(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // One warp per output pixel.  dcol = gradient of the im2col matrix.  Produces
 //   dx32 (fp32, zero-initialised by the caller) += mask * bilinear weights * dcol      scattered with vector reductions
 //   dpre16[m, 0:64]: gradient w.r.t. the PRE-activation output of the fused offset/modulator conv: offsets pass
@@ -414,8 +410,8 @@ __global__ void dcn_col2im_bwd_kernel(const T* __restrict__ x, const float* __re
               s_y = fmaf((cy ? 1.f : -1.f) * wxx, dot, s_y);
               s_x = fmaf((cx ? 1.f : -1.f) * wy, dot, s_x);
               const float wgt = wy * wxx * mk;
-              red_add_v4f(dx32 + pix, wgt * gcol[0], wgt * gcol[1], wgt * gcol[2], wgt * gcol[3]);
-              red_add_v4f(dx32 + pix + 4, wgt * gcol[4], wgt * gcol[5], wgt * gcol[6], wgt * gcol[7]);
+              red_add_v4_f32(dx32 + pix, wgt * gcol[0], wgt * gcol[1], wgt * gcol[2], wgt * gcol[3]);
+              red_add_v4_f32(dx32 + pix + 4, wgt * gcol[4], wgt * gcol[5], wgt * gcol[6], wgt * gcol[7]);
             }
           }
         }

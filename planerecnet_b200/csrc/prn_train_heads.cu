@@ -176,10 +176,6 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ dout, T* __restrict_
   }
 }
 
-__device__ __forceinline__ void red_add_v4h(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // ---------------------------------------------------------------- arbitrary bilinear resize backward (planerecnet.py:381)
 // dout [B,Ho,Wo,ld] 16-bit (first C channels are feature channels; the coord channels carry no parameter gradient)
 // -> din32 fp32 [B,H,W,C] += scattered (caller zeroes)
@@ -207,8 +203,8 @@ __global__ void resize_bilinear_bwd_kernel(const T* __restrict__ dout, float* __
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float* p = base + (static_cast<long long>(ys[k]) * W + xs[k]) * C;
-      red_add_v4h(p, wts[k] * g[0], wts[k] * g[1], wts[k] * g[2], wts[k] * g[3]);
-      red_add_v4h(p + 4, wts[k] * g[4], wts[k] * g[5], wts[k] * g[6], wts[k] * g[7]);
+      red_add_v4_f32(p, wts[k] * g[0], wts[k] * g[1], wts[k] * g[2], wts[k] * g[3]);
+      red_add_v4_f32(p + 4, wts[k] * g[4], wts[k] * g[5], wts[k] * g[6], wts[k] * g[7]);
     }
   }
 }

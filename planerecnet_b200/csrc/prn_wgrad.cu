@@ -66,10 +66,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ WgradKParams p) {
@@ -204,7 +200,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            red_add_v4(orow + c0 + 4 * j, __uint_as_float(vb[4 * j]), __uint_as_float(vb[4 * j + 1]),
+            red_add_v4_f32(orow + c0 + 4 * j, __uint_as_float(vb[4 * j]), __uint_as_float(vb[4 * j + 1]),
                        __uint_as_float(vb[4 * j + 2]), __uint_as_float(vb[4 * j + 3]));
         }
       }

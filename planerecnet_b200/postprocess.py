@@ -33,6 +33,24 @@ def matrix_nms(cate_labels, seg_masks, sum_masks, cate_scores, sigma=2.0, kernel
                   torch.ones(1, n, dtype=torch.bool, device=cate_scores.device), sigma, kernel)[0]
 
 
+def mask_nms(cate_labels, seg_masks, sum_masks, cate_scores, nms_thr=0.5):
+    """nms.py:53-80 for one image, reference signature (seg_masks [n, h, w] or [n, pixels]; candidates sorted by score):
+    returns the bool keep vector.  The greedy pass runs in prn_mask_nms_greedy on the masks' Gram matrix."""
+    n = len(cate_scores)
+    if n == 0:
+        return []
+    m = seg_masks.reshape(n, -1).float()
+    inter = torch.mm(m, m.t()).contiguous()[None]
+    area = sum_masks.float().contiguous()[None]
+    labels = cate_labels.long().contiguous()[None]
+    valid = torch.ones(1, n, dtype=torch.uint8, device=m.device)
+    keep = torch.empty(1, n, dtype=torch.uint8, device=m.device)
+    L.check(L.lib().prn_mask_nms_greedy(C.c_void_p(inter.data_ptr()), C.c_void_p(area.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                        C.c_void_p(valid.data_ptr()), C.c_void_p(keep.data_ptr()), 1, n, C.c_float(nms_thr),
+                                        L.current_stream()), "prn_mask_nms_greedy")
+    return keep[0].bool()
+
+
 def _decay(inter, areas, labels, scores, valid, sigma, kernel):
     """Batched nms.py:24-48.  inter [B,n,n] mask intersections (sorted order), areas/labels/scores/valid [B,n]."""
     n = inter.shape[-1]

@@ -207,3 +207,12 @@ def test_selection_with_mask_nms_matches_oracle_exactly(cuda_lib, seed, n_cand):
         assert torch.equal(lab.cpu(), e_lab)
         assert torch.allclose(sc.cpu(), e_sc, rtol=1e-5, atol=1e-6)
         assert torch.equal(seg32[rows].cpu(), e_seg.reshape(-1, P))
+
+
+def test_module_level_mask_nms_reference_signature(cuda_lib):
+    import os
+    cases = torch.load(os.path.join(os.path.dirname(__file__), "golden", "mask_nms.pt"))
+    for c in cases:
+        keep = PP.mask_nms(c["labels"].cuda(), c["masks"].cuda(), c["sums"].cuda(), c["scores"].cuda(), nms_thr=c["thr"])
+        assert torch.equal(keep.cpu(), c["keep"])
+    assert PP.mask_nms(torch.zeros(0), torch.zeros(0, 4, 4), torch.zeros(0), torch.zeros(0)) == []
