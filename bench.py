@@ -190,15 +190,25 @@ def main():
     # Serving loop through the public API `net.infer_pipelined(batches)`: every batch goes pinned host memory -> H2D
     # (copy stream) -> dense forward (graph replay) -> inference bookkeeping -> D2H of the detections + depth maps, all
     # inside the timed region; batch k+1's copy and forward overlap batch k's bookkeeping (two graph slots).
+    pinned = {}
+
     def d2h(res):
         out_bytes = 0
         # device -> host read of the step's result: detections (scores, classes, boxes) and depth maps of all images,
-        # concatenated per field so that the step issues 4 copies instead of 4 per image
+        # concatenated per field (4 copies per step instead of 4 per image) into pinned host buffers
+        staged = []
         for k in ("pred_scores", "pred_classes", "pred_boxes", "pred_depth"):
             parts = [r[k] for r in res if r[k] is not None]
             if parts:
-                t = torch.cat(parts).cpu()
+                t = torch.cat(parts)
+                buf = pinned.get(k)
+                if buf is None or buf.numel() < t.numel() or buf.dtype != t.dtype:
+                    buf = pinned[k] = torch.empty(max(t.numel(), 4096), dtype=t.dtype).pin_memory()
+                dst = buf[:t.numel()]
+                dst.copy_(t.reshape(-1), non_blocking=True)
+                staged.append(dst)
                 out_bytes += t.numel() * t.element_size()
+        torch.cuda.current_stream().synchronize()      # the results are on the host when the step ends
         return out_bytes
 
     e_steps = max(3, min(a.steps, 10))

@@ -127,8 +127,10 @@ class PlaneRecNet(nn.Module):
         assert not self.training, "infer_pipelined is an eval-mode loop"
         eng = self.engine
         if getattr(self, "_pipe_streams", None) is None:
-            self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream())
-        s_copy, s_fwd = self._pipe_streams
+            # bookkeeping = many tiny kernels with host round trips in between: a high-priority stream lets their CTAs
+            # in ahead of the forward's next persistent kernel instead of queueing behind it
+            self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream(priority=-1))
+        s_copy, s_fwd, s_book = self._pipe_streams
         start = torch.cuda.Event()   # work already queued on the caller's stream may still read the slots' static buffers
         start.record(torch.cuda.current_stream())
         done = [start, start]        # per graph slot: the bookkeeping that read its static buffers has been enqueued
@@ -137,11 +139,17 @@ class PlaneRecNet(nn.Module):
         def finish(p):
             st, xb, ev_f, slot = p
             main = torch.cuda.current_stream()
-            main.wait_event(ev_f)
-            res = eng.inference(self, st, xb)
-            e = torch.cuda.Event()
-            e.record(main)
+            s_book.wait_event(ev_f)
+            with torch.cuda.stream(s_book):
+                res = eng.inference(self, st, xb)
+                e = torch.cuda.Event()
+                e.record(s_book)
             done[slot] = e
+            main.wait_event(e)                     # the caller consumes the results on its own stream
+            for r in res:
+                for v in r.values():
+                    if v is not None:
+                        v.record_stream(main)
             return res
 
         with torch.no_grad():

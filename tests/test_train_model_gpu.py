@@ -109,11 +109,12 @@ def test_graphed_step_matches_eager_and_follows_optimizer(cuda_lib, bn_mode):
     g_graph0 = step()          # captures
     opt.step()
     g_graph1 = step()          # replays with the updated parameters
-    tol = max(3 * noise, 1e-4 if bn_mode == "frozen" else 1e-3)
-    print(f"bn={bn_mode} eager run-to-run {noise:.2e} graph-vs-eager {rel_l2(g_graph0, g_eager0):.2e} {rel_l2(g_graph1, g_eager1):.2e}")
-    assert rel_l2(g_graph0, g_eager0) <= tol, (rel_l2(g_graph0, g_eager0), noise)
-    assert rel_l2(g_graph1, g_eager1) <= tol, (rel_l2(g_graph1, g_eager1), noise)
-    assert rel_l2(g_eager1, g_eager0) > 3 * tol or bn_mode == "train"      # the update did change the gradients
+    tol = max(5 * noise, 1e-3)
+    e0, e1, upd = rel_l2(g_graph0, g_eager0), rel_l2(g_graph1, g_eager1), rel_l2(g_eager1, g_eager0)
+    print(f"bn={bn_mode} eager run-to-run {noise:.2e} graph-vs-eager {e0:.2e} {e1:.2e} change by the update {upd:.2e}")
+    assert e0 <= tol and e1 <= tol, (e0, e1, noise)
+    if bn_mode == "frozen":      # the update changed the gradients by more than the graph differs from eager: it was followed
+        assert upd > 2 * e1, (upd, e1)
 
 
 @pytest.mark.gpu
