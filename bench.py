@@ -217,8 +217,8 @@ def main():
     t1 = torch.cuda.Event(enable_timing=True)
     d2h_bytes = 0
     # steady state at both ends of the timed window: t0 / t1 are recorded right after a result has been delivered while the
-    # next batch's forward is already in flight; one extra batch is fed so that the last timed step still overlaps one
-    for i, res in enumerate(net.infer_pipelined(x_host for _ in range(e_warm + e_steps + 1))):
+    # next batch's forward and the one after's copy are already in flight; two extra batches are fed to keep it so at the end
+    for i, res in enumerate(net.infer_pipelined(x_host for _ in range(e_warm + e_steps + 2))):
         d2h_bytes = d2h(res)
         if i == e_warm - 1:
             t0.record()

@@ -121,8 +121,8 @@ class PlaneRecNet(nn.Module):
 
     def infer_pipelined(self, batches):
         """Serving loop over an iterable of equally shaped input batches (pinned host or device tensors): yields, in
-        order, exactly what `net(x)` returns for each batch.  Batch k+1's host-to-device copy (copy stream) and dense
-        forward (forward stream, second graph slot) run while batch k's inference bookkeeping — which has to wait for
+        order, exactly what `net(x)` returns for each batch.  Batch k+2's host-to-device copy (copy stream) and batch k+1's
+        dense forward (forward stream, second graph slot) run while batch k's inference bookkeeping — which has to wait for
         the host at its data-dependent steps (planerecnet.py:189-269) — runs on the caller's stream."""
         assert not self.training, "infer_pipelined is an eval-mode loop"
         eng = self.engine
@@ -152,13 +152,24 @@ class PlaneRecNet(nn.Module):
                         v.record_stream(main)
             return res
 
+        def issue_copy(xh):
+            with torch.cuda.stream(s_copy):
+                xb = xh if xh.is_cuda else xh.cuda(non_blocking=True)
+                ev_c = torch.cuda.Event()
+                ev_c.record(s_copy)
+            return xb, ev_c
+
         with torch.no_grad():
-            for k, xh in enumerate(batches):
+            it = iter(batches)
+            first = next(it, None)
+            pending = issue_copy(first) if first is not None else None
+            k = 0
+            while pending is not None:
+                xb, ev_c = pending
+                # the copy of batch k+1 is issued before batch k's forward is enqueued: it has a whole step to land
+                nxt = next(it, None)
+                pending = issue_copy(nxt) if nxt is not None else None
                 slot = k & 1
-                with torch.cuda.stream(s_copy):
-                    xb = xh if xh.is_cuda else xh.cuda(non_blocking=True)
-                    ev_c = torch.cuda.Event()
-                    ev_c.record(s_copy)
                 s_fwd.wait_event(ev_c)
                 if done[slot] is not None:
                     s_fwd.wait_event(done[slot])
@@ -170,6 +181,7 @@ class PlaneRecNet(nn.Module):
                 if prev is not None:
                     yield finish(prev)
                 prev = (st, xb, ev_f, slot)
+                k += 1
             if prev is not None:
                 yield finish(prev)
 
