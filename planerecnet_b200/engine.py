@@ -495,8 +495,16 @@ class Engine:
             gen = self._pack_gen
             g = torch.cuda.CUDAGraph()
             n0 = self.launches
-            with torch.cuda.graph(g):
-                st = self.forward_dense(net, sx, want_nchw)
+            import gc
+            gc.collect()
+            gc_was = gc.isenabled()
+            gc.disable()       # a cyclic-GC pass destroying old CUDA graphs / events mid-capture would invalidate it
+            try:
+                with torch.cuda.graph(g):
+                    st = self.forward_dense(net, sx, want_nchw)
+            finally:
+                if gc_was:
+                    gc.enable()
             ent = {"graph": g, "x": sx, "st": st, "gen": self._pack_gen, "wver": wver, "launches": self.launches - n0}
             self._graphs[key] = ent
         ent["x"].copy_(x, non_blocking=True)

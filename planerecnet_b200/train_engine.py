@@ -15,7 +15,9 @@ tape in reverse.  Every arithmetic step is a launch of a hand-written sm_100a ke
 torch is used for device memory, streams and parameter (un)packing only.  Activations and gradients are NHWC
 16-bit (bf16 by default: gradients need the exponent range), weight gradients fp32.
 """
+import contextlib
 import ctypes as C
+import gc
 
 import torch
 from torch import nn
@@ -849,6 +851,20 @@ class TrainEngine(Engine):
         return grads
 
 
+@contextlib.contextmanager
+def _no_gc():
+    """Stream capture runs in global error mode: a cyclic-GC pass in the middle of it may destroy CUDA graphs / events
+    of earlier steps (cudaGraphExecDestroy etc.), which invalidates the capture.  Collect first, then keep the GC off."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
 class GraphedStep:
     """Forward and backward of one training step captured as two CUDA graphs sharing a memory pool (the ~1300 launches
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
@@ -872,7 +888,7 @@ class GraphedStep:
         self.bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats]
         self.g_fwd = torch.cuda.CUDAGraph()
         n0 = eng.launches
-        with torch.cuda.graph(self.g_fwd):
+        with _no_gc(), torch.cuda.graph(self.g_fwd):
             if pack_in_graph:
                 eng._packed.clear()
             self.outs = eng.forward_train(net, self.sx)
@@ -881,7 +897,7 @@ class GraphedStep:
         self.cots = (torch.zeros_like(m), [torch.zeros_like(c) for c in cs], [torch.zeros_like(k) for k in ks], torch.zeros_like(d))
         self.g_bwd = torch.cuda.CUDAGraph()
         n0 = eng.launches
-        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+        with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
             eng.seed_output_grads(*self.cots)
             self.grads = eng.backward()
         self.bwd_launches = eng.launches - n0
@@ -901,13 +917,13 @@ class GraphedStep:
                 dst = [views[id(p)] for p in params]
                 srcs = [self.grads[id(p)].reshape(p.shape) for p in params]
                 torch.cuda.synchronize()
-                with torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
+                with _no_gc(), torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
                     torch._foreach_copy_(dst, srcs)
                 src = views
             optimizer.prepare(src)
             torch.cuda.synchronize()
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
+            with _no_gc(), torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
                 optimizer.step(src)
             # the capture executed nothing, but step() bumped versions / the warm-up above ran one real forward+backward:
             # parameters are untouched; optimizer state starts at step 0
