@@ -212,3 +212,27 @@ def test_dropin_shims_work_with_the_reference_config():
         "print('ok')\n" % (os.path.join(ROOT, "dropin"), ROOT))
     out = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_fused_adam_tables_on_cpu():
+    """Host logic of planerecnet_b200.optim.FusedAdam (no launch): pointer table, strides of 1-D gradient views, chunking,
+    per-group learning rates and their in-place refresh (train.py:251-256, 415-420)."""
+    from planerecnet_b200.optim import FusedAdam, _CHUNK
+    a, b, c = (torch.nn.Parameter(torch.zeros(s)) for s in ((3, 4), (_CHUNK + 5,), (7,)))
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    opt = FusedAdam([{"params": [a, frozen], "lr": 5e-4}, {"params": [b, c]}], lr=1e-4)
+    acc = torch.zeros(7, 2)
+    grads = {id(a): torch.ones(3, 4), id(b): torch.ones(_CHUNK + 5), id(c): acc[:, 1], id(frozen): torch.ones(2)}
+    opt.prepare(grads)
+    table, numel, lrs, chunks, n_chunks, _ = opt._tabs
+    assert table.view(-1, 5).shape[0] == 3                      # the frozen parameter is skipped
+    assert table.view(-1, 5)[:, 4].tolist() == [1, 1, 2]         # column view of a [C,2] accumulator: element stride 2
+    assert table.view(-1, 5)[2, 1].item() == acc[:, 1].data_ptr()
+    assert numel.tolist() == [12, _CHUNK + 5, 7] and n_chunks == 4
+    assert chunks.tolist() == [[0, 0], [1, 0], [1, 1], [2, 0]]
+    assert torch.allclose(lrs, torch.tensor([5e-4, 1e-4, 1e-4]))
+    lr_tensor = opt._tabs[2]
+    opt.param_groups[1]["lr"] = 2e-5                             # set_lr: same table object, refreshed in place
+    opt.prepare(grads)
+    assert opt._tabs[2] is lr_tensor and torch.allclose(lr_tensor, torch.tensor([5e-4, 2e-5, 2e-5]))
+    assert set(opt.state[id(a)]) == {"exp_avg", "exp_avg_sq"}
