@@ -212,13 +212,13 @@ def main():
         return out_bytes
 
     e_steps = max(3, min(a.steps, 10))
-    e_warm = 4
+    e_warm = 5
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     d2h_bytes = 0
     # steady state at both ends of the timed window: t0 / t1 are recorded right after a result has been delivered while the
     # next batch's forward and the one after's copy are already in flight; two extra batches are fed to keep it so at the end
-    for i, res in enumerate(net.infer_pipelined(x_host for _ in range(e_warm + e_steps + 2))):
+    for i, res in enumerate(net.infer_pipelined(x_host for _ in range(e_warm + e_steps + 3))):
         d2h_bytes = d2h(res)
         if i == e_warm - 1:
             t0.record()

@@ -119,12 +119,15 @@ class PlaneRecNet(nn.Module):
         with timer.env("Inferencing"):
             return self.engine.inference(self, st, x)
 
-    def infer_pipelined(self, batches):
+    def infer_pipelined(self, batches, depth=3):
         """Serving loop over an iterable of equally shaped input batches (pinned host or device tensors): yields, in
-        order, exactly what `net(x)` returns for each batch.  Batch k+2's host-to-device copy (copy stream) and batch k+1's
-        dense forward (forward stream, second graph slot) run while batch k's inference bookkeeping — which has to wait for
-        the host at its data-dependent steps (planerecnet.py:189-269) — runs on the caller's stream."""
+        order, exactly what `net(x)` returns for each batch.  Up to `depth` batches are in flight: while batch k's
+        inference bookkeeping — which has to wait for the host at its data-dependent steps (planerecnet.py:189-269) —
+        runs on a high-priority stream, the dense forwards of batches k+1 .. k+depth-1 are already queued on the forward
+        stream (one CUDA-graph slot each) and the next input is being copied on the copy stream."""
         assert not self.training, "infer_pipelined is an eval-mode loop"
+        assert depth >= 2
+        from collections import deque
         eng = self.engine
         if getattr(self, "_pipe_streams", None) is None:
             # bookkeeping = many tiny kernels with host round trips in between: a high-priority stream lets their CTAs
@@ -133,8 +136,8 @@ class PlaneRecNet(nn.Module):
         s_copy, s_fwd, s_book = self._pipe_streams
         start = torch.cuda.Event()   # work already queued on the caller's stream may still read the slots' static buffers
         start.record(torch.cuda.current_stream())
-        done = [start, start]        # per graph slot: the bookkeeping that read its static buffers has been enqueued
-        prev = None
+        done = [start] * depth       # per graph slot: the bookkeeping that read its static buffers has been enqueued
+        inflight = deque()
 
         def finish(p):
             st, xb, ev_f, slot = p
@@ -165,25 +168,23 @@ class PlaneRecNet(nn.Module):
             pending = issue_copy(first) if first is not None else None
             k = 0
             while pending is not None:
+                if len(inflight) == depth:         # every slot holds a batch: deliver the oldest first
+                    yield finish(inflight.popleft())
                 xb, ev_c = pending
-                # the copy of batch k+1 is issued before batch k's forward is enqueued: it has a whole step to land
-                nxt = next(it, None)
+                nxt = next(it, None)               # the copy of the following batch is issued before this forward is queued
                 pending = issue_copy(nxt) if nxt is not None else None
-                slot = k & 1
+                slot = k % depth
                 s_fwd.wait_event(ev_c)
-                if done[slot] is not None:
-                    s_fwd.wait_event(done[slot])
+                s_fwd.wait_event(done[slot])
                 with torch.cuda.stream(s_fwd):
                     st = eng.forward_dense_graph(self, xb, False, slot=slot)
                     ev_f = torch.cuda.Event()
                     ev_f.record(s_fwd)
                 xb.record_stream(s_fwd)
-                if prev is not None:
-                    yield finish(prev)
-                prev = (st, xb, ev_f, slot)
+                inflight.append((st, xb, ev_f, slot))
                 k += 1
-            if prev is not None:
-                yield finish(prev)
+            while inflight:
+                yield finish(inflight.popleft())
 
     @staticmethod
     def split_feats(feats):
