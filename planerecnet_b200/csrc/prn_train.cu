@@ -25,6 +25,17 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = Pack2<T>::unpack(w[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+
 // Channel-stationary threads: a thread keeps its 8 channels (scale/shift in registers) and walks rows with a stride of
 // (total threads / (C/8)); total thread count is a multiple of C/8 (chan_grid).  One 16-byte load per operand and row.
 template <typename T>
@@ -43,35 +54,34 @@ __global__ void __launch_bounds__(kPwThreads) bn_apply_kernel(const T* __restric
     sh[j] = __ldg(beta + c + j) - __ldg(mean_invstd + 2 * (c + j)) * sc[j];
   }
   const float lo = relu ? 0.f : -INFINITY;
-  for (long long m = gtid / cv; m < rows; m += rstep) {
-    float f[8], r[8];
-    load8(x + m * C + c, f);
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  // two rows per iteration, all loads issued before the first use (latency-bound otherwise)
+  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+    const long long m2 = m + rstep;
+    const bool two = m2 < rows;
+    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
+    const uint4 x1 = two ? __ldg(reinterpret_cast<const uint4*>(x + m2 * C + c)) : zero4;
+    uint4 r0 = zero4, r1 = zero4;
     if (res != nullptr) {
-      load8(res + m * C + c, r);
+      r0 = __ldg(reinterpret_cast<const uint4*>(res + m * C + c));
+      if (two) r1 = __ldg(reinterpret_cast<const uint4*>(res + m2 * C + c));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float f[8], r[8];
+      unpack8<T>(h ? x1 : x0, f);
+      unpack8<T>(h ? r1 : r0, r);      // zeros when there is no residual
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]) + r[j], lo);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]), lo);
+      store8(out + (h ? m2 : m) * C + c, f);
     }
-    store8(out + m * C + c, f);
   }
 }
 
 // sums[c*2] += sum_m g, sums[c*2+1] += sum_m g * xhat with g = dz * (out > 0) (out == NULL: g = dz) and
 // xhat = (x - mean) * invstd (x == NULL: second sum skipped).  Total thread count is a multiple of C/8 so that a
 // thread keeps its 8 channels for all of its rows.
-template <typename T>
-__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 v = Pack2<T>::unpack(w[j]);
-    f[2 * j] = v.x;
-    f[2 * j + 1] = v.y;
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(kPwThreads) chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out,
                                                                const T* __restrict__ x, const float* __restrict__ mean_invstd,
