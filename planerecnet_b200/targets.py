@@ -1,0 +1,79 @@
+"""Ground-truth assignment of the SOLOv2-style heads (models/functions/losses.py:200-275), device-resident.
+
+The reference sends every image's plane masks to the host, rescales them by 1/4 with cv2 (bilinear, uint8) and sends
+them back (losses.py:243-247).  For binary masks and an exact 1/4 scale that resize has a closed form — the output pixel is
+1 iff at least two of the four centre pixels of its 4x4 block are set (cv2's fixed-point bilinear with weights 1/2, 1/2
+rounds 0.5 up; checked against cv2 in tests/test_targets_cpu.py) — so the whole assignment runs where the masks live, with
+one host round trip per FPN level for the handful of integer cell coordinates.  Plain tensor indexing only (no arithmetic
+hot path); device-agnostic, which is what lets the CPU suite compare it with the oracle bit for bit."""
+import torch
+
+
+def quarter_masks(masks):
+    """[n, H, W] {0,1} (any integer / bool dtype), H and W multiples of 4 -> [n, H/4, W/4] uint8, identical to
+    cv2.resize(..., fx=fy=0.25, INTER_LINEAR) of the uint8 masks."""
+    n, H, W = masks.shape
+    if H % 4 or W % 4:
+        raise ValueError("quarter_masks needs H and W to be multiples of 4 (got %dx%d)" % (H, W))
+    m = masks.to(torch.uint8).reshape(n, H // 4, 4, W // 4, 4)
+    centre = m[:, :, 1:3, :, 1:3].sum(dim=(2, 4))
+    return (centre >= 2).to(torch.uint8)
+
+
+@torch.no_grad()
+def assign_targets(gt, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.2):
+    """losses.py:200-275 for one image.  gt: {'boxes' [n,4] xyxy, 'classes' [n], 'masks' [n,H,W]} on any device.
+    Returns per level (ins_label uint8 [m, fh, fw], cate_label int64 [S, S], ins_ind bool [S*S], grid_order list[int])."""
+    boxes, labels, masks = gt["boxes"], gt["classes"], gt["masks"]
+    dev = masks.device
+    fh, fw = feat_hw
+    up_h, up_w = fh * 4, fw * 4
+    areas = torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]))
+    out = []
+    for (lo, hi), S in zip(scale_ranges, num_grids):
+        hit = ((areas >= lo) & (areas <= hi)).nonzero().flatten()
+        cate = torch.full((S, S), num_classes, dtype=torch.int64, device=dev)
+        ind = torch.zeros(S * S, dtype=torch.bool, device=dev)
+        if hit.numel() == 0:
+            out.append((torch.zeros(0, fh, fw, dtype=torch.uint8, device=dev), cate, ind, []))
+            continue
+        bx, lb, mk = boxes[hit], labels[hit], masks[hit]
+        half_w = 0.5 * (bx[:, 2] - bx[:, 0]) * sigma
+        half_h = 0.5 * (bx[:, 3] - bx[:, 1]) * sigma
+        # centre of mass (funcs.py:213-224)
+        ys = torch.arange(mk.shape[1], dtype=torch.float32, device=dev)
+        xs = torch.arange(mk.shape[2], dtype=torch.float32, device=dev)
+        m00 = mk.sum(-1).sum(-1).clamp(min=1e-6)
+        cw = (mk * xs).sum(-1).sum(-1) / m00
+        ch = (mk * ys[:, None]).sum(-1).sum(-1) / m00
+        nonempty = mk.sum(-1).sum(-1) > 0
+
+        def cell(v, extent):                       # int((v / extent) // (1 / S)) of the reference, for all instances at once
+            return torch.floor_divide(v / extent, 1.0 / S).to(torch.int64)
+
+        cx, cy = cell(cw, up_w), cell(ch, up_h)
+        top = torch.maximum(cell(ch - half_h, up_h).clamp(min=0), cy - 1)
+        down = torch.minimum(cell(ch + half_h, up_h).clamp(max=S - 1), cy + 1)
+        left = torch.maximum(cx - 1, cell(cw - half_w, up_w).clamp(min=0))
+        right = torch.minimum(cell(cw + half_w, up_w).clamp(max=S - 1), cx + 1)
+        # the one host round trip of this level: a few integers per instance
+        rows = torch.stack([top, down, left, right, nonempty.to(torch.int64), lb.to(torch.int64)], 1).tolist()
+        src, order = [], []
+        for k, (t, d, l, r, ok, lab) in enumerate(rows):
+            if not ok:
+                continue
+            cate[t:d + 1, l:r + 1] = lab
+            for i in range(t, d + 1):
+                for j in range(l, r + 1):
+                    src.append(k)
+                    order.append(i * S + j)
+        if order:
+            small = quarter_masks(mk)
+            canvas = torch.zeros(len(order), fh, fw, dtype=torch.uint8, device=dev)
+            canvas[:, :small.shape[1], :small.shape[2]] = small[torch.tensor(src, device=dev)]
+            ind[torch.tensor(order, device=dev)] = True
+            ins = canvas
+        else:
+            ins = torch.zeros(0, fh, fw, dtype=torch.uint8, device=dev)
+        out.append((ins, cate, ind, order))
+    return out

@@ -1,0 +1,50 @@
+"""planerecnet_b200.targets (device-resident ground-truth assignment without the cv2 round trip) against cv2 itself and
+against the oracle's restatement of losses.py:200-275 (which is pinned to the unmodified reference by
+tests/golden/loss_golden.pt) — exact equality."""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import loss_cases as LC
+from oracle import prn_loss_oracle as LO
+from planerecnet_b200 import targets as T
+
+
+@pytest.mark.parametrize("shape", [(3, 480, 640), (1, 64, 96), (7, 128, 160)])
+def test_quarter_masks_equals_cv2_bilinear(shape):
+    n, H, W = shape
+    rng = np.random.default_rng(n)
+    m = (rng.random((H, W, n)) < 0.5).astype(np.uint8)
+    m[:H // 2, :W // 3] = 1                                   # solid regions and edges, not only noise
+    ref = cv2.resize(m, (int(W * 0.25 + 0.5), int(H * 0.25 + 0.5)), interpolation=cv2.INTER_LINEAR)
+    ref = ref[..., None] if ref.ndim == 2 else ref
+    got = T.quarter_masks(torch.from_numpy(m).permute(2, 0, 1))
+    assert got.dtype == torch.uint8 and np.array_equal(got.numpy(), ref.transpose(2, 0, 1))
+    with pytest.raises(ValueError):
+        T.quarter_masks(torch.zeros(1, 30, 40))
+
+
+@pytest.mark.parametrize("name", list(LC.CASES))
+def test_assignment_equals_oracle(name):
+    _, _, _, _, gts, _ = LC.synth(**LC.CASES[name])
+    for gt in gts:
+        ref = LO.assign_targets(gt, (120, 160))
+        got = T.assign_targets(gt, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"], LO.CFG["num_classes"], LO.CFG["sigma"])
+        assert len(got) == len(ref) == 4
+        for (gi, gc, gd, go), (ri, rc, rd, ro) in zip(got, ref):
+            assert go == ro
+            assert torch.equal(gc, rc) and torch.equal(gd, rd)
+            assert gi.shape == ri.shape and torch.equal(gi, ri)
+
+
+def test_assignment_skips_empty_masks_and_out_of_range_boxes():
+    masks = torch.zeros(3, 480, 640, dtype=torch.uint8)
+    masks[1, 100:300, 200:500] = 1
+    gt = dict(masks=masks, classes=torch.zeros(3, dtype=torch.int64),
+              boxes=torch.tensor([[10, 10, 200, 200], [200, 100, 500, 300], [0, 0, 0.5, 0.5]], dtype=torch.float64))
+    got = T.assign_targets(gt, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"])
+    ref = LO.assign_targets(gt, (120, 160))
+    for (gi, gc, gd, go), (ri, rc, rd, ro) in zip(got, ref):
+        assert go == ro and torch.equal(gc, rc) and torch.equal(gd, rd) and torch.equal(gi, ri)
+    assert sum(len(t[3]) for t in got) > 0
