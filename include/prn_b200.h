@@ -286,6 +286,22 @@ int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin
 int prn_adam_multi(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
                    float* state3, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- dense parts of PlaneRecNetLoss (models/functions/losses.py), fp32 ------------------------------ */
+
+/* SigmoidFocalLoss(alpha, gamma, reduction='sum') over all grid cells (losses.py:121-138, 331-352): logits fp32 [n][ld]
+ * (first nc columns valid), labels int64 [n] with nc = background (all-zero one-hot row).  *loss_sum += the loss;
+ * dlogits fp32 [n][nc] (optional) = d(loss_sum)/d(logits).  The caller applies focal_weight / (num_ins + 1). */
+int prn_focal_loss(const float* logits, const int64_t* labels, float alpha, float gamma, float* loss_sum, float* dlogits, int64_t n,
+                   int32_t ld, int32_t nc, void* stream);
+/* depth_weight * RMSElogLoss(reduction='mean') on F.interpolate(depth, x2 bilinear) vs gt with valid = gt > min_depth
+ * (losses.py:141-147, 371-392): depth fp32 [B,h,w], gt fp32 [B,2h,2w]; sums fp32 [B][2] (caller zeroes), loss fp32 [1],
+ * coef fp32 [B] (per-image factor reused by the backward). */
+int prn_depth_rmselog_fwd(const float* depth, const float* gt, float* sums, float* loss, float* coef, int32_t batch, int32_t h,
+                          int32_t w, float min_depth, float clamp_val, float weight, void* stream);
+/* d_depth fp32 [B,h,w] (caller zeroes) += d(loss)/d(depth), scattered through the transpose of the x2 resampler. */
+int prn_depth_rmselog_bwd(const float* depth, const float* gt, const float* coef, float* d_depth, int32_t batch, int32_t h, int32_t w,
+                          float min_depth, float clamp_val, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
