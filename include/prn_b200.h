@@ -302,6 +302,21 @@ int prn_depth_rmselog_fwd(const float* depth, const float* gt, float* sums, floa
 int prn_depth_rmselog_bwd(const float* depth, const float* gt, const float* coef, float* d_depth, int32_t batch, int32_t h, int32_t w,
                           float min_depth, float clamp_val, void* stream);
 
+/* Dice (losses.py:101-111, 355-368) and depth-gradient "lava" (losses.py:168-197, 277-286) terms over the instance rows
+ * seg fp32 [rows][pixels] = sigmoid(dynamic conv of the mask features with the positive cells' kernels; a grouped
+ * prn_conv2d_fwd with PRN_ACT_SIGMOID), rows grouped per image (image = row / rows_per_img); target uint8 [rows][pixels];
+ * gw fp32 [B][pixels] from prn_lava_weights.  stats fp32 [rows][4] = {sum s*t, sum s*s, sum t*t, sum s*gw}. */
+int prn_dice_lava_rows(const float* seg, const uint8_t* target, const float* gw, float* stats, int32_t rows, int32_t pixels,
+                       int32_t rows_per_img, void* stream);
+/* dx16[row][p] = (coef[row][0]*t + 2*coef[row][1]*s + coef[row][2]*gw) * s*(1-s): gradient w.r.t. the pre-sigmoid rows. */
+int prn_dice_lava_bwd(const float* seg, const uint8_t* target, const float* gw, const float* coef, void* dx16, int32_t rows,
+                      int32_t pixels, int32_t rows_per_img, int32_t dtype, void* stream);
+/* Lava pixel weights: gmap = min(|sobel/8 of reflect-padded gt|^2 / max(gt, depth_res)^2, 1e-2), 0 below 1e-4
+ * (losses.py:186-188, 288-329), pulled back through the bilinear resize [h,w] -> [H,W] of LavaLoss (losses.py:283):
+ * gw fp32 [B][h*w] and gsum fp32 [B] (both zeroed by the caller) are accumulated. */
+int prn_lava_weights(const float* gt, float* gw, float* gsum, int32_t batch, int32_t H, int32_t W, int32_t h, int32_t w, float depth_res,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,3 +171,141 @@ int prn_depth_rmselog_bwd(const float* depth, const float* gt, const float* coef
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- dice + depth-gradient ("lava") terms over instance rows
+// seg fp32 [rows][P] = sigmoid mask probabilities of the positive cells' dynamic convolutions (one row per instance,
+// rows grouped per image: image = row / rows_per_img); target uint8 [rows][P]; gw fp32 [B][P] = per-image pixel weights of
+// the lava term (the depth-gradient map pulled back through the bilinear x4 resampler).
+//   stats[row] = {a = sum s*t, b = sum s*s, c = sum t*t, lv = sum s*gw}          (losses.py:355-368, 277-286)
+namespace prn {
+
+__global__ void __launch_bounds__(256) dice_lava_rows_kernel(const float* __restrict__ seg, const unsigned char* __restrict__ target,
+                                                           const float* __restrict__ gw, float* __restrict__ stats, int P,
+                                                           int rows_per_img) {
+  const int row = blockIdx.x;
+  const float* s = seg + static_cast<long long>(row) * P;
+  const unsigned char* t = target + static_cast<long long>(row) * P;
+  const float* g = gw + static_cast<long long>(row / rows_per_img) * P;
+  float a = 0.f, b = 0.f, c = 0.f, lv = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float sv = __ldg(s + i), tv = static_cast<float>(t[i]);
+    a = fmaf(sv, tv, a);
+    b = fmaf(sv, sv, b);
+    c = fmaf(tv, tv, c);
+    lv = fmaf(sv, __ldg(g + i), lv);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    lv += __shfl_xor_sync(0xffffffffu, lv, o);
+  }
+  __shared__ float red[8][4];
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = a; red[threadIdx.x >> 5][1] = b; red[threadIdx.x >> 5][2] = c; red[threadIdx.x >> 5][3] = lv; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    stats[static_cast<long long>(row) * 4 + threadIdx.x] = v;
+  }
+}
+
+// dx[row][p] = (ca*t + 2*cb*s + cl*gw) * s * (1 - s), coef[row] = {ca, cb, cl}; 16-bit output (operand of the two gradient
+// contractions); rows with all-zero coefficients (padding) produce zeros
+template <typename T>
+__global__ void dice_lava_bwd_kernel(const float* __restrict__ seg, const unsigned char* __restrict__ target, const float* __restrict__ gw,
+                                     const float* __restrict__ coef, T* __restrict__ dx, int P, int rows_per_img, long long total8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int row = static_cast<int>(e / P), p = static_cast<int>(e - static_cast<long long>(row) * P);
+    const float ca = __ldg(coef + 3 * row), cb = __ldg(coef + 3 * row + 1), cl = __ldg(coef + 3 * row + 2);
+    const float* g = gw + static_cast<long long>(row / rows_per_img) * P + p;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sv = __ldg(seg + e + j), tv = static_cast<float>(target[e + j]);
+      o[j] = (ca * tv + 2.f * cb * sv + cl * __ldg(g + j)) * sv * (1.f - sv);
+    }
+    store8(dx + e, o);
+  }
+}
+
+// Lava pixel weights: gmap = clamp(sobel(gt)^2-sum / max(gt, res)^2, max 1e-2), zeroed below 1e-4 (losses.py:288-329, 186-188),
+// pulled back through F.interpolate(seg, size=(H, W), bilinear, align_corners=False) from [h, w] = [H/4, W/4]:
+// gw[b][y][x] += weight of (Y, X) on (y, x) * gmap[b][Y][X];  gsum[b] += gmap.  One thread per full-resolution pixel.
+__global__ void lava_weights_kernel(const float* __restrict__ gt, float* __restrict__ gw, float* __restrict__ gsum, int H, int W, int h,
+                                    int w, float depth_res) {
+  const int b = blockIdx.y;
+  const float* d = gt + static_cast<long long>(b) * H * W;
+  float* o = gw + static_cast<long long>(b) * h * w;
+  const float sy_scale = static_cast<float>(h) / static_cast<float>(H), sx_scale = static_cast<float>(w) / static_cast<float>(W);
+  float local = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int Y = i / W, X = i % W;
+    auto at = [&](int yy, int xx) {      // reflect padding by 1
+      yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);
+      xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+      return __ldg(d + yy * W + xx);
+    };
+    const float gx = (at(Y - 1, X - 1) - at(Y - 1, X + 1) + 2.f * (at(Y, X - 1) - at(Y, X + 1)) + at(Y + 1, X - 1) - at(Y + 1, X + 1)) * 0.125f;
+    const float gy = (at(Y - 1, X - 1) + 2.f * at(Y - 1, X) + at(Y - 1, X + 1) - at(Y + 1, X - 1) - 2.f * at(Y + 1, X) - at(Y + 1, X + 1)) * 0.125f;
+    const float dc = fmaxf(at(Y, X), depth_res);
+    float gm = (gx * gx + gy * gy) / (dc * dc);
+    gm = fminf(gm, 1e-2f);
+    if (gm < 1e-4f) gm = 0.f;
+    if (gm == 0.f) continue;
+    local += gm;
+    // source coordinates of the resampler at (Y, X)
+    float fy = (static_cast<float>(Y) + 0.5f) * sy_scale - 0.5f, fx = (static_cast<float>(X) + 0.5f) * sx_scale - 0.5f;
+    fy = fy < 0.f ? 0.f : fy;
+    fx = fx < 0.f ? 0.f : fx;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    y0 = y0 > h - 1 ? h - 1 : y0;
+    x0 = x0 > w - 1 ? w - 1 : x0;
+    const int y1 = y0 < h - 1 ? y0 + 1 : y0, x1 = x0 < w - 1 ? x0 + 1 : x0;
+    const float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+    atomicAdd(o + y0 * w + x0, gm * (1.f - ly) * (1.f - lx));
+    atomicAdd(o + y0 * w + x1, gm * (1.f - ly) * lx);
+    atomicAdd(o + y1 * w + x0, gm * ly * (1.f - lx));
+    atomicAdd(o + y1 * w + x1, gm * ly * lx);
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) local += __shfl_xor_sync(0xffffffffu, local, k);
+  if ((threadIdx.x & 31) == 0 && local != 0.f) atomicAdd(gsum + b, local);
+}
+
+}  // namespace prn
+
+extern "C" {
+
+int prn_dice_lava_rows(const float* seg, const uint8_t* target, const float* gw, float* stats, int32_t rows, int32_t pixels,
+                       int32_t rows_per_img, void* stream) {
+  PRN_REQUIRE(seg && target && gw && stats && rows > 0 && pixels > 0 && rows_per_img > 0 && rows % rows_per_img == 0,
+              "dice_lava_rows: bad arguments");
+  dice_lava_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(seg, target, gw, stats, pixels, rows_per_img);
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_dice_lava_bwd(const float* seg, const uint8_t* target, const float* gw, const float* coef, void* dx16, int32_t rows,
+                      int32_t pixels, int32_t rows_per_img, int32_t dtype, void* stream) {
+  PRN_REQUIRE(seg && target && gw && coef && dx16 && rows > 0 && pixels > 0 && pixels % 8 == 0 && rows_per_img > 0 &&
+                  rows % rows_per_img == 0, "dice_lava_bwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total8 = static_cast<long long>(rows) * pixels / 8;
+  PRN_DISPATCH(dtype,
+               (dice_lava_bwd_kernel<__nv_bfloat16><<<pw_grid(total8), kPwThreads, 0, st>>>(seg, target, gw, coef, static_cast<__nv_bfloat16*>(dx16), pixels, rows_per_img, total8)),
+               (dice_lava_bwd_kernel<__half><<<pw_grid(total8), kPwThreads, 0, st>>>(seg, target, gw, coef, static_cast<__half*>(dx16), pixels, rows_per_img, total8)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_lava_weights(const float* gt, float* gw, float* gsum, int32_t batch, int32_t H, int32_t W, int32_t h, int32_t w, float depth_res,
+                     void* stream) {
+  PRN_REQUIRE(gt && gw && gsum && batch > 0 && H > 2 && W > 2 && h > 0 && w > 0, "lava_weights: bad arguments");
+  const dim3 grid(static_cast<unsigned>(pw_grid(static_cast<long long>(H) * W / 4 + 1)), static_cast<unsigned>(batch));
+  lava_weights_kernel<<<grid, kPwThreads, 0, static_cast<cudaStream_t>(stream)>>>(gt, gw, gsum, H, W, h, w, depth_res);
+  PRN_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -3,10 +3,13 @@
   focal_cate_loss(cate32, labels, num_ins)   losses.py:121-138  sigmoid focal over all grid cells / (num_ins + 1)
   depth_rmselog_loss(depth_pred, gt_depths)  losses.py:141-147  depth_weight * RMSE-log on the x2-upsampled prediction
 
-The dice / lava terms (dynamic 1x1 convolutions of the mask features with the positive cells' kernels) and the plane
-normal loss are not built yet; the reference's own implementations run on the training outputs unchanged meanwhile.
+  ins_lava_losses(mask_pred, kernel_preds, targets, gt_depths)   losses.py:81-118, 168-197  dice + depth-gradient terms
+
+The plane-normal term (numpy-RNG triplet sampling, vnl.py) is not built; the reference's implementation runs on the
+training outputs unchanged meanwhile.
 Targets come from planerecnet_b200.targets (device-resident assignment)."""
 import ctypes as C
+import math
 
 import torch
 
@@ -75,3 +78,157 @@ class _DepthRMSELog(torch.autograd.Function):
 def depth_rmselog_loss(depth_pred, gt_depths, min_depth=1 / 1000, clamp_val=1e-9, weight=5.0):
     """depth_pred fp32 [B,1,h,w] (the model's training output), gt_depths [B,1,2h,2w]."""
     return _DepthRMSELog.apply(depth_pred, gt_depths, min_depth, clamp_val, weight)
+
+
+# ------------------------------------------------------------------------------------------ dice + lava terms
+class CudaBackend:
+    """The five device steps of the instance-mask losses on libprn_b200 (tests substitute a torch emulation to check the
+    orchestration and the gradient algebra on the CPU)."""
+
+    def __init__(self, dtype=L.PRN_F16):
+        # f16 operands: the dice gradient is cancellation-dominated (positive and negative regions of a mask nearly
+        # cancel in the sums over pixels), so 10 mantissa bits matter; the gradient rows are pre-scaled into f16's range
+        from . import ops
+        self.ops, self.dt, self.tdt = ops, dtype, ops.torch_dtype(dtype)
+
+    def to16(self, t):
+        return t.to(self.tdt).contiguous()
+
+    def seg_rows(self, wsel16, mask16):
+        """sigmoid(K_sel . mask^T): wsel16 [B,n,C], mask16 [B,P,C] -> fp32 [B*n, P] (grouped contraction, per-image operands)."""
+        B, n, Cc = wsel16.shape
+        P = mask16.shape[1]
+        seg = torch.empty(B * n, P, device=wsel16.device)
+        self.ops.conv2d(wsel16, mask16.reshape(B * P, Cc), batch=B, h_in=n, w_in=1, ksize=1, act=L.ACT_SIGMOID, out32=seg,
+                        ld_out32=P, n_pad=P, w_group_rows=P, dtype=self.dt)
+        return seg
+
+    def row_stats(self, seg, target, gw, n):
+        stats = torch.empty(seg.shape[0], 4, device=seg.device)
+        L.check(L.lib().prn_dice_lava_rows(_p(seg), _p(target), _p(gw), _p(stats), seg.shape[0], seg.shape[1], n, L.current_stream()),
+                "prn_dice_lava_rows")
+        return stats
+
+    def row_bwd(self, seg, target, gw, coef, n):
+        dx = torch.empty(seg.shape, dtype=self.tdt, device=seg.device)
+        L.check(L.lib().prn_dice_lava_bwd(_p(seg), _p(target), _p(gw), _p(coef), _p(dx), seg.shape[0], seg.shape[1], n, self.dt,
+                                          L.current_stream()), "prn_dice_lava_bwd")
+        return dx
+
+    def grouped_nt(self, a16, w16):
+        """out[b] = a16[b] @ w16[b]^T in fp32: a16 [B,m,K], w16 [B,N,K] (K multiple of 64, N multiple of 16)."""
+        B, m, K = a16.shape
+        N = w16.shape[1]
+        out = torch.empty(B * m, N, device=a16.device)
+        self.ops.conv2d(a16.reshape(B, m, 1, K), w16.reshape(B * N, K), batch=B, h_in=m, w_in=1, ksize=1, out32=out, ld_out32=N,
+                        n_pad=N, w_group_rows=N, dtype=self.dt)
+        return out.view(B, m, N)
+
+    def lava_weights(self, gt, h, w, depth_res):
+        B, _, H, W = gt.shape
+        gw = torch.zeros(B, h * w, device=gt.device)
+        gsum = torch.zeros(B, device=gt.device)
+        gt32 = gt.float().contiguous()             # named: the pointer must outlive the launch
+        L.check(L.lib().prn_lava_weights(_p(gt32), _p(gw), _p(gsum), B, H, W, h, w, C.c_float(depth_res), L.current_stream()),
+                "prn_lava_weights")
+        return gw, gsum
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _InsLava(torch.autograd.Function):
+    """(dice instance loss, lava loss) of losses.py:81-118, 168-197 as one node: the positive cells' kernels are gathered
+    into per-image row blocks, their masks come from one grouped tensor-core contraction, the per-row sums and the
+    gradient rows from two passes, and the two gradient contractions (w.r.t. kernels: over pixels; w.r.t. mask features:
+    over instances) from the same grouped contraction.  Per-row scalar algebra (a few hundred numbers) stays in torch."""
+
+    @staticmethod
+    def forward(ctx, be, targets, gw, gsum, w_dice, w_lava, mask_pred, *kernel_preds):
+        B, Cc, fh, fw = mask_pred.shape
+        P = fh * fw
+        dev = mask_pred.device
+        n_levels = len(kernel_preds)
+        counts = [[len(targets[b][l][3]) for l in range(n_levels)] for b in range(B)]
+        n_b = [sum(c) for c in counts]
+        n = _round_up(max(max(n_b), 1), 16)
+        wsel = torch.zeros(B, n, Cc, device=dev)
+        tgt = torch.zeros(B, n, P, dtype=torch.uint8, device=dev)
+        valid = torch.zeros(B, n, dtype=torch.bool, device=dev)
+        for b in range(B):
+            off = 0
+            for l in range(n_levels):
+                order = targets[b][l][3]
+                if order:
+                    idx = torch.tensor(order, device=dev)
+                    wsel[b, off:off + len(order)] = kernel_preds[l][b].reshape(Cc, -1)[:, idx].t()
+                    tgt[b, off:off + len(order)] = targets[b][l][0].reshape(len(order), P).to(dev)
+                    off += len(order)
+            valid[b, :n_b[b]] = True
+        mask16 = be.to16(mask_pred.reshape(B, Cc, P).transpose(1, 2))        # [B, P, C]
+        wsel16 = be.to16(wsel)
+        seg = be.seg_rows(wsel16, mask16)                                     # [B*n, P] sigmoid probabilities
+        stats = be.row_stats(seg, tgt.view(B * n, P), gw, n).view(B, n, 4)
+        a, bq, c, lv = stats.unbind(-1)
+        n_total = max(sum(n_b), 1)
+        den = bq + c + 0.002
+        dice = torch.where(valid, 1 - 2 * a / den, torch.zeros_like(a))
+        loss_ins = w_dice * dice.sum() / n_total
+        nb_t = torch.tensor(n_b, dtype=torch.float32, device=dev)
+        elig = (nb_t > 0) & (gsum > 0)
+        n_elig = int(elig.sum())
+        per_img = torch.where(elig, (lv * valid).sum(1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
+        loss_lav = w_lava * per_img.sum() / n_elig if n_elig else torch.zeros((), device=dev)
+        # d(loss)/d{a, b, lv} per row
+        ca = torch.where(valid, -w_dice / n_total * 2 / den, torch.zeros_like(a))
+        cb = torch.where(valid, w_dice / n_total * 2 * a / (den * den), torch.zeros_like(a))
+        cl_img = torch.where(elig, w_lava / max(n_elig, 1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
+        cl = cl_img[:, None] * valid
+        ctx.be, ctx.targets, ctx.counts, ctx.shapes = be, targets, counts, (B, Cc, fh, fw, n, [k.shape for k in kernel_preds])
+        ctx.save_for_backward(seg, tgt, gw, mask16, wsel16, ca, cb, cl)
+        return loss_ins, loss_lav
+
+    @staticmethod
+    def backward(ctx, g_ins, g_lav):
+        be = ctx.be
+        seg, tgt, gw, mask16, wsel16, ca, cb, cl = ctx.saved_tensors
+        B, Cc, fh, fw, n, kshapes = ctx.shapes
+        P = fh * fw
+        dev = seg.device
+        coef = torch.stack([ca * g_ins, cb * g_ins, cl * g_lav], -1).reshape(B * n, 3)
+        # power-of-two scale that puts the largest possible |dx| near 2^12 (16-bit storage of the gradient rows)
+        bound = float(((coef[:, 0].abs() + 2 * coef[:, 1].abs()).max() + coef[:, 2].abs().max() * gw.max()) * 0.25)
+        scale = 2.0 ** math.floor(math.log2(4096.0 / bound)) if bound > 0 and math.isfinite(bound) else 1.0
+        coef = (coef * scale).contiguous()
+        dx16 = be.row_bwd(seg, tgt.view(B * n, P), gw, coef, n).view(B, n, P)        # scaled gradient of the pre-sigmoid rows
+        # w.r.t. the selected kernels: dK[b] = dX[b] (n x P) . mask[b] (P x C)
+        dK = be.grouped_nt(dx16, mask16.transpose(1, 2).contiguous()) / scale       # [B, n, C]
+        # w.r.t. the mask features: dM[b] = dX[b]^T (P x n) . K_sel[b] (n x C)
+        n64 = _round_up(n, 64)
+        dxT = torch.zeros(B, P, n64, dtype=dx16.dtype, device=dev)
+        dxT[:, :, :n] = dx16.transpose(1, 2)
+        kT = torch.zeros(B, Cc, n64, dtype=wsel16.dtype, device=dev)
+        kT[:, :, :n] = wsel16.transpose(1, 2)
+        dM = be.grouped_nt(dxT, kT) / scale                                           # [B, P, C]
+        d_mask = dM.transpose(1, 2).reshape(B, Cc, fh, fw).contiguous()
+        d_kern = []
+        for l, shp in enumerate(kshapes):
+            gk = torch.zeros(shp, device=dev)
+            for b in range(B):
+                order = ctx.targets[b][l][3]
+                if order:
+                    off = sum(ctx.counts[b][:l])
+                    gk[b].view(Cc, -1).index_add_(1, torch.tensor(order, device=dev), dK[b, off:off + len(order)].t().float())
+            d_kern.append(gk)
+        return (None, None, None, None, None, None, d_mask, *d_kern)
+
+
+def ins_lava_losses(mask_pred, kernel_preds, targets, gt_depths, backend=None, dice_weight=3.0, lava_weight=1.0,
+                    depth_resolution=1 / 1000):
+    """(losses['ins'], losses['lav']) of PlaneRecNetLoss.forward for the model's training outputs mask_pred [B,128,h,w] and
+    kernel_preds [[B,128,S,S]] x levels; targets[b][level] from planerecnet_b200.targets.assign_targets."""
+    be = backend or CudaBackend()
+    fh, fw = mask_pred.shape[-2:]
+    gw, gsum = be.lava_weights(gt_depths, fh, fw, depth_resolution)
+    return _InsLava.apply(be, targets, gw, gsum, dice_weight, lava_weight, mask_pred, *kernel_preds)

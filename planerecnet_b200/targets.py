@@ -5,7 +5,12 @@ them back (losses.py:243-247).  For binary masks and an exact 1/4 scale that res
 1 iff at least two of the four centre pixels of its 4x4 block are set (cv2's fixed-point bilinear with weights 1/2, 1/2
 rounds 0.5 up; checked against cv2 in tests/test_targets_cpu.py) — so the whole assignment runs where the masks live, with
 one host round trip per FPN level for the handful of integer cell coordinates.  Plain tensor indexing only (no arithmetic
-hot path); device-agnostic, which is what lets the CPU suite compare it with the oracle bit for bit."""
+hot path); device-agnostic, which is what lets the CPU suite compare it with the oracle bit for bit.
+
+Open point (round 2): run on CUDA, one of the three synthetic cases (integer boxes, centres on exact multiples of the grid
+pitch) resolves a cell boundary differently from the CPU run although every step is meant to be exact — the reference's
+`(c / extent) // (1 / S)` in float32 sits on such boundaries.  tests/test_loss_kernels_gpu.py therefore feeds the losses
+with the CPU assignment and only reports whether the device-side one agrees."""
 import torch
 
 
@@ -40,12 +45,15 @@ def assign_targets(gt, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.
         bx, lb, mk = boxes[hit], labels[hit], masks[hit]
         half_w = 0.5 * (bx[:, 2] - bx[:, 0]) * sigma
         half_h = 0.5 * (bx[:, 3] - bx[:, 1]) * sigma
-        # centre of mass (funcs.py:213-224)
-        ys = torch.arange(mk.shape[1], dtype=torch.float32, device=dev)
-        xs = torch.arange(mk.shape[2], dtype=torch.float32, device=dev)
-        m00 = mk.sum(-1).sum(-1).clamp(min=1e-6)
-        cw = (mk * xs).sum(-1).sum(-1) / m00
-        ch = (mk * ys[:, None]).sum(-1).sum(-1) / m00
+        # centre of mass (funcs.py:213-224).  The moments are sums of up to 3e5 pixel coordinates: accumulated in float64
+        # they are exact and therefore identical on every device, whereas the reference's float32 sums depend on the
+        # reduction order (its own CPU and CUDA runs can put a centre on different sides of a grid-cell boundary).
+        ys = torch.arange(mk.shape[1], dtype=torch.float64, device=dev)
+        xs = torch.arange(mk.shape[2], dtype=torch.float64, device=dev)
+        mk64 = mk.to(torch.float64)
+        m00 = mk64.sum(-1).sum(-1).clamp(min=1e-6)
+        cw = ((mk64 * xs).sum(-1).sum(-1) / m00).to(torch.float32)
+        ch = ((mk64 * ys[:, None]).sum(-1).sum(-1) / m00).to(torch.float32)
         nonempty = mk.sum(-1).sum(-1) > 0
 
         def cell(v, extent):                       # int((v / extent) // (1 / S)) of the reference, for all instances at once

@@ -49,3 +49,65 @@ def test_depth_rmselog_loss(cuda_lib, B, h, w):
     (2.0 * got).backward()
     assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref))
     assert float((dd.grad.cpu() / 2.0 - d.grad).abs().max()) <= 1e-4 * float(d.grad.abs().max())
+
+
+def test_dice_lava_row_kernels_match_emulation(cuda_lib):
+    """prn_lava_weights / prn_dice_lava_rows / prn_dice_lava_bwd against their torch emulation on identical fp32 inputs."""
+    import loss_cases as LC
+    from loss_emulation import EmuBackend
+    emu, be = EmuBackend(), PL.CudaBackend()
+    g = torch.Generator().manual_seed(0)
+    gt = 0.5 + 4 * torch.rand(2, 1, 96, 128, generator=g)
+    gt[:, :, 20:60, 30:90] += torch.linspace(0, 3, 60)[None, None, None, :]          # a slope and steps: non-trivial gradients
+    gw_r, gs_r = emu.lava_weights(gt, 24, 32, 1 / 1000)
+    gw, gs = be.lava_weights(gt.cuda(), 24, 32, 1 / 1000)
+    assert float(gs_r.min()) > 0
+    assert float((gs.cpu() - gs_r).abs().max()) <= 1e-4 * float(gs_r.max())
+    assert float((gw.cpu() - gw_r).abs().max()) <= 1e-4 * float(gw_r.max())
+    B, n, P = 2, 16, 24 * 32
+    seg = torch.rand(B * n, P, generator=g)
+    tgt = (torch.rand(B * n, P, generator=g) < 0.3).to(torch.uint8)
+    st_r = emu.row_stats(seg, tgt, gw_r, n)
+    st = be.row_stats(seg.cuda(), tgt.cuda(), gw, n)
+    assert float((st.cpu() - st_r).abs().max() / st_r.abs().max()) <= 1e-5
+    coef = torch.randn(B * n, 3, generator=g)
+    dx_r = emu.row_bwd(seg, tgt, gw_r, coef, n)
+    dx = be.row_bwd(seg.cuda(), tgt.cuda(), gw, coef.cuda(), n)
+    assert float((dx.float().cpu() - dx_r).abs().max()) <= (2.0 ** -8 + 1e-4) * float(dx_r.abs().max())      # one 16-bit rounding
+
+
+@pytest.mark.parametrize("name", ["loss_seed0", "loss_seed2_many_tiny"])
+def test_ins_lava_losses_match_oracle(cuda_lib, name):
+    """The dice and lava terms end to end on the GPU (f16 operands of the three grouped contractions, fp32 sums) against
+    the oracle: values within 1e-2, gradients w.r.t. the mask features and every level's kernels by cosine / rel-L2."""
+    import numpy as np
+    import loss_cases as LC
+    from helpers import rel_l2
+    from planerecnet_b200 import targets as T
+    mask, cate, kern, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+    leaves = [mask] + kern
+    for t in leaves:
+        t.requires_grad_(True)
+    np.random.seed(0)
+    ref = LO.loss_forward(mask, cate, kern, depth, gts, gt_depth)
+    (ref["ins"] + ref["lav"].sum()).backward()
+    dm, dk = mask.detach().cuda().requires_grad_(True), [k.detach().cuda().requires_grad_(True) for k in kern]
+    # targets from the same (CPU) assignment the oracle uses; the device-side assignment is compared with it below
+    targets = [T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"]) for g in gts]
+    gts_d = [{k: v.cuda() for k, v in g.items()} for g in gts]
+    targets_dev = [T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"]) for g in gts_d]
+    same = all(td[3] == tc[3] and torch.equal(td[0].cpu(), tc[0]) for a, b in zip(targets_dev, targets) for td, tc in zip(a, b))
+    print(f"{name}: device-side target assignment identical to the CPU one: {same}")
+    l_ins, l_lav = PL.ins_lava_losses(dm, dk, targets, gt_depth.cuda())
+    (l_ins + l_lav).backward()
+    assert abs(float(l_ins) - float(ref["ins"])) <= 1e-2 * abs(float(ref["ins"]))
+    assert abs(float(l_lav) - float(ref["lav"].sum())) <= 1e-2 * abs(float(ref["lav"].sum()))
+    for got, t in zip([dm] + dk, leaves):
+        if t.grad is None or float(t.grad.abs().max()) == 0.0:
+            assert got.grad is None or float(got.grad.abs().max()) == 0.0
+            continue
+        a, b = got.grad.cpu().double().flatten(), t.grad.double().flatten()
+        cos = float((a @ b) / (a.norm() * b.norm()))
+        print(f"{name}: grad {tuple(t.shape)} cos {cos:.5f} rel-L2 {rel_l2(got.grad.cpu(), t.grad):.3e}")
+        # the dice gradient is cancellation-dominated: 16-bit rounding of the operands is amplified (cf. DESIGN §4)
+        assert cos >= 0.995 and rel_l2(got.grad.cpu(), t.grad) <= 0.1, (cos, rel_l2(got.grad.cpu(), t.grad))

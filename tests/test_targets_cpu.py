@@ -48,3 +48,32 @@ def test_assignment_skips_empty_masks_and_out_of_range_boxes():
     for (gi, gc, gd, go), (ri, rc, rd, ro) in zip(got, ref):
         assert go == ro and torch.equal(gc, rc) and torch.equal(gd, rd) and torch.equal(gi, ri)
     assert sum(len(t[3]) for t in got) > 0
+
+
+@pytest.mark.parametrize("name", ["loss_seed0", "loss_seed2_many_tiny"])
+def test_ins_lava_orchestration_equals_oracle_on_cpu(name):
+    """planerecnet_b200.losses.ins_lava_losses with the torch emulation of its five device steps == the oracle's 'ins' and
+    'lav' terms and their gradients w.r.t. the mask features and every level's kernels (fp32, 1e-4)."""
+    import numpy as np
+    from loss_emulation import EmuBackend
+    from planerecnet_b200 import losses as PL
+    mask, cate, kern, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+    leaves = [mask] + kern
+    for t in leaves:
+        t.requires_grad_(True)
+    np.random.seed(0)
+    ref = LO.loss_forward(mask, cate, kern, depth, gts, gt_depth)
+    (ref["ins"] + 2.0 * ref["lav"].sum()).backward()
+    ref_g = [None if t.grad is None else t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+    targets = [T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"]) for g in gts]
+    l_ins, l_lav = PL.ins_lava_losses(mask, kern, targets, gt_depth, backend=EmuBackend())
+    assert abs(float(l_ins) - float(ref["ins"])) <= 1e-5 * abs(float(ref["ins"]))
+    assert abs(float(l_lav) - float(ref["lav"].sum())) <= 1e-5 * abs(float(ref["lav"].sum()))
+    (l_ins + 2.0 * l_lav).backward()
+    for t, rg in zip(leaves, ref_g):
+        if rg is None:
+            assert t.grad is None or float(t.grad.abs().max()) == 0.0
+        else:
+            assert float((t.grad - rg).abs().max()) <= 1e-4 * float(rg.abs().max())
