@@ -71,6 +71,8 @@ PlaneRecNet_101_config = Config({
     # loss weights (data/config.py:459-468, 511-514) — carried for callers, unused by the dense forward
     "dice_weight": 3.0, "focal_weight": 1.0, "depth_weight": 5.0, "use_lava_loss": True, "use_plane_loss": True,
     "lava_weight": 1.0, "pln_weight": 1.0, "focal_gamma": 2.0, "focal_alpha": 0.25,
+    # scannet_dataset (data/config.py:113-136): only what the loss reads
+    "dataset": Config({"name": "ScanNetDataset", "depth_resolution": 1 / 1000, "min_depth": 1 / 1000, "max_depth": 40}),
 })
 
 PlaneRecNet_50_config = PlaneRecNet_101_config.copy({"name": "PlaneRecNet_50", "backbone": resnet50_dcnv2_backbone})

@@ -124,6 +124,12 @@ class CudaBackend:
                         n_pad=N, w_group_rows=N, dtype=self.dt)
         return out.view(B, m, N)
 
+    def focal_sum(self, logits, labels, alpha, gamma, nc):
+        return _FocalSum.apply(logits, labels, alpha, gamma, nc)
+
+    def depth_rmselog(self, depth, gt, min_depth, clamp_val, weight):
+        return _DepthRMSELog.apply(depth, gt, min_depth, clamp_val, weight)
+
     def lava_weights(self, gt, h, w, depth_res):
         B, _, H, W = gt.shape
         gw = torch.zeros(B, h * w, device=gt.device)
@@ -232,3 +238,144 @@ def ins_lava_losses(mask_pred, kernel_preds, targets, gt_depths, backend=None, d
     fh, fw = mask_pred.shape[-2:]
     gw, gsum = be.lava_weights(gt_depths, fh, fw, depth_resolution)
     return _InsLava.apply(be, targets, gw, gsum, dice_weight, lava_weight, mask_pred, *kernel_preds)
+
+
+# ------------------------------------------------------------------------------------------ plane surface-normal term
+class _PlaneNormal:
+    """models/functions/vnl.py:6-165.  Host-side by design: the triplets are drawn with numpy's global
+    RNG per plane, so the sampling stays in Python in the reference's call order; the few thousand 3x3 cross products run
+    as torch ops on the depth map's device."""
+
+    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4):
+        self.size, self.ratio, self.delta_z = size, sample_ratio, delta_z
+        self._grid = {}
+
+    def _uv(self, dev):
+        if dev not in self._grid:
+            h, w = self.size
+            u = (torch.arange(w, dtype=torch.float32, device=dev)[None, None, :] - float(w // 2)).expand(1, h, w)
+            v = (torch.arange(h, dtype=torch.float32, device=dev)[None, :, None] - float(h // 2)).expand(1, h, w)
+            self._grid[dev] = (u, v)
+        return self._grid[dev]
+
+    def points(self, depth, K):
+        u, v = self._uv(depth.device)
+        return torch.cat([u * depth.abs() / K[0, 0], v * depth.abs() / K[1, 1], depth], 0).permute(1, 2, 0)
+
+    def sample(self, num):
+        import numpy as np
+        assert num <= self.size[0] * self.size[1]
+        idx = []
+        for _ in range(3):
+            p = np.random.choice(num, int(num * self.ratio), replace=True)
+            np.random.shuffle(p)
+            idx.append(p)
+        return idx
+
+    @staticmethod
+    def groups(idx, pts):
+        return torch.stack([pts[idx[0]], pts[idx[1]], pts[idx[2]]], 2)
+
+    def usable(self, idx, pts, delta_cos=0.985, delta_diff=0.005):
+        g = self.groups(idx, pts)
+        diff = torch.stack([g[:, :, 1] - g[:, :, 0], g[:, :, 2] - g[:, :, 0], g[:, :, 2] - g[:, :, 1]], 2)
+        q = diff.permute(0, 2, 1)
+        qn = q.norm(2, dim=2)
+        cosm = (torch.bmm(q, diff) / (torch.bmm(qn.unsqueeze(2), qn.unsqueeze(1)) + 1e-8)).reshape(diff.shape[0], -1)
+        colinear = ((cosm > delta_cos) | (cosm < -delta_cos)).sum(1) > 3
+        in_front = (g[:, 2, :] > self.delta_z).sum(1) == 3
+        near = (((diff[:, 0, :].abs() < delta_diff).sum(1) > 0) & ((diff[:, 1, :].abs() < delta_diff).sum(1) > 0) &
+                ((diff[:, 2, :].abs() < delta_diff).sum(1) > 0))
+        return in_front & ~(near | colinear), g
+
+    @staticmethod
+    def normals(g, keep):
+        g = g[keep]
+        nrm_v = torch.cross(g[:, :, 1] - g[:, :, 0], g[:, :, 2] - g[:, :, 0], dim=1)
+        nrm = torch.norm(nrm_v, 2, dim=1, keepdim=True)
+        return nrm_v / (nrm + (nrm == 0.0).float() * 0.01)
+
+    @staticmethod
+    def tail(loss):
+        loss, _ = torch.sort(loss, dim=0, descending=False)
+        loss = loss[int(loss.shape[0] * 0.25):]
+        return torch.nansum(loss) / loss.shape[0]
+
+    def __call__(self, pred_depth, gt_masks, gt_normals, gt_depth, K):
+        import torch.nn.functional as F
+        pts = self.points(pred_depth, K)
+        n_planes = gt_normals.shape[0]
+        total = 0
+        rest = torch.logical_not(gt_masks.sum(0).bool())
+        for i in range(n_planes):
+            seg = pts[gt_masks[i], :]
+            idx = self.sample(seg.shape[0])
+            keep, g = self.usable(idx, seg)
+            cos = F.cosine_similarity(self.normals(g, keep), gt_normals[i].unsqueeze(0), dim=1).abs()
+            total = total + self.tail(1 - cos)
+        if rest.sum() > 0:
+            gt_pts = self.points(gt_depth, K)
+            idx = self.sample(int(rest.sum()))
+            keep, g_gt = self.usable(idx, gt_pts[rest, :], delta_diff=0.1)
+            if keep.sum() == 0:
+                return total / n_planes
+            g_pred = self.groups(idx, pts[rest, :])
+            g_pred[g_pred[:, 2, :] == 0] = 0.0001
+            cos = F.cosine_similarity(self.normals(g_pred, keep), self.normals(g_gt, keep), dim=1).abs()
+            return (total + self.tail(1 - cos)) / (n_planes + 1)
+        return total / n_planes
+
+
+# ------------------------------------------------------------------------------------------ the joint loss
+class PlaneRecNetLoss(torch.nn.Module):
+    """Drop-in for models/functions/losses.py:PlaneRecNetLoss (same constructor-time cfg fields, same forward signature and
+    result dict {'ins','cat','dpt','pln','lav'}): target assignment on the device (targets.py), dice + lava and focal and
+    RMSE-log terms on libprn_b200 kernels, plane-normal term host-side.  Reference quirks kept: the lava valid mask stays
+    None for the presets' dataset name (losses.py:172), the plane term assumes 480x640 (losses.py:50)."""
+
+    def __init__(self, cfg=None, backend=None):
+        super().__init__()
+        if cfg is None:
+            from .config import cfg as _cfg
+            cfg = _cfg
+        self.num_classes = cfg.num_classes
+        self.num_grids = list(cfg.solov2.num_grids)
+        self.scale_ranges = cfg.solov2.fpn_scale_ranges
+        self.sigma = cfg.solov2.sigma
+        self.focal_alpha, self.focal_gamma = cfg.focal_alpha, cfg.focal_gamma
+        self.w_ins, self.w_cat, self.w_dpt = cfg.dice_weight, cfg.focal_weight, cfg.depth_weight
+        self.w_lav, self.w_pln = cfg.lava_weight, cfg.pln_weight
+        self.use_lava, self.use_plane = cfg.use_lava_loss, cfg.use_plane_loss
+        self.min_depth, self.depth_resolution = cfg.dataset.min_depth, cfg.dataset.depth_resolution
+        self.backend = backend
+        self.vnl = _PlaneNormal((480, 640))
+
+    def forward(self, net, mask_preds, cate_preds, kernel_preds, depth_preds, gt_instances, gt_depths):
+        from .targets import assign_targets
+        import torch.nn.functional as F
+        be = self.backend or CudaBackend()
+        B = len(gt_instances)
+        fh, fw = mask_preds.shape[-2:]
+        targets = [assign_targets(g, (fh, fw), self.num_grids, self.scale_ranges, self.num_classes, self.sigma) for g in gt_instances]
+        losses = {}
+        gw, gsum = be.lava_weights(gt_depths, fh, fw, self.depth_resolution)
+        if not self.use_lava:
+            gsum = torch.zeros_like(gsum)
+        ins, lav = _InsLava.apply(be, targets, gw, gsum, self.w_ins, self.w_lav, mask_preds, *kernel_preds)
+        losses["ins"] = ins
+        # category: rows ordered (level, image, cell) like losses.py:121-133
+        n_levels = len(self.num_grids)
+        labels = torch.cat([torch.cat([targets[b][l][1].flatten() for b in range(B)]) for l in range(n_levels)])
+        logits = torch.cat([c.permute(0, 2, 3, 1).reshape(-1, self.num_classes) for c in cate_preds]).contiguous()
+        # number of distinct positive cells (losses.py:114: sum of the boolean cell map, not of the instance rows)
+        num_ins = sum(int(targets[b][l][2].sum()) for b in range(B) for l in range(n_levels))
+        losses["cat"] = self.w_cat * be.focal_sum(logits, labels, self.focal_alpha, self.focal_gamma, self.num_classes) / (num_ins + 1)
+        losses["dpt"] = be.depth_rmselog(depth_preds, gt_depths, self.min_depth, 1e-9, self.w_dpt)
+        if self.use_plane:
+            up = F.interpolate(depth_preds, scale_factor=2, mode="bilinear", align_corners=False)
+            pln = [self.vnl(up[b], gt_instances[b]["masks"].bool(), gt_instances[b]["plane_paras"][:, :3], gt_depths[b],
+                            gt_instances[b]["k_matrix"]) for b in range(B)]
+            losses["pln"] = torch.stack(pln).mean() * self.w_pln
+        if self.use_lava:
+            losses["lav"] = lav
+        return losses

@@ -32,3 +32,15 @@ class EmuBackend:
         up = F.interpolate(probe, size=gt.shape[-2:], mode="bilinear")
         (gw,) = torch.autograd.grad((up * g).sum(), probe)
         return gw.reshape(gt.shape[0], -1), g.reshape(gt.shape[0], -1).sum(1)
+
+    def focal_sum(self, logits, labels, alpha, gamma, nc):
+        from oracle import prn_loss_oracle as LO
+        oh = torch.zeros(logits.shape[0], nc)
+        pos = torch.nonzero(labels != nc).squeeze(1)
+        oh[pos, labels[pos]] = 1
+        return LO.sigmoid_focal_sum(logits[:, :nc], oh, alpha, gamma)
+
+    def depth_rmselog(self, depth, gt, min_depth, clamp_val, weight):
+        from oracle import prn_loss_oracle as LO
+        up = F.interpolate(depth, scale_factor=2, mode="bilinear", align_corners=False)
+        return weight * LO.rmse_log_mean(up, gt, gt > min_depth, clamp_val)

@@ -77,3 +77,33 @@ def test_ins_lava_orchestration_equals_oracle_on_cpu(name):
             assert t.grad is None or float(t.grad.abs().max()) == 0.0
         else:
             assert float((t.grad - rg).abs().max()) <= 1e-4 * float(rg.abs().max())
+
+
+@pytest.mark.parametrize("name", list(LC.CASES))
+def test_assembled_loss_module_equals_reference_golden_on_cpu(name):
+    """planerecnet_b200.losses.PlaneRecNetLoss (target assignment + five terms, reference signature) with the torch
+    emulation of the device steps == the UNMODIFIED reference's loss values (tests/golden/loss_golden.pt) and gradient norms."""
+    import math
+    import os
+    import numpy as np
+    from loss_emulation import EmuBackend
+    from planerecnet_b200 import losses as PL
+    from planerecnet_b200.config import cfg, set_cfg
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.pt"))[name]
+    set_cfg("PlaneRecNet_101_config")
+    crit = PL.PlaneRecNetLoss(cfg, backend=EmuBackend())
+    mask, cate, kern, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+    leaves = [mask] + cate + kern + [depth]
+    for t in leaves:
+        t.requires_grad_(True)
+    np.random.seed(0)
+    out = crit(None, mask, cate, kern, depth, gts, gt_depth)
+    assert list(out) == ["ins", "cat", "dpt", "pln", "lav"]
+    for k, v in gold["losses"].items():
+        got = float(out[k].detach().sum())
+        assert (math.isnan(got) if math.isnan(v) else abs(got - v) <= 2e-5 * max(1.0, abs(v))), (k, got, v)
+    if not any(math.isnan(v) for v in gold["losses"].values()):
+        sum(v.sum() for v in out.values()).backward()
+        got = [0.0 if t.grad is None else float(t.grad.double().norm()) for t in leaves]
+        for a, b in zip(got, gold["grad_norms"]):
+            assert abs(a - b) <= 2e-4 * max(b, 1e-6), (got, gold["grad_norms"])
