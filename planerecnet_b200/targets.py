@@ -7,10 +7,12 @@ rounds 0.5 up; checked against cv2 in tests/test_targets_cpu.py) — so the whol
 one host round trip per FPN level for the handful of integer cell coordinates.  Plain tensor indexing only (no arithmetic
 hot path); device-agnostic, which is what lets the CPU suite compare it with the oracle bit for bit.
 
-Open point (round 2): run on CUDA, one of the three synthetic cases (integer boxes, centres on exact multiples of the grid
-pitch) resolves a cell boundary differently from the CPU run although every step is meant to be exact — the reference's
-`(c / extent) // (1 / S)` in float32 sits on such boundaries.  tests/test_loss_kernels_gpu.py therefore feeds the losses
-with the CPU assignment and only reports whether the device-side one agrees."""
+Device independence: the reference's `(c / extent) // (1 / S)` sits exactly on grid-cell boundaries for round inputs, and
+torch's CUDA kernels divide by Python scalars through a reciprocal (last-bit differences), so an earlier version of this
+module resolved one synthetic case differently on CUDA than on the CPU.  The moments are now accumulated exactly (float64)
+and every division uses device-tensor divisors (IEEE quotients on both devices); the CUDA side of this could not be
+re-run in round 1 (GPU budget spent), so tests/test_loss_kernels_gpu.py still feeds the losses with the CPU assignment and
+only reports whether the device-side one agrees."""
 import torch
 
 
@@ -57,7 +59,12 @@ def assign_targets(gt, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.
         nonempty = mk.sum(-1).sum(-1) > 0
 
         def cell(v, extent):                       # int((v / extent) // (1 / S)) of the reference, for all instances at once
-            return torch.floor_divide(v / extent, 1.0 / S).to(torch.int64)
+            # divisors as device tensors of v's dtype: with Python-scalar divisors torch's CUDA kernels take a
+            # multiply-by-reciprocal shortcut that may differ from the IEEE quotient in the last bit — enough to move a
+            # centre that sits exactly on a grid-cell boundary (0.5 // 0.025) to the other cell than the CPU run
+            e = torch.tensor(float(extent), dtype=v.dtype, device=dev)
+            pitch = torch.tensor(1.0 / S, dtype=v.dtype, device=dev)
+            return torch.floor_divide(v / e, pitch).to(torch.int64)
 
         cx, cy = cell(cw, up_w), cell(ch, up_h)
         top = torch.maximum(cell(ch - half_h, up_h).clamp(min=0), cy - 1)
