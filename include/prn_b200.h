@@ -88,6 +88,9 @@ typedef struct PrnConv {
 
 const char* prn_last_error(void);
 int prn_abi_version(void);
+/* sha256 of the sources this library was compiled from (planerecnet_b200/csrc/build.py:fingerprint); the Python binding
+ * refuses a library whose fingerprint differs from the sources next to it (a stale .so from another checkout). */
+const char* prn_build_fingerprint(void);
 /* SM count of the current device (grid sizing is done inside the library; exposed for bench/roofline). */
 int prn_device_sm_count(void);
 

@@ -70,20 +70,28 @@ def lib():
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU or PyTorch fallback for the PlaneRecNet hot path)")
     l = C.CDLL(LIB_PATH)
+    if not hasattr(l, "prn_build_fingerprint"):
+        raise PrnError(f"{LIB_PATH} predates the source tree (no build fingerprint): rebuild it with __graft_entry__.build()")
+    l.prn_build_fingerprint.restype = C.c_char_p
+    from .csrc import build as _B
+    built, want = l.prn_build_fingerprint().decode(), _B.fingerprint()
+    if built != want:
+        raise PrnError(f"{LIB_PATH} was built from other sources (fingerprint {built[:12]} != {want[:12]}): "
+                       "rebuild it with `python -c 'import __graft_entry__ as g; g.build()'`")
     l.prn_last_error.restype = C.c_char_p
     l.prn_abi_version.restype = C.c_int
     l.prn_device_sm_count.restype = C.c_int
     for name in EXPORTS:
         if not hasattr(l, name):
             raise PrnError(f"{LIB_PATH} does not export {name}")
-        getattr(l, name).restype = C.c_int if name != "prn_last_error" else C.c_char_p
+        getattr(l, name).restype = C.c_char_p if name in ("prn_last_error", "prn_build_fingerprint") else C.c_int
     _lib = l
     return l
 
 
 # every symbol include/prn_b200.h declares (tests check the header against this list and the .so)
 EXPORTS = [
-    "prn_last_error", "prn_abi_version", "prn_device_sm_count",
+    "prn_last_error", "prn_abi_version", "prn_build_fingerprint", "prn_device_sm_count",
     "prn_conv2d_fwd", "prn_conv2d_fwd_profile", "prn_conv2d_plan", "prn_conv2d_plan_ex",
     "prn_stem_im2col", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",

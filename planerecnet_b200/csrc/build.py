@@ -8,7 +8,6 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libprn_b200.so")
-STAMP = os.path.join(HERE, ".build_stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -34,19 +33,35 @@ def _fingerprint():
     return h.hexdigest()
 
 
+def fingerprint():
+    """sha256 over the kernel sources, this script and the public header: compiled into the library
+    (prn_build_fingerprint()) so that a stale .so left over from another checkout is detected at load time."""
+    return _fingerprint()
+
+
+def embedded_fingerprint(path=LIB):
+    """The fingerprint the shared library was built from ('' if none).  Read from the file's bytes (marker "PRN_FP:"), not
+    through dlopen: a handle opened here would be served again, stale, after a rebuild in the same process."""
+    try:
+        with open(path, "rb") as fh:
+            blob = fh.read()
+    except OSError:
+        return ""
+    i = blob.find(b"PRN_FP:")
+    return blob[i + 7:i + 7 + 64].decode("ascii", "replace") if i >= 0 else ""
+
+
 def build(force=False, verbose=False):
     fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        with open(STAMP) as fh:
-            if fh.read().strip() == fp:
-                return LIB
+    if not force and os.path.exists(LIB) and embedded_fingerprint() == fp:
+        return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     for src in sources():
         obj = src[:-3] + ".o"
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f'-DPRN_BUILD_FP="{fp}"', "-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -56,8 +71,6 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     cmd = [nvcc, "-shared", "-arch=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    with open(STAMP, "w") as fh:
-        fh.write(fp)
     return LIB
 
 

@@ -67,5 +67,10 @@ int sm_count() {
 extern "C" {
 const char* prn_last_error(void) { return prn::g_err; }
 int prn_abi_version(void) { return 1; }
+#ifndef PRN_BUILD_FP
+#define PRN_BUILD_FP "unknown"
+#endif
+static const char g_build_fp[] = "PRN_FP:" PRN_BUILD_FP;     // the marker lets build.py read it from the file's bytes
+const char* prn_build_fingerprint(void) { return g_build_fp + 7; }
 int prn_device_sm_count(void) { return prn::sm_count(); }
 }

@@ -876,6 +876,12 @@ class GraphedStep:
         self.eng, self.net = eng, net
         self.sx = torch.empty_like(x)
         self.sx.copy_(x)
+        self.bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats]
+        # the eager warm-up below is not a training step: it must leave the BatchNorm buffers (running statistics through
+        # raw pointers, num_batches_tracked) exactly as it found them, or every newly captured graph would apply its
+        # first batch twice
+        bn_bufs = [b for m in self.bns for b in (m.running_mean, m.running_var, m.num_batches_tracked)]
+        bn_saved = [b.detach().clone() for b in bn_bufs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                 # eager warm-up: function attributes, allocator, first packs
@@ -883,9 +889,11 @@ class GraphedStep:
             eng.seed_output_grads(torch.zeros_like(outs[0]), [torch.zeros_like(c) for c in outs[1]],
                                   [torch.zeros_like(k) for k in outs[2]], torch.zeros_like(outs[3]))
             eng.backward()
+            with torch.no_grad():
+                for b, sv in zip(bn_bufs, bn_saved):
+                    b.copy_(sv)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.bns = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.track_running_stats]
         self.g_fwd = torch.cuda.CUDAGraph()
         n0 = eng.launches
         with _no_gc(), torch.cuda.graph(self.g_fwd):

@@ -92,13 +92,13 @@ def test_ins_lava_losses_match_oracle(cuda_lib, name):
     ref = LO.loss_forward(mask, cate, kern, depth, gts, gt_depth)
     (ref["ins"] + ref["lav"].sum()).backward()
     dm, dk = mask.detach().cuda().requires_grad_(True), [k.detach().cuda().requires_grad_(True) for k in kern]
-    # targets from the same (CPU) assignment the oracle uses; the device-side assignment is compared with it below
+    # the device-side assignment must equal the (CPU) assignment the oracle uses, bit for bit; the losses consume it
     targets = [T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"]) for g in gts]
     gts_d = [{k: v.cuda() for k, v in g.items()} for g in gts]
     targets_dev = [T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"]) for g in gts_d]
     same = all(td[3] == tc[3] and torch.equal(td[0].cpu(), tc[0]) for a, b in zip(targets_dev, targets) for td, tc in zip(a, b))
-    print(f"{name}: device-side target assignment identical to the CPU one: {same}")
-    l_ins, l_lav = PL.ins_lava_losses(dm, dk, targets, gt_depth.cuda())
+    assert same, f"{name}: device-side target assignment differs from the CPU one"
+    l_ins, l_lav = PL.ins_lava_losses(dm, dk, targets_dev, gt_depth.cuda())
     (l_ins + l_lav).backward()
     assert abs(float(l_ins) - float(ref["ins"])) <= 1e-2 * abs(float(ref["ins"]))
     assert abs(float(l_lav) - float(ref["lav"].sum())) <= 1e-2 * abs(float(ref["lav"].sum()))
@@ -111,3 +111,58 @@ def test_ins_lava_losses_match_oracle(cuda_lib, name):
         print(f"{name}: grad {tuple(t.shape)} cos {cos:.5f} rel-L2 {rel_l2(got.grad.cpu(), t.grad):.3e}")
         # the dice gradient is cancellation-dominated: 16-bit rounding of the operands is amplified
         assert cos >= 0.995 and rel_l2(got.grad.cpu(), t.grad) <= 0.1, (cos, rel_l2(got.grad.cpu(), t.grad))
+
+
+@pytest.mark.parametrize("name", ["loss_seed0", "loss_seed1_b1", "loss_seed2_many_tiny"])
+def test_device_target_assignment_is_bit_exact(cuda_lib, name):
+    """Integer / index work must be bit-exact: the SOLO target assignment computed on CUDA tensors equals the CPU one and the
+    unmodified reference's own assignment stored in tests/golden/loss_golden.pt (grid cells, positive cells, mask sums)."""
+    import os
+    import loss_cases as LC
+    from planerecnet_b200 import targets as T
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.pt"))[name]
+    _, _, _, _, gts, _ = LC.synth(**LC.CASES[name])
+    for b, g in enumerate(gts):
+        cpu = T.assign_targets(g, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"])
+        dev = T.assign_targets({k: v.cuda() for k, v in g.items()}, (120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"])
+        for lvl, (tc, td) in enumerate(zip(cpu, dev)):
+            assert td[3] == tc[3], (name, b, lvl, "grid order differs between CUDA and CPU")
+            assert torch.equal(td[0].cpu(), tc[0]) and torch.equal(td[1].cpu(), tc[1]) and torch.equal(td[2].cpu(), tc[2])
+            assert [int(o) for o in td[3]] == gold["grid_orders"][b][lvl], (name, b, lvl, "differs from the reference's assignment")
+            assert (td[1].cpu() != 2).nonzero().tolist() == gold["cate_pos"][b][lvl]
+        assert [int(t[0].sum()) for t in dev] == gold["ins_label_sums"][b]
+
+
+@pytest.mark.parametrize("name", ["loss_seed0", "loss_seed1_b1", "loss_seed2_many_tiny"])
+def test_assembled_loss_module_matches_reference_golden_on_gpu(cuda_lib, name):
+    """planerecnet_b200.losses.PlaneRecNetLoss end to end on the GPU (device-side targets, kernel-backed dice / lava / focal /
+    depth terms, host-side plane term) against the UNMODIFIED reference's values in tests/golden/loss_golden.pt:
+    loss terms within 1e-2 relative (f16 operands in the mask contractions; fp32 elsewhere: 1e-4), gradient norms within 2e-2."""
+    import os
+    import numpy as np
+    import loss_cases as LC
+    from planerecnet_b200.config import cfg, set_cfg
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.pt"))[name]
+    set_cfg("PlaneRecNet_101_config")
+    crit = PL.PlaneRecNetLoss(cfg)
+    mask, cate, kern, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+    leaves = [t.cuda().requires_grad_(True) for t in [mask] + cate + kern + [depth]]
+    gts_d = [{k: v.cuda() for k, v in g.items()} for g in gts]
+    np.random.seed(0)
+    out = crit(None, leaves[0], leaves[1:5], leaves[5:9], leaves[9], gts_d, gt_depth.cuda())
+    assert set(out.keys()) == {"ins", "cat", "dpt", "pln", "lav"}
+    tol = {"ins": 1e-2, "lav": 1e-2, "cat": 1e-4, "dpt": 1e-4, "pln": 2e-3}
+    for k, ref in gold["losses"].items():
+        got = float(out[k].sum())
+        if ref != ref:                      # the reference's NaN for a degenerate plane
+            assert got != got, (k, got)
+            continue
+        assert abs(got - ref) <= tol[k] * abs(ref) + 1e-6, (name, k, got, ref)
+    total = sum(v.sum() for v in out.values())
+    total.backward()                        # like train.py:349-350 (the reference backpropagates a non-finite total as well)
+    for t, ref in zip(leaves, gold["grad_norms"]):
+        got = 0.0 if t.grad is None else float(t.grad.double().norm())
+        if ref != ref:
+            assert got != got, (name, tuple(t.shape), got)
+        else:
+            assert abs(got - ref) <= 2e-2 * abs(ref) + 1e-7, (name, tuple(t.shape), got, ref)

@@ -101,12 +101,25 @@ def test_graphed_step_matches_eager_and_follows_optimizer(cuda_lib, bn_mode):
     state = {k: v.clone() for k, v in net.state_dict().items()}
     net.use_train_graph = False
     g_eager0 = step()
+    bn1 = net.backbone.bn1
+    eager_bufs = (bn1.running_mean.clone(), bn1.running_var.clone(), int(bn1.num_batches_tracked))
     noise = rel_l2(step(), g_eager0)          # run-to-run noise floor of the eager path
     opt.step()
     g_eager1 = step()
     net.load_state_dict(state)
     net.use_train_graph = True
     g_graph0 = step()          # captures
+    # the capture's eager warm-up must not count as a step: BatchNorm buffers after the first graphed step == after the
+    # first eager step (running statistics once, num_batches_tracked + 1)
+    nbt0 = int(state["backbone.bn1.num_batches_tracked"])
+    if bn_mode == "train":
+        assert eager_bufs[2] == nbt0 + 1 and int(bn1.num_batches_tracked) == nbt0 + 1, (eager_bufs[2], int(bn1.num_batches_tracked))
+        for m_ in net.modules():
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                assert int(m_.num_batches_tracked) == nbt0 + 1
+        assert rel_l2(bn1.running_mean, eager_bufs[0]) < 2e-3 and rel_l2(bn1.running_var, eager_bufs[1]) < 2e-3
+    else:
+        assert int(bn1.num_batches_tracked) == nbt0 and torch.equal(bn1.running_mean, state["backbone.bn1.running_mean"])
     opt.step()
     g_graph1 = step()          # replays with the updated parameters
     tol = max(5 * noise, 1e-3)
