@@ -40,7 +40,9 @@ typedef enum PrnAct {
   PRN_ACT_SIGMOID_AVG4 = 5   /* sigmoid, then mean over 4 consecutive rows; output has M/4 rows */
 } PrnAct;
 
-typedef enum PrnPadMode { PRN_PAD_ZERO = 0, PRN_PAD_REFLECT = 1 } PrnPadMode;
+/* PRN_PAD_CLAMP (replicate the border pixel) is what ReflectionPad2d(1) of a nearest-x2-upsampled map is at the low
+ * resolution: the sub-pixel form of the decoder's deconv blocks (planerecnet.py:540-567) uses it together with `shuffle_n`. */
+typedef enum PrnPadMode { PRN_PAD_ZERO = 0, PRN_PAD_REFLECT = 1, PRN_PAD_CLAMP = 2 } PrnPadMode;
 
 /* One convolution-like contraction  out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] ),
  * m = (image, ho, wo) flattened, k = (ky, kx, c) with c running over src0's then src1's channels.
@@ -84,6 +86,11 @@ typedef struct PrnConv {
   float* stats;
   int32_t stats_cg;
   int32_t dtype;           /* PrnDtype of src/weight/residual/out16 */
+  /* Pixel shuffle of the output (0 = off): the n_pad = 4*shuffle_n columns are four sub-pixel phases (a,b) of shuffle_n
+   * channels each; column (2a+b)*shuffle_n + c of output pixel (y,x) is stored at pixel (2y+a, 2x+b), channel c of a
+   * [batch, 2*h_out, 2*w_out, ld_out16] tensor.  With PRN_PAD_CLAMP and the phase-combined 3x3 weights this is
+   * Upsample(x2, nearest) -> ReflectionPad2d(1) -> Conv2d(3x3) (planerecnet.py:540-567) evaluated at the low resolution. */
+  int32_t shuffle_n;
 } PrnConv;
 
 const char* prn_last_error(void);

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libprn_b200.so")
 
 PRN_F16, PRN_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SOFTPLUS, ACT_DCN_OFFMASK, ACT_SIGMOID_AVG4 = range(6)
-PAD_ZERO, PAD_REFLECT = 0, 1
+PAD_ZERO, PAD_REFLECT, PAD_CLAMP = 0, 1, 2
 
 
 class PrnError(RuntimeError):
@@ -38,6 +38,7 @@ class PrnConv(C.Structure):
         ("out_img_rows", C.c_int32),
         ("stats", C.c_void_p), ("stats_cg", C.c_int32),
         ("dtype", C.c_int32),
+        ("shuffle_n", C.c_int32),
     ]
 
 

@@ -26,6 +26,11 @@ int set_error(int code, const char* fmt, ...);
 int encode_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          int dtype, uint64_t pitch_elems = 0);
 
+// General tiled tensor map over a 16-bit tensor: dims / box innermost first, strides_bytes[i] = byte stride of dimension
+// i + 1 (rank - 1 entries), swizzle_bytes in {0, 32, 64, 128} (box[0] * 2 bytes must not exceed it), OOB elements read as 0.
+int encode_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes, int dtype);
+
 int sm_count();
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -127,6 +127,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the shared-memory source of all but the N most recent bulk groups has been read
 template <int N>
@@ -161,6 +167,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO = 1024 B
   d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+// Same with an explicit stride between 8-row groups and the 3-bit base-offset field (bits 49-51): rows of an operand
+// that live in a larger address-swizzled array ("pixel rows" of a halo tile) and start at any 128-byte row of it.
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_off & 7u) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.

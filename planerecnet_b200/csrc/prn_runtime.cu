@@ -51,6 +51,33 @@ int encode_tmap_2d_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint
   return PRN_OK;
 }
 
+int encode_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, int swizzle_bytes, int dtype) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return set_error(PRN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (rank < 2 || rank > 5) return set_error(PRN_ERR_INVALID, "tensor map rank must be 2..5");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(PRN_ERR_INVALID, "tensor map base must be 16-byte aligned");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      if (strides_bytes[i - 1] % 16 != 0) return set_error(PRN_ERR_INVALID, "tensor map strides must be multiples of 16 bytes");
+      gstr[i - 1] = strides_bytes[i - 1];
+    }
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dtype == PRN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                   const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(PRN_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+  return PRN_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n) return n;

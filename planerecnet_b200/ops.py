@@ -42,6 +42,27 @@ def pack_conv_weight(w, c_splits=None, n_pad=None, dtype=L.PRN_BF16, scale=None)
     return w.to(torch_dtype(dtype)).contiguous()
 
 
+def subpixel_weights(w):
+    """[Cout, Cin, 3, 3] -> [4*Cout, Cin, 3, 3]: the four sub-pixel phases of Upsample(x2, nearest) -> ReflectionPad2d(1) ->
+    Conv2d(3x3) (planerecnet.py:540-567) as one 3x3 convolution at the LOW resolution with replicate padding.  Output pixel
+    (2y+a, 2x+b) reads upsampled rows 2y+a-1 .. 2y+a+1 = low-resolution rows {y-1, y, y} (a = 0) or {y, y, y+1} (a = 1); the
+    reflected border row of the upsampled map is the clamped low-resolution row.  Phase (a, b) occupies output rows
+    [(2a+b)*Cout, +Cout); taps that fall on the same low-resolution pixel are summed (in fp32, before the 16-bit rounding)."""
+    cout, cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    w = w.detach().float()
+    sets = {0: ([0], [1, 2], []), 1: ([], [0, 1], [2])}      # phase -> source taps of low-resolution tap 0, 1, 2
+    out = torch.zeros(4, cout, cin, 3, 3, dtype=torch.float32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ty in range(3):
+                for tx in range(3):
+                    for ky in sets[a][ty]:
+                        for kx in sets[b][tx]:
+                            out[2 * a + b, :, :, ty, tx] += w[:, :, ky, kx]
+    return out.reshape(4 * cout, cin, 3, 3)
+
+
 def pad_vec(v, n_pad):
     v = v.detach().float()
     if v.numel() < n_pad:
@@ -52,7 +73,7 @@ def pad_vec(v, n_pad):
 def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mode=L.PAD_ZERO, upsample=1,
            src1=None, bias=None, residual=None, act=L.ACT_NONE, act_param=0.0, out16=None, out32=None,
            ld_out16=None, ld_out32=None, out_img_rows=0, stats=None, stats_cg=0, dcn_offmask=None,
-           n_pad=None, w_group_rows=0, dtype=L.PRN_BF16, c0=None, c1=None, ld_res=None, counters=None):
+           n_pad=None, w_group_rows=0, dtype=L.PRN_BF16, c0=None, c1=None, ld_res=None, counters=None, shuffle_n=0):
     """Launch prn_conv2d_fwd.  src*/residual/out16 are 16-bit NHWC tensors (any shape, channels last)."""
     d = L.PrnConv()
     d.src0 = src0.data_ptr()
@@ -83,6 +104,7 @@ def conv2d(src0, weight, *, batch, h_in, w_in, ksize=1, stride=1, pad=0, pad_mod
     d.stats = stats.data_ptr() if stats is not None else None
     d.stats_cg = stats_cg
     d.dtype = dtype
+    d.shuffle_n = shuffle_n
     if counters is not None:
         L.check(L.lib().prn_conv2d_fwd_profile(C.byref(d), L.current_stream(), C.c_void_p(counters.data_ptr())),
                 "prn_conv2d_fwd_profile")

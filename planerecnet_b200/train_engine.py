@@ -911,23 +911,26 @@ class GraphedStep:
         self.bwd_launches = eng.launches - n0
         self.optimizer, self.world = optimizer, world
         self.g_opt = self.g_flat = None
+        self.flat = None
+        self._reduced = False
+        params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
+        src = self.grads
+        if world > 1:
+            # one persistent flat fp32 buffer for the NCCL all-reduce; the optimizer reads the averaged views
+            self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
+            views, off = {}, 0
+            for p in params:
+                views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self.flat_views = views
+            self.g_flat = torch.cuda.CUDAGraph()
+            dst = [views[id(p)] for p in params]
+            srcs = [self.grads[id(p)].reshape(p.shape) for p in params]
+            torch.cuda.synchronize()
+            with _no_gc(), torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
+                torch._foreach_copy_(dst, srcs)
+            src = views
         if optimizer is not None:
-            params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
-            src = self.grads
-            if world > 1:
-                # one flat fp32 buffer for the NCCL all-reduce; the optimizer reads the averaged views
-                self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
-                views, off = {}, 0
-                for p in params:
-                    views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
-                    off += p.numel()
-                self.g_flat = torch.cuda.CUDAGraph()
-                dst = [views[id(p)] for p in params]
-                srcs = [self.grads[id(p)].reshape(p.shape) for p in params]
-                torch.cuda.synchronize()
-                with _no_gc(), torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
-                    torch._foreach_copy_(dst, srcs)
-                src = views
             optimizer.prepare(src)
             torch.cuda.synchronize()
             self.g_opt = torch.cuda.CUDAGraph()
@@ -936,13 +939,25 @@ class GraphedStep:
             # the capture executed nothing, but step() bumped versions / the warm-up above ran one real forward+backward:
             # parameters are untouched; optimizer state starts at step 0
 
+    def allreduce_grads(self):
+        """Average the gradients of the last backward over the ranks: ONE NCCL all-reduce (ReduceOp.AVG) over the persistent
+        flat fp32 buffer (gathered by one captured multi-tensor copy).  Returns {id(param): averaged view}."""
+        if self.g_flat is None:
+            return self.grads
+        import torch.distributed as dist
+        self.g_flat.replay()
+        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        self._reduced = True
+        return self.flat_views
+
+    def allreduce_desc(self):
+        return f"nccl, 1 all-reduce (avg) of the flat fp32 gradient buffer ({self.flat.numel() * 4 / 2 ** 20:.0f} MiB) per step" if self.flat is not None else None
+
     def optimizer_step(self):
         """(all-reduce the gradients of the last backward over the ranks and) apply the optimizer, from graphs."""
-        if self.g_flat is not None:
-            import torch.distributed as dist
-            self.g_flat.replay()
-            dist.all_reduce(self.flat)
-            self.flat.div_(self.world)
+        if self.g_flat is not None and not self._reduced:
+            self.allreduce_grads()
+        self._reduced = False
         self.g_opt.replay()
         for p in self.net.parameters():
             torch.autograd.graph.increment_version(p)
@@ -971,6 +986,7 @@ class GraphedStep:
         put(self.cots[3], d_depth)
         self.g_bwd.replay()
         self.eng.launches += self.bwd_launches
+        self._reduced = False
         return self.grads
 
 

@@ -42,6 +42,21 @@ CASES = {
     "dcn_s2_c256": dict(B=2, H=30, W=40, C=256, N=256, k=3, pad=1, stride=2, bias=True, dcn=True),
     "offmask_conv": dict(B=2, H=15, W=20, C=128, N=27, k=3, pad=1, bias=True, act="offmask", out32=True),
     "f16_3x3_c128": dict(B=2, H=15, W=20, C=128, N=128, k=3, pad=1, bias=True, act="relu", dtype="f16"),
+    # ---- TMA halo-tile kernel (3x3 / stride 1 / pad 1): patch geometry, padding modes, concat, sub-pixel deconv
+    "3x3_halo_odd_sizes": dict(B=3, H=21, W=13, C=64, N=64, k=3, pad=1, bias=True),
+    "3x3_halo_120x160_c64_n64": dict(B=1, H=120, W=160, C=64, N=64, k=3, pad=1, bias=True, act="relu", dtype="f16"),
+    "3x3_halo_concat_c64_c128": dict(B=2, H=30, W=40, C=64, C1=128, N=128, k=3, pad=1, bias=True, act="relu"),
+    "3x3_halo_n512": dict(B=2, H=15, W=20, C=128, N=512, k=3, pad=1, bias=True),
+    "3x3_reflect_big": dict(B=2, H=33, W=41, C=128, N=128, k=3, pad=1, reflect=True, bias=True),
+    "3x3_reflect_concat": dict(B=2, H=16, W=24, C=128, C1=128, N=128, k=3, pad=1, reflect=True, bias=True, act="relu"),
+    "3x3_clamp_c128": dict(B=2, H=15, W=20, C=128, N=128, k=3, pad=1, clamp=True, bias=True),
+    "3x3_subpixel_up2_reflect_n64": dict(B=2, H=15, W=20, C=128, C1=128, N=64, k=3, pad=1, reflect=True, up=2, bias=True, act="relu",
+                                         subpixel=True),
+    "3x3_subpixel_up2_reflect_n128_f16": dict(B=2, H=30, W=24, C=256, N=128, k=3, pad=1, reflect=True, up=2, bias=True, act="relu",
+                                              subpixel=True, dtype="f16"),
+    "3x3_halo_kernelpred_rows": dict(B=2, H=24, W=24, C=256, N=128, k=3, pad=1, bias=True, out32=True),
+    "1x1_residual_relu_n1024": dict(B=2, H=30, W=40, C=256, N=1024, k=1, bias=True, residual=True, act="relu"),
+    "1x1_c64_n256_big": dict(B=2, H=60, W=80, C=64, N=256, k=1, bias=True, act="relu", dtype="f16"),
 }
 
 ACTS = {None: L.ACT_NONE, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID, "softplus": L.ACT_SOFTPLUS,
@@ -100,6 +115,9 @@ def run_case(name, seed=0, verbose=False):
         if c.get("reflect"):
             xi = F.pad(xi, (pad, pad, pad, pad), mode="reflect")
             ref = F.conv2d(xi, wf, bias, stride, 0)
+        elif c.get("clamp"):
+            xi = F.pad(xi, (pad, pad, pad, pad), mode="replicate")
+            ref = F.conv2d(xi, wf, bias, stride, 0)
         else:
             ref = F.conv2d(xi, wf, bias, stride, pad)
     ref = ref.permute(0, 2, 3, 1).reshape(M, N)          # [M, N]
@@ -117,8 +135,14 @@ def run_case(name, seed=0, verbose=False):
         ref = torch.sigmoid(ref).reshape(M // 4, 4, N).mean(1)
 
     # ---------------- device
+    subpixel = c.get("subpixel", False)
     if grouped:
         wp = w_all.reshape(B * N, ctot).contiguous().to(dev)
+    elif subpixel:
+        # Upsample(x2) -> ReflectionPad2d(1) -> conv3x3 evaluated at the low resolution: phase-combined weights, replicate
+        # padding, pixel-shuffled store (the reference above is the plain upsample + reflect + conv)
+        splits = [(Cc, Cc)] + ([(C1, C1)] if C1 else [])
+        wp = ops.pack_conv_weight(ops.subpixel_weights(w_all.float()), splits, 4 * N, dt).to(dev)
     else:
         splits = [(Cc, Cc)] + ([(C1, C1)] if C1 else [])
         wp = ops.pack_conv_weight(w_all, splits, n_pad, dt).to(dev)
@@ -129,8 +153,14 @@ def run_case(name, seed=0, verbose=False):
     if "stats_cg" in c:
         nstat = (B * (n_pad // c["stats_cg"])) if c["stats_cg"] else n_pad
         stats = torch.zeros(nstat, 2, device=dev)
-    ops.conv2d(x0.to(dev), wp, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad,
-               pad_mode=L.PAD_REFLECT if c.get("reflect") else L.PAD_ZERO, upsample=up,
+    if subpixel:
+        assert N % 32 == 0 and up == 2 and c.get("reflect")
+        ops.conv2d(x0.to(dev), wp, batch=B, h_in=H, w_in=W, ksize=3, stride=1, pad=1, pad_mode=L.PAD_CLAMP, upsample=1,
+                   src1=x1.to(dev) if C1 else None, bias=bias.repeat(4).to(dev) if bias is not None else None, act=ACTS[act],
+                   out16=out16, ld_out16=n_pad, n_pad=4 * N, dtype=dt, shuffle_n=N)
+    else:
+      ops.conv2d(x0.to(dev), wp, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad,
+               pad_mode=L.PAD_REFLECT if c.get("reflect") else (L.PAD_CLAMP if c.get("clamp") else L.PAD_ZERO), upsample=up,
                src1=x1.to(dev) if C1 else None, bias=ops.pad_vec(bias, n_pad).to(dev) if bias is not None else None,
                residual=res.to(dev) if res is not None else None, act=ACTS[act], act_param=5.0,
                out16=out16, out32=out32, stats=stats, stats_cg=c.get("stats_cg", 0),

@@ -236,3 +236,20 @@ def test_fused_adam_tables_on_cpu():
     opt.prepare(grads)
     assert opt._tabs[2] is lr_tensor and torch.allclose(lr_tensor, torch.tensor([5e-4, 2e-5, 2e-5]))
     assert set(opt.state[id(a)]) == {"exp_avg", "exp_avg_sq"}
+
+
+def test_subpixel_weights_reproduce_upsample_reflect_conv():
+    """ops.subpixel_weights: Upsample(x2, nearest) -> ReflectionPad2d(1) -> Conv2d(3x3) (planerecnet.py:540-567) equals a 3x3
+    convolution with replicate padding at the low resolution followed by a pixel shuffle of the four phase blocks."""
+    import torch
+    import torch.nn.functional as F
+    from planerecnet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 7, 9, generator=g, dtype=torch.float64)
+    w = torch.randn(6, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.pad(F.interpolate(x, scale_factor=2, mode="nearest"), (1, 1, 1, 1), mode="reflect"), w)
+    wc = ops.subpixel_weights(w.float()).double()
+    # subpixel_weights sums in fp32: compare against the same sums in fp64 to 1e-6
+    low = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="replicate"), wc).reshape(2, 2, 2, 6, 7, 9)       # [B, a, b, C, H, W]
+    got = low.permute(0, 3, 4, 1, 5, 2).reshape(2, 6, 14, 18)
+    assert float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())

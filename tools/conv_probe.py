@@ -31,6 +31,13 @@ SHAPES = {
     "ppa_dyn": (8, 1200, 4, 128, 3728, 1, 1, {"grouped": True, "act": L.ACT_SIGMOID_AVG4}),
     "ppa_1x1_3776_256": (8, 30, 40, 3776, 256, 1, 1, {}),
     "mask2_3x3_256_128": (8, 30, 40, 256, 128, 3, 1, {}),
+    "deconv4_subpixel_256_4x64": (8, 120, 160, 256, 256, 3, 1, {"clamp": True, "shuffle": 64}),
+    "deconv3_subpixel_256_4x128": (8, 60, 80, 256, 512, 3, 1, {"clamp": True, "shuffle": 128}),
+    "conv4_reflect_256_128": (8, 120, 160, 256, 128, 3, 1, {"reflect": True}),
+    "fpn1_3x3_256": (8, 60, 80, 256, 256, 3, 1, {}),
+    "inst_3x3_256_s16": (8, 16, 16, 256, 256, 3, 1, {}),
+    "l1_1x1_512_128": (8, 60, 80, 512, 128, 1, 1, {}),
+    "l3_1x1_512_2048": (8, 15, 20, 512, 2048, 1, 1, {}),
     "dcn_l2_256": (8, 30, 40, 256, 256, 3, 1, {"dcn": True}),
     "dcn_l1_128": (8, 60, 80, 128, 128, 3, 1, {"dcn": True}),
     "dcn_l3_512": (8, 15, 20, 512, 512, 3, 1, {"dcn": True}),
@@ -56,6 +63,9 @@ def probe(name, dt=L.PRN_F16, reps=20):
     act = ex.get("act", L.ACT_RELU)
     m_out = M // 4 if act == L.ACT_SIGMOID_AVG4 else M
     ld = ops.round_up(n_pad, 64) if grouped else n_pad
+    shuffle = ex.get("shuffle", 0)
+    if shuffle:
+        m_out, ld = 4 * M, shuffle
     out16 = None if ex.get("out32") else torch.empty(m_out, ld, device="cuda", dtype=tdt)
     out32 = torch.empty(m_out, n_pad, device="cuda") if ex.get("out32") else None
     bias = torch.zeros(n_pad, device="cuda")
@@ -68,7 +78,8 @@ def probe(name, dt=L.PRN_F16, reps=20):
 
     def run(counters=None):
         ops.conv2d(x, w, batch=B, h_in=H, w_in=W, ksize=k, stride=stride, pad=pad,
-                   pad_mode=L.PAD_REFLECT if ex.get("reflect") else L.PAD_ZERO, upsample=up, bias=bias, act=act,
+                   pad_mode=L.PAD_REFLECT if ex.get("reflect") else (L.PAD_CLAMP if ex.get("clamp") else L.PAD_ZERO),
+                   upsample=up, bias=bias, act=act, shuffle_n=shuffle,
                    out16=out16, out32=out32, ld_out16=ld if out16 is not None else None, dcn_offmask=om,
                    n_pad=N if grouped else n_pad, w_group_rows=N if grouped else 0, dtype=dt, counters=counters,
                    out_img_rows=(Ho * Wo // 4 if act == L.ACT_SIGMOID_AVG4 else 0))
@@ -93,7 +104,7 @@ def probe(name, dt=L.PRN_F16, reps=20):
     kb = max(1, c[3])
     print(f"{name:20s} M={M:7d} N={N:5d} K={k * k * Cc:5d} {us:8.1f} us {tfl:7.1f} TFLOP/s | "
           f"prod tot={c[0]:9d} wEmpty={c[1]:9d} wCp={c[2]:9d} kb={c[3]:5d} ({c[0] // kb} cyc/kb) | "
-          f"mma tot={c[4]:9d} wFull={c[5]:9d} wTmemE={c[6]:8d} | epi tot={c[7]:9d} wTfull={c[8]:9d}", flush=True)
+          f"mma tot={c[4]:9d} wFull={c[5]:9d} wTmemE={c[6]:8d} wB={c[9]:8d} | epi tot={c[7]:9d} wTfull={c[8]:9d}", flush=True)
 
 
 def C_int():
