@@ -118,6 +118,12 @@ int prn_conv2d_plan_ex(const PrnConv* desc, int32_t* out8);
  * 7x7/s2/p3 conv (models/backbone.py:101,200), zero padded from 147 to 192, so the stem runs as a
  * K=192 contraction through prn_conv2d_fwd. */
 int prn_stem_im2col(const float* x_nchw, void* out16, int32_t batch, int32_t h, int32_t w, int32_t dtype, void* stream);
+/* The same rows straight from the camera image: BGR NHWC [B, h_img, w_img, 3], uint8 (is_u8 != 0) or fp32, values 0..255 —
+ * the input of FastBaseTransform (data/augmentations.py:496-530).  (x - mean) / std per BGR channel, BGR -> RGB
+ * (augmentations.py:516-527) and pad_even_divided (models/functions/funcs.py:204-210: raw zeros up to h_pad x w_pad) are folded
+ * into the load.  mean_bgr3 / std_bgr3: HOST pointers to 3 floats each (data/config.py:33-34). */
+int prn_stem_im2col_image(const void* img_bgr_nhwc, int32_t is_u8, void* out16, int32_t batch, int32_t h_img, int32_t w_img,
+                          int32_t h_pad, int32_t w_pad, const float* mean_bgr3, const float* std_bgr3, int32_t dtype, void* stream);
 /* nn.MaxPool2d(3, 2, 1): models/backbone.py:104,203. */
 int prn_maxpool3x3s2(const void* in16, void* out16, int32_t batch, int32_t h, int32_t w, int32_t c, int32_t dtype, void* stream);
 /* 2x2 mean == F.interpolate(bilinear, x0.5, align_corners=False): models/fpn.py:54, planerecnet.py:115. */

@@ -94,7 +94,7 @@ def lib():
 EXPORTS = [
     "prn_last_error", "prn_abi_version", "prn_build_fingerprint", "prn_device_sm_count",
     "prn_conv2d_fwd", "prn_conv2d_fwd_profile", "prn_conv2d_plan", "prn_conv2d_plan_ex",
-    "prn_stem_im2col", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
+    "prn_stem_im2col", "prn_stem_im2col_image", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
     "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",
     "prn_conv3x3_to1_reflect", "prn_conv3x3_to1_reflect_devbias", "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box", "prn_mask_nms_greedy",

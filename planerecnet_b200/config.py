@@ -8,6 +8,11 @@ import copy
 from .models.backbone import ResNetBackbone
 
 
+# data/config.py:33-34: per-channel mean / std of the input images in BGR order (FastBaseTransform, data/augmentations.py:510-511)
+MEANS = (103.94, 116.78, 123.68)
+STD = (57.38, 57.12, 58.40)
+
+
 class Config(object):
     """Attribute bag with copy()/replace(), mirroring data/config.py:42-81."""
 

@@ -254,7 +254,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
     const bool has_res = d.residual != nullptr;
     const bool has_stats = d.stats != nullptr;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long w_tfull = 0;
+    long long w_tfull = 0, w_ld = 0, w_st = 0;
     const long long t_role0 = prof ? clock64() : 0;
     int bias_n0 = -1;
     const uint32_t stg_tile = stg_base + static_cast<uint32_t>(warp) * 4096u;   // two 2 KB buffers
@@ -324,7 +324,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         }
       }
       while (ci < ntot) {
+        const long long tq0 = prof ? clock64() : 0;
         tmem_ld_wait();
+        if (prof) w_ld += clock64() - tq0;
         tmem_ld_publish16(vb);
         tmem_ld_publish16(vb + 16);
         float x[32];
@@ -351,8 +353,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         uint32_t srow = 0u;
         if (p.tma_store) {
           // two staging buffers per warp: the store of the chunk before last must have finished READING its buffer
+          const long long tq1 = prof ? clock64() : 0;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
+          if (prof) w_st += clock64() - tq1;
           srow = stg_tile + (n_store & 1u) * 2048u + static_cast<uint32_t>(lane) * 64u;
         }
         const int col0 = n0 + ci * 32;
@@ -390,7 +394,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
       if (acc == 0) acc_ph ^= 1u;
     }
     if (p.tma_store && lane == 0) bulk_wait<0>();
-    if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull; }
+    if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull; p.dbg[10] = w_ld; p.dbg[11] = w_st; }
   }
 
   tc_fence_before();
@@ -543,7 +547,8 @@ static int tma_plan(const PrnConv& d, TmaKParams* p) {
   p->dbg = nullptr;
   const bool dense16 = d.out16 != nullptr && d.out32 == nullptr && d.act != PRN_ACT_SIGMOID_AVG4 && d.shuffle_n == 0 &&
                        (reinterpret_cast<uintptr_t>(d.out16) & 15) == 0 && d.ld_out16 % 8 == 0;
-  p->tma_store = (dense16 && (p->halo ? true : (p->groups == 1 && p->out_img_rows == p->hw_out))) ? 1 : 0;
+  static const bool store_off = [] { const char* e = getenv("PRN_TMA_STORE"); return e != nullptr && e[0] == '0'; }();
+  p->tma_store = (!store_off && dense16 && (p->halo ? true : (p->groups == 1 && p->out_img_rows == p->hw_out))) ? 1 : 0;
   p->lean_epi = (d.out16 != nullptr && d.out32 == nullptr && d.stats == nullptr &&
                  (d.act == PRN_ACT_NONE || d.act == PRN_ACT_RELU) && n_tile % 32 == 0 && d.n_pad % 32 == 0) ? 1 : 0;
   p->base_off_mode = tma_base_off();

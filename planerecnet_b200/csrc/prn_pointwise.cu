@@ -54,6 +54,60 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   }
 }
 
+// Same im2col straight from the CAMERA image: BGR, NHWC, uint8 or float [B, H_img, W_img, 3] with values 0..255 — the input
+// of FastBaseTransform (data/augmentations.py:496-530).  The transform ((x - MEANS) / STD per BGR channel, then BGR -> RGB) and
+// pad_even_divided (models/functions/funcs.py:204-210: zero-valued raw pixels up to the next multiple of 32, i.e.
+// -mean/std after normalisation) are folded into the patch load; pixels outside the padded extent are the conv's zero padding.
+template <typename T, typename U>
+__global__ void __launch_bounds__(256) stem_im2col_image_kernel(const U* __restrict__ img, T* __restrict__ out, int B, int Hi, int Wi,
+                                                                int H, int W, float m0, float m1, float m2, float s0, float s1,
+                                                                float s2) {
+  __shared__ float patch[21 * (kStemPatchW + 3)];
+  __shared__ __align__(16) short koff[192];
+  constexpr int kPW = kStemPatchW + 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const int strips = (Wo + kStemPx - 1) / kStemPx;
+  const int strip = blockIdx.x % strips;
+  const int ho = (blockIdx.x / strips) % Ho;
+  const int b = blockIdx.x / (strips * Ho);
+  const int wo0 = strip * kStemPx;
+  const int x0 = 2 * wo0 - 3, y0 = 2 * ho - 3;
+  if (threadIdx.x < 192) {
+    const int k = threadIdx.x;
+    const int c = k % 3, tap = k / 3;
+    koff[k] = k < 147 ? static_cast<short>((c * 7 + tap / 7) * kPW + tap % 7) : static_cast<short>(-1);
+  }
+  // patch[(c_rgb * 7 + ky)][col]; the three BGR values of a pixel are adjacent in memory: one thread loads one pixel
+  for (int i = threadIdx.x; i < 7 * kStemPatchW; i += blockDim.x) {
+    const int col = i % kStemPatchW, ky = i / kStemPatchW;
+    const int yy = y0 + ky, xx = x0 + col;
+    float r = 0.f, g = 0.f, bl = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+      float vb = 0.f, vg = 0.f, vr = 0.f;                 // pad_even_divided: raw zeros outside the camera image
+      if (yy < Hi && xx < Wi) {
+        const U* px = img + ((static_cast<long long>(b) * Hi + yy) * Wi + xx) * 3;
+        vb = static_cast<float>(px[0]); vg = static_cast<float>(px[1]); vr = static_cast<float>(px[2]);
+      }
+      bl = (vb - m0) / s0; g = (vg - m1) / s1; r = (vr - m2) / s2;      // (img - mean) / std in BGR order, then BGR -> RGB
+    }
+    patch[(0 * 7 + ky) * kPW + col] = r;
+    patch[(1 * 7 + ky) * kPW + col] = g;
+    patch[(2 * 7 + ky) * kPW + col] = bl;
+  }
+  __syncthreads();
+  const int npx = min(kStemPx, Wo - wo0);
+  for (int i = threadIdx.x; i < npx * 24; i += blockDim.x) {
+    const int kc = i % 24, px = i / 24;
+    const uint4 ko = *reinterpret_cast<const uint4*>(koff + kc * 8);
+    const short* o = reinterpret_cast<const short*>(&ko);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = o[j] >= 0 ? patch[o[j] + 2 * px] : 0.f;
+    const long long m = (static_cast<long long>(b) * Ho + ho) * Wo + wo0 + px;
+    store8(out + m * 192 + kc * 8, f);
+  }
+}
+
 // ---------------------------------------------------------------- 3x3/s2/p1 max pool (models/backbone.py:104)
 template <typename T>
 __global__ void maxpool3s2_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int H, int W, int C) {
@@ -352,6 +406,27 @@ int prn_stem_im2col(const float* x_nchw, void* out16, int32_t batch, int32_t h, 
   PRN_DISPATCH(dtype,
                (stem_im2col_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x_nchw, static_cast<__nv_bfloat16*>(out16), batch, h, w)),
                (stem_im2col_kernel<__half><<<grid, 256, 0, st>>>(x_nchw, static_cast<__half*>(out16), batch, h, w)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_stem_im2col_image(const void* img_bgr_nhwc, int32_t is_u8, void* out16, int32_t batch, int32_t h_img, int32_t w_img,
+                          int32_t h_pad, int32_t w_pad, const float* mean_bgr3, const float* std_bgr3, int32_t dtype, void* stream) {
+  PRN_REQUIRE(img_bgr_nhwc && out16 && mean_bgr3 && std_bgr3 && batch > 0 && h_img > 0 && w_img > 0 && h_pad >= h_img &&
+                  w_pad >= w_img && h_pad % 2 == 0 && w_pad % 2 == 0, "stem_im2col_image: bad arguments");
+  PRN_REQUIRE(std_bgr3[0] != 0.f && std_bgr3[1] != 0.f && std_bgr3[2] != 0.f, "stem_im2col_image: zero std");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int strips = (w_pad / 2 + kStemPx - 1) / kStemPx;
+  const int grid = batch * (h_pad / 2) * strips;
+  const float m0 = mean_bgr3[0], m1 = mean_bgr3[1], m2 = mean_bgr3[2], s0 = std_bgr3[0], s1 = std_bgr3[1], s2 = std_bgr3[2];
+#define PRN_STEM_IMG(T, U)                                                                                                  \
+  stem_im2col_image_kernel<T, U><<<grid, 256, 0, st>>>(static_cast<const U*>(img_bgr_nhwc), static_cast<T*>(out16), batch, h_img, \
+                                                       w_img, h_pad, w_pad, m0, m1, m2, s0, s1, s2)
+  if (is_u8) {
+    PRN_DISPATCH(dtype, (PRN_STEM_IMG(__nv_bfloat16, uint8_t)), (PRN_STEM_IMG(__half, uint8_t)));
+  } else {
+    PRN_DISPATCH(dtype, (PRN_STEM_IMG(__nv_bfloat16, float)), (PRN_STEM_IMG(__half, float)));
+  }
+#undef PRN_STEM_IMG
   PRN_LAUNCH_CHECK();
 }
 

@@ -232,13 +232,35 @@ class Engine:
         return self.gn_relu(y, stats, gn)
 
     # ------------------------------------------------------------------ stages
-    def backbone(self, x, bb):
-        """models/backbone.py:197-209.  x: NCHW fp32 CUDA.  Returns [C2..C5] NHWC 16-bit."""
-        assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
-        x = x.detach().float().contiguous()
-        B, _, H, W = x.shape
-        a = self._empty(B, H // 2, W // 2, 192)
-        self._call(self.lib.prn_stem_im2col, C.c_void_p(x.data_ptr()), C.c_void_p(a.data_ptr()), B, H, W, self.dt, self._st())
+    def stem_rows_from_images(self, frames, mean_bgr=None, std_bgr=None):
+        """FastBaseTransform (data/augmentations.py:496-530) + pad_even_divided (models/functions/funcs.py:204-210) folded into
+        the stem's im2col: frames [B, H, W, 3] BGR, uint8 or fp32 (0..255), CUDA.  Returns (rows [B, Hp/2, Wp/2, 192], Hp, Wp)."""
+        from .config import MEANS, STD
+        assert frames.is_cuda and frames.dim() == 4 and frames.shape[-1] == 3, "expected CUDA [B, H, W, 3] BGR frames"
+        if frames.dtype not in (torch.uint8, torch.float32):
+            frames = frames.float()
+        frames = frames.contiguous()
+        B, Hi, Wi, _ = frames.shape
+        Hp, Wp = (Hi + 31) // 32 * 32, (Wi + 31) // 32 * 32
+        mean = (C.c_float * 3)(*(mean_bgr or MEANS))
+        std = (C.c_float * 3)(*(std_bgr or STD))
+        a = self._empty(B, Hp // 2, Wp // 2, 192)
+        self._call(self.lib.prn_stem_im2col_image, C.c_void_p(frames.data_ptr()), 1 if frames.dtype == torch.uint8 else 0,
+                   C.c_void_p(a.data_ptr()), B, Hi, Wi, Hp, Wp, mean, std, self.dt, self._st())
+        return a, Hp, Wp
+
+    def backbone(self, x, bb, frames=False):
+        """models/backbone.py:197-209.  x: NCHW fp32 CUDA (normalised RGB), or with frames=True the camera frames
+        [B, H, W, 3] BGR uint8 / fp32 (the input transform runs inside the stem's im2col).  Returns [C2..C5] NHWC 16-bit."""
+        if frames:
+            a, H, W = self.stem_rows_from_images(x)
+            B = x.shape[0]
+        else:
+            assert x.is_cuda and x.dim() == 4 and x.shape[1] == 3
+            x = x.detach().float().contiguous()
+            B, _, H, W = x.shape
+            a = self._empty(B, H // 2, W // 2, 192)
+            self._call(self.lib.prn_stem_im2col, C.c_void_p(x.data_ptr()), C.c_void_p(a.data_ptr()), B, H, W, self.dt, self._st())
 
         def build_stem():
             w = bb.conv1.weight.detach().float()
@@ -458,10 +480,10 @@ class Engine:
         return self.to_nchw(d32, 1)
 
     # ------------------------------------------------------------------ whole dense forward (planerecnet.py:73-103)
-    def forward_dense(self, net, x, want_nchw=True):
+    def forward_dense(self, net, x, want_nchw=True, frames=False):
         if not x.is_cuda:
             raise L.PrnError("PlaneRecNet (B200) forward needs a CUDA input tensor; there is no CPU path")
-        cs_all = self.backbone(x, net.backbone)
+        cs_all = self.backbone(x, net.backbone, frames=frames)
         dec_cs = [cs_all[i] for i in net.depth_decoder_indices]
         if not self.multi_stream:
             ps = self.fpn([cs_all[i] for i in net.fpn_indices], net.fpn)
@@ -503,12 +525,12 @@ class Engine:
             st["outputs"] = (self.to_nchw(mask16, net.num_masks), cates, kerns, self.to_nchw(d32, 1))
         return st
 
-    def forward_dense_graph(self, net, x, want_nchw=True, slot=0):
+    def forward_dense_graph(self, net, x, want_nchw=True, slot=0, frames=False):
         """Same as forward_dense, replayed from a CUDA graph captured per (model, input shape, weight
         version): several hundred kernel launches become one graph launch.  The returned tensors are the
         graph's static buffers: consume them before the next call with the same `slot` (a pipelined caller
         alternates two slots so that one batch's bookkeeping can overlap the next batch's forward)."""
-        key = (id(net), tuple(x.shape), want_nchw, slot)
+        key = (id(net), tuple(x.shape), x.dtype, want_nchw, slot, frames)
         ent = self._graphs.get(key)
         # the graph bakes in pointers to the packed weights: any in-place parameter / buffer update (optimizer step,
         # load_state_dict, BN statistics) bumps a tensor version and forces a re-pack + re-capture
@@ -523,7 +545,7 @@ class Engine:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):          # warm-up: packs weights, primes the allocator
                 for _ in range(2):
-                    self.forward_dense(net, sx, want_nchw)
+                    self.forward_dense(net, sx, want_nchw, frames)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             gen = self._pack_gen
@@ -535,7 +557,7 @@ class Engine:
             gc.disable()       # a cyclic-GC pass destroying old CUDA graphs / events mid-capture would invalidate it
             try:
                 with torch.cuda.graph(g):
-                    st = self.forward_dense(net, sx, want_nchw)
+                    st = self.forward_dense(net, sx, want_nchw, frames)
             finally:
                 if gc_was:
                     gc.enable()

@@ -119,6 +119,18 @@ class PlaneRecNet(nn.Module):
         with timer.env("Inferencing"):
             return self.engine.inference(self, st, x)
 
+    def forward_frames(self, frames):
+        """Eval-mode `net(FastBaseTransform()(frames))` (simple_inference.py:226-231, eval.py:85-88) for camera frames
+        [B, H, W, 3] BGR, uint8 or fp32 0..255 on CUDA, with the transform (mean/std per BGR channel, BGR -> RGB) and
+        `pad_even_divided` (zero raw pixels up to the next multiples of 32) folded into the stem's im2col: no NHWC -> NCHW ->
+        NHWC bounce and no normalised fp32 copy of the batch.  Detections refer to the padded size, like the reference's."""
+        assert not self.training, "forward_frames is an eval-mode entry point"
+        B, Hi, Wi, _ = frames.shape
+        Hp, Wp = (Hi + 31) // 32 * 32, (Wi + 31) // 32 * 32
+        st = (self.engine.forward_dense_graph if self.use_cuda_graph else self.engine.forward_dense)(self, frames, False, frames=True)
+        shape_only = torch.empty(0, device=frames.device).expand(B, 3, Hp, Wp)      # the bookkeeping only reads the input size
+        return self.engine.inference(self, st, shape_only)
+
     def infer_pipelined(self, batches, depth=3):
         """Serving loop over an iterable of equally shaped input batches (pinned host or device tensors): yields, in
         order, exactly what `net(x)` returns for each batch.  Up to `depth` batches are in flight: while batch k's

@@ -35,7 +35,7 @@ def perturb_(net, seed=1234):
 
 def make_input(B, H, W, seed=0):
     g = torch.Generator().manual_seed(seed)
-    return torch.randn(B, 3, H, W, generator=g)
+    return torch.randn(B, 3, H, W, generator=g, device="cpu")
 
 
 def make_gt(B, H=480, W=640, seed=0, n_lo=3, n_hi=10):
@@ -45,21 +45,21 @@ def make_gt(B, H=480, W=640, seed=0, n_lo=3, n_hi=10):
     g = torch.Generator().manual_seed(1000 + seed)
     gts = []
     for _ in range(B):
-        n = int(torch.randint(n_lo, n_hi + 1, (1,), generator=g))
-        masks = torch.zeros(n, H, W, dtype=torch.uint8)
-        boxes = torch.zeros(n, 4, dtype=torch.float64)
+        n = int(torch.randint(n_lo, n_hi + 1, (1,), generator=g, device="cpu"))
+        masks = torch.zeros(n, H, W, dtype=torch.uint8, device="cpu")
+        boxes = torch.zeros(n, 4, dtype=torch.float64, device="cpu")
         for i in range(n):
-            w = int(torch.randint(W // 20, (2 * W) // 3, (1,), generator=g))
-            h = int(torch.randint(H // 16, (3 * H) // 4, (1,), generator=g))
-            x0 = int(torch.randint(0, W - w, (1,), generator=g))
-            y0 = int(torch.randint(0, H - h, (1,), generator=g))
+            w = int(torch.randint(W // 20, (2 * W) // 3, (1,), generator=g, device="cpu"))
+            h = int(torch.randint(H // 16, (3 * H) // 4, (1,), generator=g, device="cpu"))
+            x0 = int(torch.randint(0, W - w, (1,), generator=g, device="cpu"))
+            y0 = int(torch.randint(0, H - h, (1,), generator=g, device="cpu"))
             masks[i, y0:y0 + h, x0:x0 + w] = 1
-            boxes[i] = torch.tensor([x0, y0, x0 + w, y0 + h], dtype=torch.float64)
-        nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g, dtype=torch.float64), dim=1)
-        planes = torch.cat([nrm, torch.rand(n, 1, generator=g, dtype=torch.float64) + 1], 1)
-        K = torch.tensor([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], dtype=torch.float64)
-        gts.append(dict(masks=masks, boxes=boxes, classes=torch.zeros(n, dtype=torch.int64), plane_paras=planes, k_matrix=K))
-    gt_depth = 0.5 + 4 * torch.rand(B, 1, H, W, generator=g)
+            boxes[i] = torch.tensor([x0, y0, x0 + w, y0 + h], dtype=torch.float64, device="cpu")
+        nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g, dtype=torch.float64, device="cpu"), dim=1)
+        planes = torch.cat([nrm, torch.rand(n, 1, generator=g, dtype=torch.float64, device="cpu") + 1], 1)
+        K = torch.tensor([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], dtype=torch.float64, device="cpu")
+        gts.append(dict(masks=masks, boxes=boxes, classes=torch.zeros(n, dtype=torch.int64, device="cpu"), plane_paras=planes, k_matrix=K))
+    gt_depth = 0.5 + 4 * torch.rand(B, 1, H, W, generator=g, device="cpu")
     return gts, gt_depth
 
 
@@ -70,7 +70,7 @@ def make_cotangents(outs, seed=1, device=None):
     m, cs, ks, d = outs
 
     def mk(t):
-        v = torch.randn(t.shape, generator=g) / t[0].numel() ** 0.5
+        v = torch.randn(t.shape, generator=g, device="cpu") / t[0].numel() ** 0.5
         return v.to(device if device is not None else t.device)
 
     return (mk(m), [mk(c) for c in cs], [mk(k) for k in ks], mk(d))

@@ -145,3 +145,58 @@ def test_conv3x3_to1_reflect_softplus(eng):
               C.c_void_p(out.data_ptr()), 2, 21, 35, 64, 1, eng.dt, eng._st())
     exp = F.softplus(F.conv2d(F.pad(ref, (1, 1, 1, 1), mode="reflect"), w, torch.tensor([0.3])))
     assert (out.cpu().permute(0, 3, 1, 2) - exp).abs().max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("u8,hw", [(True, (96, 128)), (False, (96, 128)), (True, (75, 101))])
+def test_stem_rows_from_camera_frames_equal_transform_then_im2col(cuda_lib, u8, hw):
+    """FastBaseTransform (data/augmentations.py:496-530: (x - MEANS) / STD per BGR channel, BGR -> RGB) and
+    pad_even_divided (models/functions/funcs.py:204-210) folded into the stem's im2col give BIT-IDENTICAL rows to running the
+    transform in torch and feeding prn_stem_im2col (same fp32 arithmetic before the one 16-bit rounding)."""
+    import torch
+    from planerecnet_b200.config import MEANS, STD
+    from planerecnet_b200.engine import Engine
+    eng = Engine("f16")
+    Hi, Wi = hw
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (2, Hi, Wi, 3), generator=g, dtype=torch.uint8)
+    fr = frames.cuda() if u8 else frames.float().cuda()
+    rows, Hp, Wp = eng.stem_rows_from_images(fr)
+    # the reference's path: pad_even_divided on the raw image, then FastBaseTransform
+    padded = torch.zeros(2, Hp, Wp, 3)
+    padded[:, :Hi, :Wi] = frames.float()
+    img = padded.permute(0, 3, 1, 2).contiguous()
+    mean = torch.tensor(MEANS).float()[None, :, None, None]
+    std = torch.tensor(STD).float()[None, :, None, None]
+    x = ((img - mean) / std)[:, (2, 1, 0), :, :].contiguous().cuda()
+    ref = eng._empty(2, Hp // 2, Wp // 2, 192)
+    import ctypes as C
+    eng._call(eng.lib.prn_stem_im2col, C.c_void_p(x.data_ptr()), C.c_void_p(ref.data_ptr()), 2, Hp, Wp, eng.dt, eng._st())
+    torch.cuda.synchronize()
+    assert (Hp, Wp) == ((Hi + 31) // 32 * 32, (Wi + 31) // 32 * 32)
+    assert torch.equal(rows.view(torch.int16), ref.view(torch.int16))
+
+
+@pytest.mark.gpu
+def test_forward_frames_equals_forward_of_transformed_batch(cuda_lib):
+    """net.forward_frames(frames) == net(FastBaseTransform()(frames)): same detections and depth (dense forward inputs are
+    bit-identical, so only the GroupNorm atomics' run-to-run noise remains)."""
+    import torch
+    import helpers as H
+    from planerecnet_b200.config import MEANS, STD
+    net = H.perturb_(H.build_ours("PlaneRecNet_50_config")).eval().cuda()
+    g = torch.Generator().manual_seed(1)
+    frames = torch.randint(0, 256, (2, 128, 160, 3), generator=g, dtype=torch.uint8).cuda()
+    mean = torch.tensor(MEANS, device="cuda").float()[None, :, None, None]
+    std = torch.tensor(STD, device="cuda").float()[None, :, None, None]
+    x = ((frames.float().permute(0, 3, 1, 2).contiguous() - mean) / std)[:, (2, 1, 0), :, :].contiguous()
+    with torch.no_grad():
+        ref = net(x)
+        ref = [{k: (None if v is None else v.clone()) for k, v in r.items()} for r in ref]
+        got = net.forward_frames(frames)
+    for r, o in zip(got, ref):
+        assert list(r.keys()) == list(o.keys())
+        assert H.rel_l2(r["pred_depth"], o["pred_depth"]) < 2e-3
+        n_r = 0 if r["pred_scores"] is None else len(r["pred_scores"])
+        n_o = 0 if o["pred_scores"] is None else len(o["pred_scores"])
+        assert abs(n_r - n_o) <= max(2, n_o // 5), (n_r, n_o)

@@ -229,6 +229,54 @@ t4_kernel(const __grid_constant__ CUtensorMap tm, const T4Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- T5
+// tcgen05.mma issue/execute rate with operands resident in shared memory (no loads in flight): cycles per M x N x 16 MMA.
+// mode 0: SS (A and B from shared memory), one accumulator; 1: SS, two accumulators alternating; 2: A from TMEM (TS), one
+// accumulator.  m = 128 or 64.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__global__ void __launch_bounds__(128, 1) t5_kernel(long long* out, int mode, int m, int n, int iters) {
+  extern __shared__ uint8_t raw[];
+  const uint32_t raw_u = smem_u32(raw);
+  const uint32_t base = (raw_u + 1023u) & ~1023u;
+  uint8_t* bp = raw + (base - raw_u);
+  const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 16;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (16384 + 32768) / 16; i += 128) reinterpret_cast<uint4*>(bp)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  if (tid < 32) { tmem_alloc(slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(bp + 16384 + 32768 + 16);
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc(0, m, n);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int k = it & 3;
+      const uint32_t d = tmem + ((mode == 1 && (it & 4)) ? 256u : 0u);
+      if (mode == 2) umma_f16_ts(d, tmem + 480u, desc_sw128(b_s + k * 32, 1024, 0), idesc, it > 7 ? 1u : 0u);
+      else umma_f16(d, desc_sw128(a_s + k * 32, 1024, 0), desc_sw128(b_s + k * 32, 1024, 0), idesc, it > 7 ? 1u : 0u);
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (tid < 32) tmem_dealloc(tmem, 512);
+}
+
 static float h2f(__half h) { return __half2float(h); }
 
 int main(int argc, char** argv) {
@@ -417,6 +465,28 @@ int main(int argc, char** argv) {
       printf("T4 %-88s: %.1f B/clk/SM (mean), %.1f (slowest CTA); chip %.2f TB/s\n", c.name, bytes / (csum / c.grid), bytes / cmax,
              bytes * c.grid / (ms * 1e-3) / 1e12);
     }
+  }
+  // ------------------------------------------------------------------ T5
+  {
+    long long* dout;
+    CK(cudaMalloc(&dout, 16));
+    CK(cudaFuncSetAttribute(t5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024));
+    const int iters = 512;
+    const char* mname[3] = {"SS 1 accumulator ", "SS 2 accumulators", "TS (A in TMEM)   "};
+    for (int mode = 0; mode < 3; ++mode)
+      for (int m : {128, 64})
+        for (int n : {32, 64, 128, 256}) {
+          if (mode == 1 && n > 128 && false) continue;
+          long long h[2];
+          for (int rep = 0; rep < 2; ++rep) {
+            t5_kernel<<<1, 128, 52 * 1024>>>(dout, mode, m, n, iters);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("T5 LAUNCH-ERR %s (mode %d m %d n %d)\n", cudaGetErrorString(e), mode, m, n); return 3; }
+          }
+          CK(cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost));
+          printf("T5 %s M=%3d N=%3d: %.1f cycles per MMA to issue, %.1f to complete  (math floor %d)\n", mname[mode], m, n,
+                 (double)h[0] / iters, (double)h[1] / iters, n / 2);
+        }
   }
   printf("probe done\n");
   return 0;
