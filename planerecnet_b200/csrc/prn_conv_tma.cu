@@ -10,11 +10,10 @@
 //   1x1 / stride 1 ("linear mode"): one M tile = 128 consecutive pixel rows = one 2-D TMA box per 64-channel block.
 //
 // Warp roles (512 threads, persistent CTAs, static round-robin tile schedule):
-//   WG0, WG1 (warps 0-7)  epilogue: tcgen05.ld -> bias/residual/activation/statistics -> TMA stores through two 2 KB
+//   WG0-WG2 (warps 0-11)  epilogue: tcgen05.ld -> bias/residual/activation/statistics -> TMA stores through two 2 KB
 //                          staging buffers per warp (a store drains while the next chunk is converted), or direct stores
-//   warp 8                 halo border patch (reflect / clamp), otherwise idle
 //   warp 12                A producer (TMA), warp 14: B producer (TMA, one {64 k, n_tile} weight box per tap and block)
-//   warp 13                MMA issuer + TMEM owner
+//   warp 13                MMA issuer + TMEM owner, warp 15: halo border patch (reflect / clamp padding)
 //
 // Replaces the same nn.Conv2d / F.conv2d call sites as prn_conv.cu (include/prn_b200.h); prn_conv2d_fwd dispatches here
 // when the geometry qualifies (conv_tma_eligible) and falls back to the gather kernel otherwise.
@@ -46,6 +45,7 @@ struct TmaKParams {
 };
 
 constexpr int kTmaCtrlBytes = 2048;     // barriers (first 512 B), bias staging (+1024, 1 KB)
+constexpr int kTmaStageOutBytes = 3 * 4 * 4096;   // per epilogue warp (up to 12) two 2 KB staging buffers
 
 template <typename T, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -53,6 +53,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
                 const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
                 const __grid_constant__ TmaKParams p) {
   constexpr bool kFull = kEpi != 0;
+  // epilogue warpgroups: three (WG0-2, 152 registers per thread) for the inference instantiations; the BatchNorm-statistics
+  // instantiation of the training step needs 184 registers per thread and keeps two (WG2 idles)
+  constexpr int kTmaEpiGroups = kEpi == 2 ? 2 : 3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -67,8 +70,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
   const uint32_t bar_tempty = base + 336;        // [2]
   const uint32_t tmem_slot = base + 352;
   float* bias_s = reinterpret_cast<float*>(base_ptr + 1024);
-  const uint32_t stg_base = base + kTmaCtrlBytes;                 // 8 warps x 2 x 2 KB
-  const uint32_t a_base = stg_base + kStageOutBytes;              // 1024-aligned
+  const uint32_t stg_base = base + kTmaCtrlBytes;                 // 12 warps x 2 x 2 KB
+  const uint32_t a_base = stg_base + kTmaStageOutBytes;           // 1024-aligned
   const uint32_t b_base = a_base + static_cast<uint32_t>(p.sa) * p.a_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
@@ -91,7 +94,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 2 * kEpiWarps * 32);
+      mbar_init(bar_tempty + 8 * a, kTmaEpiGroups * kEpiWarps * 32);
     }
     mbar_fence_init();
   }
@@ -118,7 +121,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         if (p.halo) {
           const int img = mt / p.tiles_per_img, rem = mt - img * p.tiles_per_img;
           const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-          c_w = tx * kPatchW - 1; c_h = ty * kPatchH - 1; c_n = img;
+          c_w = tx * kPatchW - d.pad; c_h = ty * kPatchH - d.pad; c_n = img;      // pad 1, or 2 (zero padding only)
         } else {
           const int g = mt / p.m_tiles, mm = mt - g * p.m_tiles;
           row0 = g * p.m_group + mm * kTileM;
@@ -196,10 +199,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         if (acc == 0) acc_ph ^= 1u;
       }
       if (prof) { p.dbg[4] = clock64() - t_role0; p.dbg[5] = w_a; p.dbg[6] = w_tempty; p.dbg[9] = w_b; }
-    }
-  } else if (wg == 2) {
-    reg_dec<56>();
-    if (warp == 8 && p.fix != 0) {
+    } else if (warp == 15 && p.fix != 0) {
       // =========================================================== halo border patch (reflect / clamp padding)
       // The TMA box zero-fills pixels outside the image; nn.ReflectionPad2d(1) needs image row 1 at row -1 (row H-2 at
       // row H), replicate padding row 0 (row H-1); same for columns.  Rows first, then columns over all rows (corners).
@@ -242,22 +242,24 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         }
       }
     }
+  } else if (wg >= kTmaEpiGroups) {
+    reg_dec<56>();
   } else {
-    // =========================================================== epilogue (WG0 + WG1)
-    reg_inc<184>();
+    // =========================================================== epilogue (WG0 + WG1 [+ WG2])
+    if constexpr (kTmaEpiGroups == 3) reg_inc<152>(); else reg_inc<184>();
     const int q = warp & 3;         // TMEM lane quarter
-    const int ge = wg;              // epilogue group: owns the 64-column groups with index % 2 == ge
-    const int etid = threadIdx.x;   // 0 .. 255
+    const int ge = wg;              // epilogue group: owns the 32-column chunks with index % 3 == ge
+    const int etid = threadIdx.x;   // 0 .. 383
     int acc = 0;
     uint32_t acc_ph = 0;
     const bool avg4 = d.act == PRN_ACT_SIGMOID_AVG4;
     const bool has_res = d.residual != nullptr;
     const bool has_stats = d.stats != nullptr;
     const bool prof = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-    long long w_tfull = 0, w_ld = 0, w_st = 0;
+    long long w_tfull = 0;
     const long long t_role0 = prof ? clock64() : 0;
     int bias_n0 = -1;
-    const uint32_t stg_tile = stg_base + static_cast<uint32_t>(warp) * 4096u;   // two 2 KB buffers
+    const uint32_t stg_tile = stg_base + static_cast<uint32_t>(warp) * 4096u;   // two 2 KB buffers (warps 0-11)
     uint32_t n_store = 0;           // chunks this warp has staged so far (selects the buffer)
     const int m_local = q * 32 + lane;
     for (int tile = t0; tile < p.total_tiles; tile += t_step) {
@@ -293,9 +295,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
       const T* res_row = has_res ? static_cast<const T*>(d.residual) + rrow * d.ld_res + n0 : nullptr;
 
       if (d.bias != nullptr && n0 != bias_n0) {
-        named_bar_sync(1, 2 * kEpiWarps * 32);
-        for (int i = etid; i < n_valid; i += 2 * kEpiWarps * 32) bias_s[i] = __ldg(d.bias + n0 + i);
-        named_bar_sync(1, 2 * kEpiWarps * 32);
+        named_bar_sync(1, kTmaEpiGroups * kEpiWarps * 32);
+        for (int i = etid; i < n_valid; i += kTmaEpiGroups * kEpiWarps * 32) bias_s[i] = __ldg(d.bias + n0 + i);
+        named_bar_sync(1, kTmaEpiGroups * kEpiWarps * 32);
         bias_n0 = n0;
       }
 
@@ -305,46 +307,32 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
 
       const int n32 = n_valid >> 5;
       const int ntot = n32 + ((kFull && (n_valid & 16)) ? 1 : 0);
-      auto next_of = [&](int c) {
-        ++c;
-        while (c < ntot && ((c >> 1) & 1) != ge) ++c;
-        return c;
-      };
-      int ci = ge == 0 ? 0 : next_of(0);
+      // chunk c belongs to group c % kTmaEpiGroups (three groups, N = 256: 3 + 3 + 2 chunks)
+      auto next_of = [&](int c) { return c + kTmaEpiGroups; };
+      int ci = ge;
       uint32_t vb[32];
-      uint4 rb[4];
       __syncwarp();
       if (ci < ntot) {
-        if (ci < n32) {
-          tmem_ld_x32(t_row + ci * 32, vb);
-          load_res<32>(rb, res_row + ci * 32, has_res && valid);
-        } else {
-          tmem_ld_x16(t_row + ci * 32, vb);
-          load_res<16>(rb, res_row + ci * 32, has_res && valid);
-        }
+        if (ci < n32) tmem_ld_x32(t_row + ci * 32, vb);
+        else tmem_ld_x16(t_row + ci * 32, vb);
       }
       while (ci < ntot) {
-        const long long tq0 = prof ? clock64() : 0;
+        // residual of THIS chunk: issued first, consumed after the accumulator has been unpacked (three epilogue warps per
+        // scheduler cover the latency; prefetching it one chunk ahead would cost 16 more registers per thread)
+        uint4 rc[4];
+        if (ci < n32) load_res<32>(rc, res_row + ci * 32, has_res && valid);
+        else load_res<16>(rc, res_row + ci * 32, has_res && valid);
         tmem_ld_wait();
-        if (prof) w_ld += clock64() - tq0;
         tmem_ld_publish16(vb);
         tmem_ld_publish16(vb + 16);
         float x[32];
-        uint4 rc[4];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(vb[j]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rc[j] = rb[j];
         const int cn = next_of(ci);
         __syncwarp();
         if (cn < ntot) {
-          if (cn < n32) {
-            tmem_ld_x32(t_row + cn * 32, vb);
-            load_res<32>(rb, res_row + cn * 32, has_res && valid);
-          } else {
-            tmem_ld_x16(t_row + cn * 32, vb);
-            load_res<16>(rb, res_row + cn * 32, has_res && valid);
-          }
+          if (cn < n32) tmem_ld_x32(t_row + cn * 32, vb);
+          else tmem_ld_x16(t_row + cn * 32, vb);
         }
         if (kFull && p.halo && has_stats && d.stats_cg > 0 && !valid) {
 #pragma unroll
@@ -353,10 +341,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         uint32_t srow = 0u;
         if (p.tma_store) {
           // two staging buffers per warp: the store of the chunk before last must have finished READING its buffer
-          const long long tq1 = prof ? clock64() : 0;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
-          if (prof) w_st += clock64() - tq1;
           srow = stg_tile + (n_store & 1u) * 2048u + static_cast<uint32_t>(lane) * 64u;
         }
         const int col0 = n0 + ci * 32;
@@ -394,7 +380,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
       if (acc == 0) acc_ph ^= 1u;
     }
     if (p.tma_store && lane == 0) bulk_wait<0>();
-    if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull; p.dbg[10] = w_ld; p.dbg[11] = w_st; }
+    if (prof) { p.dbg[7] = clock64() - t_role0; p.dbg[8] = w_tfull;  }
   }
 
   tc_fence_before();
@@ -427,7 +413,8 @@ bool conv_tma_eligible(const PrnConv& d) {
   if (!tma_mode()) return false;
   if (d.dcn_offmask != nullptr || d.upsample != 1 || d.stride != 1) return false;
   if (d.dtype != PRN_BF16 && d.dtype != PRN_F16) return false;
-  const bool k3 = d.ksize == 3 && d.pad == 1;
+  // pad 2 with zero padding = the "full" correlation the input gradient of a reflection-padded 3x3 conv needs (train_engine.py)
+  const bool k3 = d.ksize == 3 && (d.pad == 1 || (d.pad == 2 && d.pad_mode == PRN_PAD_ZERO && d.shuffle_n == 0));
   const bool k1 = d.ksize == 1 && d.pad == 0;
   if (!k3 && !k1) return false;
   if (k1 && d.pad_mode != PRN_PAD_ZERO) return false;
@@ -446,7 +433,10 @@ static int tma_plan(const PrnConv& d, TmaKParams* p) {
   PRN_REQUIRE(d.c0 > 0 && d.c0 % 64 == 0 && d.c1 >= 0 && d.c1 % 64 == 0, "conv: channel counts must be multiples of 64 (c0=%d c1=%d)", d.c0, d.c1);
   PRN_REQUIRE(d.c1 == 0 || d.src1 != nullptr, "conv: src1 is NULL but c1=%d", d.c1);
   PRN_REQUIRE(d.batch > 0 && d.h_in > 0 && d.w_in > 0, "conv: bad spatial dims");
-  PRN_REQUIRE(d.h_out == d.h_in && d.w_out == d.w_in, "conv: h_out/w_out inconsistent with input dims");
+  {
+    const int grow = d.ksize == 3 ? 2 * d.pad - 2 : 0;
+    PRN_REQUIRE(d.h_out == d.h_in + grow && d.w_out == d.w_in + grow, "conv: h_out/w_out inconsistent with input dims");
+  }
   PRN_REQUIRE(d.n_pad > 0 && d.n_pad % 16 == 0, "conv: n_pad must be a positive multiple of 16 (got %d)", d.n_pad);
   PRN_REQUIRE(d.out16 != nullptr || d.out32 != nullptr, "conv: no output buffer");
   PRN_REQUIRE(d.out16 == nullptr || d.ld_out16 % 8 == 0, "conv: ld_out16 must be a multiple of 8");
@@ -526,7 +516,7 @@ static int tma_plan(const PrnConv& d, TmaKParams* p) {
   p->tmem_cols = cols;
   p->b_stage_bytes = static_cast<uint32_t>(n_tile) * 128u;
   // shared memory: control + store staging + A ring + B ring
-  const int avail = kSmemBudget - 1024 - kTmaCtrlBytes - kStageOutBytes;
+  const int avail = kSmemBudget - 1024 - kTmaCtrlBytes - kTmaStageOutBytes;
   int sa = p->halo ? 2 : 4;
   int sb = (avail - sa * static_cast<int>(p->a_stage_bytes)) / static_cast<int>(p->b_stage_bytes);
   if (p->halo && sb > 8) {           // small weight tiles: a third halo stage instead of more than 8 weight stages
@@ -647,7 +637,7 @@ int conv_tma_launch(const PrnConv* desc, void* stream, long long* dbg) {
   }
   const int sms = sm_count();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  const size_t smem = 1024 + kTmaCtrlBytes + kStageOutBytes + static_cast<size_t>(p.sa) * p.a_stage_bytes +
+  const size_t smem = 1024 + kTmaCtrlBytes + kTmaStageOutBytes + static_cast<size_t>(p.sa) * p.a_stage_bytes +
                       static_cast<size_t>(p.sb) * p.b_stage_bytes;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool bnstats = d.stats != nullptr && d.stats_cg == 0;

@@ -54,6 +54,7 @@ CASES = {
                                          subpixel=True),
     "3x3_subpixel_up2_reflect_n128_f16": dict(B=2, H=30, W=24, C=256, N=128, k=3, pad=1, reflect=True, up=2, bias=True, act="relu",
                                               subpixel=True, dtype="f16"),
+    "3x3_halo_pad2_full_correlation": dict(B=2, H=15, W=20, C=128, N=128, k=3, pad=2, bias=True),
     "3x3_halo_kernelpred_rows": dict(B=2, H=24, W=24, C=256, N=128, k=3, pad=1, bias=True, out32=True),
     "1x1_residual_relu_n1024": dict(B=2, H=30, W=40, C=256, N=1024, k=1, bias=True, residual=True, act="relu"),
     "1x1_c64_n256_big": dict(B=2, H=60, W=80, C=64, N=256, k=1, bias=True, act="relu", dtype="f16"),

@@ -115,25 +115,37 @@ def test_train_step_480x640_bs8_graph_equals_eager(cuda_lib):
     net = TC._build("PlaneRecNet_101_config", cond=True).train().cuda()
     x = H.make_input(B_BENCH, H_IMG, W_IMG, 0).cuda()
     eng = net.train_engine
-    outs = eng.forward_train(net, x)
-    cots = make_cotangents(outs, seed=1, device="cuda")
-    eng.seed_output_grads(*cots)
-    g_eager = {k: v.clone() for k, v in eng.backward().items()}
-    o_eager = [outs[0].clone(), outs[3].clone()]
+
+    def flat(g):
+        return torch.cat([g[id(p)].flatten().float() for p in net.parameters() if id(p) in g]).clone()
+
+    def cosine(a, b):
+        return float((a.double() @ b.double()) / (a.double().norm() * b.double().norm()))
+
+    def eager():
+        outs = eng.forward_train(net, x)
+        cots_ = make_cotangents(outs, seed=1, device="cuda")
+        eng.seed_output_grads(*cots_)
+        g = flat(eng.backward())
+        return [outs[0].clone(), outs[3].clone()], g, cots_
+
+    o_e0, g_e0, cots = eager()
+    o_e1, g_e1, _ = eager()
+    # run-to-run noise of the eager path itself (fp32 atomics in the BatchNorm statistics -> 16-bit rounding flips, amplified by
+    # the batch-statistics network): the graph replay has to agree with eager to that noise, not better
+    noise_m, noise_d, noise_cos = H.rel_l2(o_e1[0], o_e0[0]), H.rel_l2(o_e1[1], o_e0[1]), cosine(g_e1, g_e0)
     step = GraphedStep(eng, net, x)
     so = step.forward(x)
-    g_graph = step.backward(*cots)
+    gg = step.backward(*cots)
     torch.cuda.synchronize()
-    e_m, e_d = H.rel_l2(so[0], o_eager[0]), H.rel_l2(so[3], o_eager[1])
-    print("bs8 480x640 graph-vs-eager outputs", e_m, e_d)
-    assert e_m < 5e-2 and e_d < 5e-2, (e_m, e_d)
-    a = torch.cat([g_graph[id(p)].flatten().float() for p in net.parameters() if id(p) in g_graph])
-    b = torch.cat([g_eager[id(p)].flatten().float() for p in net.parameters() if id(p) in g_eager])
-    assert a.numel() == b.numel() and bool(torch.isfinite(a).all())
     n_params = sum(1 for p in net.parameters() if p.requires_grad)
-    assert len(g_graph) >= n_params, (len(g_graph), n_params)
-    cos = float((a.double() @ b.double()) / (a.double().norm() * b.double().norm()))
-    print("bs8 480x640 graph-vs-eager gradient cosine", cos)
-    assert cos > 0.95, cos          # run-to-run noise of the fp32 atomics, amplified by batch-statistics BatchNorm
+    assert len(gg) >= n_params, (len(gg), n_params)
+    g_g = flat(gg)
+    assert g_g.numel() == g_e0.numel() and bool(torch.isfinite(g_g).all())
+    e_m, e_d, cos = H.rel_l2(so[0], o_e0[0]), H.rel_l2(so[3], o_e0[1]), cosine(g_g, g_e0)
+    print(f"bs8 480x640: eager run-to-run mask {noise_m:.2e} depth {noise_d:.2e} grad cosine {noise_cos:.4f} | "
+          f"graph vs eager mask {e_m:.2e} depth {e_d:.2e} grad cosine {cos:.4f}")
+    assert e_m <= max(3 * noise_m, 5e-3) and e_d <= max(3 * noise_d, 5e-3), (e_m, e_d, noise_m, noise_d)
+    assert (1 - cos) <= max(3 * (1 - noise_cos), 1e-3), (cos, noise_cos)
     del step
     torch.cuda.empty_cache()

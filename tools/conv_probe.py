@@ -104,7 +104,7 @@ def probe(name, dt=L.PRN_F16, reps=20):
     kb = max(1, c[3])
     print(f"{name:20s} M={M:7d} N={N:5d} K={k * k * Cc:5d} {us:8.1f} us {tfl:7.1f} TFLOP/s | "
           f"prod tot={c[0]:9d} wEmpty={c[1]:9d} wCp={c[2]:9d} kb={c[3]:5d} ({c[0] // kb} cyc/kb) | "
-          f"mma tot={c[4]:9d} wFull={c[5]:9d} wTmemE={c[6]:8d} wB={c[9]:8d} | epi tot={c[7]:9d} wTfull={c[8]:9d} wLd={c[10]:7d} wStore={c[11]:7d}", flush=True)
+          f"mma tot={c[4]:9d} wFull={c[5]:9d} wTmemE={c[6]:8d} wB={c[9]:8d} | epi tot={c[7]:9d} wTfull={c[8]:9d} wLd={c[10]:7d} wStore={c[11]:7d} ldIssue={c[12]:7d} chunk={c[13]:7d} stIssue={c[14]:7d}", flush=True)
 
 
 def C_int():

@@ -84,6 +84,10 @@ def run_simple_inference(a):
     ckpt = os.path.join(tmp, "PlaneRecNet_random_init.pth")
     net = planerecnet.PlaneRecNet(cfg)
     keys = list(net.state_dict().keys())
+    with torch.no_grad():
+        # the script looks class names up in cfg.dataset.class_names = ('plane',) (simple_inference.py:106): a random-init model
+        # must not emit class 1, which no trained checkpoint does
+        net.inst_head.cate_pred.bias[1] = -20.0
     net.save_weights(ckpt)
     del net
     out_png = os.path.join(tmp, "out.png")
