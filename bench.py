@@ -406,6 +406,7 @@ def main():
                 parity = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
         # ---- end to end through the public serving API
+        from planerecnet_b200.postprocess import pack_mask_bits
         pinned = {}
 
         def d2h(res):
@@ -414,11 +415,9 @@ def main():
             out_bytes = 0
             staged = []
             fields = {k: [r[k] for r in res if r[k] is not None] for k in ("pred_scores", "pred_classes", "pred_boxes", "pred_depth")}
-            masks = [r["pred_masks"] for r in res if r["pred_masks"] is not None]
-            if masks:
-                m = torch.cat(masks).reshape(-1, 8).to(torch.uint8)
-                wts = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=m.device)
-                fields["pred_masks_packed"] = [(m * wts).sum(1, dtype=torch.uint8)]
+            packed = pack_mask_bits([r["pred_masks"] for r in res])            # prn_pack_mask_bits: one launch for the batch
+            if packed is not None:
+                fields["pred_masks_packed"] = [packed]
             for k, parts in fields.items():
                 if parts:
                     t = torch.cat(parts) if len(parts) > 1 else parts[0]

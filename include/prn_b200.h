@@ -181,6 +181,10 @@ int prn_mask_stats(const float* seg, void* mask16, float* area, float* ssum, int
 int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool, int32_t* boxes, int32_t n_inst, int32_t h,
                           int32_t w, int32_t h_out, int32_t w_out, float thr, void* stream);
 
+/* Instance masks for the host: bool [n_bool] (one byte each, the `pred_masks` of planerecnet.py:275,283) -> bits, LSB first
+ * (out byte i, bit j = mask byte 8 i + j); n_bool a multiple of 16.  8x fewer bytes over PCIe for the serving loop's D2H. */
+int prn_pack_mask_bits(const void* masks_bool, void* out_bits, int64_t n_bool, void* stream);
+
 /* Greedy mask-NMS (models/functions/nms.py:53-80, selected by nms_type == 'mask', planerecnet.py:249-252) over the
  * score-sorted candidates of each image: inter fp32 [B][n][n] = mask intersections, area fp32 [B][n], labels int64 [B][n],
  * valid/keep uint8 [B][n].  keep[j] = valid[j] and no kept earlier candidate of the same label has IoU > thr with j. */

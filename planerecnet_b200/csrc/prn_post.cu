@@ -129,7 +129,39 @@ __global__ void upsample_mask_box_kernel(const float* __restrict__ seg, const in
 
 using namespace prn;
 
+// bool [n] (one byte each, 0/1) -> bits, LSB first: out[i] bit j = in[8 i + j].  16 input bytes per thread.
+__global__ void pack_mask_bits_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long long n_pairs) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_pairs;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t x = w[k] & 0x01010101u;                       // bytes b0..b3 -> bits 0, 8, 16, 24
+      const uint32_t nib = (x | (x >> 7) | (x >> 14) | (x >> 21)) & 0xFu;
+      bits |= nib << (4 * k);
+    }
+    reinterpret_cast<uint16_t*>(out)[i] = static_cast<uint16_t>(bits);
+  }
+}
+
 extern "C" {
+
+int prn_pack_mask_bits(const void* masks_bool, void* out_bits, int64_t n_bool, void* stream) {
+  PRN_REQUIRE(masks_bool && out_bits && n_bool > 0 && n_bool % 16 == 0 && (reinterpret_cast<uintptr_t>(masks_bool) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out_bits) & 1) == 0,
+              "pack_mask_bits: need a 16-byte aligned input of a multiple of 16 bools");
+  const long long n_pairs = n_bool / 16;
+  const int threads = 256;
+  long long blocks = (n_pairs + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_mask_bits_kernel<<<static_cast<int>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(masks_bool), static_cast<uint8_t*>(out_bits), n_pairs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(PRN_ERR_CUDA, "pack_mask_bits launch: %s", cudaGetErrorString(e));
+  return PRN_OK;
+}
 
 int prn_point_nms_sigmoid(const float* logits, float* scores, int32_t batch, int32_t total, int32_t ld, int32_t nc,
                           int32_t n_levels, const int32_t* grids_dev, void* stream) {

@@ -5,9 +5,11 @@
 
   ins_lava_losses(mask_pred, kernel_preds, targets, gt_depths)   losses.py:81-118, 168-197  dice + depth-gradient terms
 
-The plane-normal term (numpy-RNG triplet sampling, vnl.py) is not built; the reference's implementation runs on the
-training outputs unchanged meanwhile.
-Targets come from planerecnet_b200.targets (device-resident assignment)."""
+  _PlaneNormalBatched                                            losses.py:150-165, vnl.py:6-165  plane surface-normal term of a
+                                                                 whole batch in a few dozen tensor ops (numpy-RNG-exact triplets)
+  PlaneRecNetLoss                                                losses.py:12-198  the joint loss behind the reference's signature
+
+Targets come from planerecnet_b200.targets (device-resident assignment, one host round trip per batch)."""
 import ctypes as C
 import math
 
@@ -326,6 +328,178 @@ class _PlaneNormal:
         return total / n_planes
 
 
+class _PlaneNormalBatched:
+    """The same plane surface-normal term (models/functions/vnl.py:6-165) for a whole batch in a few dozen tensor ops instead of a
+    Python loop over every plane of every image (48 planes + 8 "rest" regions per batch of 8: ~1000 tiny launches and a host
+    round trip per plane before).  One host sync fetches the pixel count of every region; the triplets are then drawn
+
+      sampling="numpy"   with numpy's GLOBAL RNG in exactly the reference's call order (image by image, plane by plane, then the
+                         non-planar rest: `choice` + `shuffle`, three times, vnl.py:48-53) — bit-identical triplets, hence loss
+                         values and gradients equal to the reference's for a given `np.random.seed`; ~1.5 ms of host time per plane;
+      sampling="device"  with torch's device RNG (i.i.d. uniform indices: the reference's shuffle of i.i.d. draws is a
+                         statistical no-op) — same distribution, no host work;
+
+    and everything after the sampling (gather of the triplets' 3-D points, the colinear / in-front / too-close tests, normals,
+    |cos| against the plane normal resp. the ground-truth normals, worst-75 % tail per region) is evaluated for all triplets of
+    all regions at once; the per-region sort of the tail is one global sort on the composite key (region, loss)."""
+
+    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4, sampling="numpy"):
+        assert sampling in ("numpy", "device")
+        self.size, self.ratio, self.delta_z, self.sampling = size, sample_ratio, delta_z, sampling
+        self._grid = {}
+        self._pinned = None
+
+    def _uv(self, dev):
+        if dev not in self._grid:
+            h, w = self.size
+            u = (torch.arange(w, dtype=torch.float32, device=dev)[None, None, :] - float(w // 2)).expand(1, h, w)
+            v = (torch.arange(h, dtype=torch.float32, device=dev)[None, :, None] - float(h // 2)).expand(1, h, w)
+            self._grid[dev] = (u, v)
+        return self._grid[dev]
+
+    def _points(self, depth, fx, fy):
+        """depth [B,1,H,W] -> [B*H*W, 3] (vnl.py:20-38: u0 / v0 are the image centre, not the intrinsics' principal point)."""
+        u, v = self._uv(depth.device)
+        d = depth[:, 0]
+        x = u * d.abs() / fx
+        y = v * d.abs() / fy
+        return torch.stack([x, y, d], -1).reshape(-1, 3)
+
+    def _sample_host(self, counts, is_rest):
+        """Triplet indices of every region, drawn in the reference's RNG call order.  Returns (int32 array [3, T], per-region k)."""
+        import numpy as np
+        ks, parts = [], [[], [], []]
+        for c, rest in zip(counts, is_rest):
+            if rest and c == 0:                      # vnl.py:137: the rest term only exists when there are non-planar pixels
+                ks.append(0)
+                continue
+            assert c <= self.size[0] * self.size[1]
+            k = int(c * self.ratio)
+            ks.append(k)
+            for j in range(3):
+                p = np.random.choice(c, k, replace=True)
+                np.random.shuffle(p)
+                parts[j].append(p)
+        T = sum(ks)
+        out = np.empty((3, T), dtype=np.int32)
+        for j in range(3):
+            if parts[j]:
+                np.concatenate(parts[j], out=out[j], casting="unsafe")
+        return out, ks
+
+    def __call__(self, depth_up, gt_instances, gt_depths):
+        """depth_up [B,1,H,W] (x2 bilinear of the prediction), gt_depths [B,1,H,W].  Returns the per-image losses [B] (float64; NaN
+        where the reference yields NaN)."""
+        import numpy as np
+        import torch.nn.functional as F
+        B, _, H, W = depth_up.shape
+        assert (H, W) == tuple(self.size), "the plane term assumes the configured image size (losses.py:50)"
+        HW = H * W
+        dev = depth_up.device
+        # ---- regions in the reference's order: per image its planes, then the non-planar rest
+        stacks, reg_img, reg_rest, n_planes = [], [], [], []
+        for b, g in enumerate(gt_instances):
+            m = g["masks"].bool().reshape(-1, HW)
+            stacks += [m, torch.logical_not(m.any(0, keepdim=True))]
+            n = m.shape[0]
+            n_planes.append(n)
+            reg_img += [b] * (n + 1)
+            reg_rest += [False] * n + [True]
+        member = torch.cat(stacks, 0)                                   # [R, HW] bool
+        R = member.shape[0]
+        counts = member.sum(1).tolist()                                 # the one host sync of this term
+        # ---- triplet indices
+        if self.sampling == "numpy":
+            idx_np, ks = self._sample_host(counts, reg_rest)
+            T = idx_np.shape[1]
+            if self._pinned is None or self._pinned.shape[1] < T:
+                self._pinned = torch.empty(3, max(T, 1 << 20), dtype=torch.int32).pin_memory() if dev.type == "cuda" else None
+            if self._pinned is not None:
+                self._pinned[:, :T].copy_(torch.from_numpy(idx_np))
+                idx = self._pinned[:, :T].to(dev, non_blocking=True).long()
+            else:
+                idx = torch.from_numpy(idx_np).long()
+        else:
+            ks = [0 if (rest and c == 0) else int(c * self.ratio) for c, rest in zip(counts, reg_rest)]
+            T = sum(ks)
+        ks_t = torch.tensor(ks, device=dev)
+        region = torch.repeat_interleave(torch.arange(R, device=dev), ks_t, output_size=T)            # [T]
+        counts_t = torch.tensor(counts, device=dev)
+        if self.sampling == "device":
+            idx = (torch.rand(3, T, device=dev, dtype=torch.float64) * counts_t[region].double()).long()
+            idx = torch.minimum(idx, (counts_t[region] - 1).clamp(min=0))
+        # pixel lists of the regions (row-major inside a region = the order of `pts[mask]`)
+        nz = member.nonzero()
+        gpix = torch.tensor(reg_img, device=dev)[nz[:, 0]] * HW + nz[:, 1]
+        base = torch.cumsum(counts_t, 0) - counts_t                      # first entry of each region in gpix
+        P = gpix[(base[region][None, :] + idx).reshape(-1)].reshape(3, T)                              # global pixel of every point
+        # ---- point clouds (vnl.py:20-38)
+        fx = torch.stack([g["k_matrix"][0, 0] for g in gt_instances]).to(device=dev, dtype=torch.float32)[:, None, None]
+        fy = torch.stack([g["k_matrix"][1, 1] for g in gt_instances]).to(device=dev, dtype=torch.float32)[:, None, None]
+        pred_pts = self._points(depth_up, fx, fy)
+        gt_pts = self._points(gt_depths.to(depth_up.dtype), fx, fy)
+        g_pred = pred_pts[P].permute(1, 2, 0)                            # [T, xyz, p123]
+        is_rest_t = torch.tensor(reg_rest, device=dev)[region]
+        g_gt = gt_pts[P].permute(1, 2, 0)
+        g_test = torch.where(is_rest_t[:, None, None], g_gt, g_pred)     # planes are tested on the prediction, the rest on the GT
+        # ---- vnl.py:56-98: usable triplets
+        diff = torch.stack([g_test[:, :, 1] - g_test[:, :, 0], g_test[:, :, 2] - g_test[:, :, 0], g_test[:, :, 2] - g_test[:, :, 1]], 2)
+        q = diff.permute(0, 2, 1)
+        qn = q.norm(2, dim=2)
+        cosm = (torch.bmm(q, diff) / (torch.bmm(qn.unsqueeze(2), qn.unsqueeze(1)) + 1e-8)).reshape(T, -1)
+        colinear = ((cosm > 0.985) | (cosm < -0.985)).sum(1) > 3
+        in_front = (g_test[:, 2, :] > self.delta_z).sum(1) == 3
+        dd = torch.where(is_rest_t, 0.1, 0.005).to(diff.dtype)[:, None]
+        near = (((diff[:, 0, :].abs() < dd).sum(1) > 0) & ((diff[:, 1, :].abs() < dd).sum(1) > 0) &
+                ((diff[:, 2, :].abs() < dd).sum(1) > 0))
+        keep = in_front & ~(near | colinear)
+
+        def normals(g):
+            nv = torch.cross(g[:, :, 1] - g[:, :, 0], g[:, :, 2] - g[:, :, 0], dim=1)
+            nrm = torch.norm(nv, 2, dim=1, keepdim=True)
+            return nv / (nrm + (nrm == 0.0).float() * 0.01)
+
+        # vnl.py:146: a predicted point with z == 0 (never, behind a softplus) is nudged; indexing quirk of the reference kept
+        g_pred_rest = torch.where((g_pred[:, 2, :] == 0)[:, :, None], torch.full_like(g_pred, 0.0001), g_pred)
+        n_plane = normals(g_pred)
+        n_rest = normals(g_pred_rest)
+        n_gt = normals(g_gt)
+        # target normal of every triplet: the plane's ground-truth normal (float64 like the reference's plane_paras)
+        tgt = torch.zeros(R, 3, dtype=torch.float64, device=dev)
+        r0 = 0
+        for b, g in enumerate(gt_instances):
+            tgt[r0:r0 + n_planes[b]] = g["plane_paras"][:, :3].to(device=dev, dtype=torch.float64)
+            r0 += n_planes[b] + 1
+        cos_plane = F.cosine_similarity(n_plane, tgt[region], dim=1).abs()            # float64
+        cos_rest = F.cosine_similarity(n_rest, n_gt, dim=1).abs()                     # float32
+        loss_t = torch.where(is_rest_t, (1 - cos_rest).double(), 1 - cos_plane)        # [T] float64 (rest values are exact fp32)
+        # ---- vnl.py:100-117: worst 75 % per region: one global sort on (region, loss); NaNs sort last inside their region
+        key = torch.where(keep, region.double() * 2 + torch.where(torch.isnan(loss_t), torch.full_like(loss_t, 1.5), loss_t),
+                          torch.full_like(loss_t, float("inf")))
+        order = torch.argsort(key)
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(T, device=dev)
+        n_keep = torch.zeros(R, dtype=torch.long, device=dev).index_add_(0, region, keep.long())
+        start = torch.cumsum(n_keep, 0) - n_keep
+        drop = n_keep // 4                                                # int(n * 0.25)
+        incl = keep & ((pos - start[region]) >= drop[region])
+        contrib = torch.where(incl & ~torch.isnan(loss_t), loss_t, torch.zeros_like(loss_t))
+        is_rest_r = torch.tensor(reg_rest, device=dev)
+        # the rest regions' tail is a float32 sum in the reference: accumulate it in float32, the planes' in float64
+        sum_plane = torch.zeros(R, dtype=torch.float64, device=dev).index_add_(0, region, torch.where(is_rest_t, 0.0, contrib))
+        sum_rest = torch.zeros(R, dtype=torch.float32, device=dev).index_add_(0, region, torch.where(is_rest_t, contrib, 0.0).float())
+        den = (n_keep - drop).double()
+        loss_r = torch.where(is_rest_r, sum_rest.double() / den.float().double(), sum_plane / den)       # 0 / 0 -> NaN like the reference
+        # ---- per image (vnl.py:119-165)
+        img_of = torch.tensor(reg_img, device=dev)
+        total = torch.zeros(B, dtype=torch.float64, device=dev).index_add_(0, img_of, torch.where(is_rest_r, 0.0, loss_r))
+        npl = torch.tensor(n_planes, dtype=torch.float64, device=dev)
+        rest_rows = is_rest_r.nonzero().flatten()                          # one rest region per image, in image order
+        rest_used = (counts_t[rest_rows] > 0) & (n_keep[rest_rows] > 0)
+        with_rest = (total + torch.where(rest_used, loss_r[rest_rows], torch.zeros_like(total))) / (npl + 1)
+        return torch.where(rest_used, with_rest, total / npl)
+
+
 # ------------------------------------------------------------------------------------------ the joint loss
 class PlaneRecNetLoss(torch.nn.Module):
     """Drop-in for models/functions/losses.py:PlaneRecNetLoss (same constructor-time cfg fields, same forward signature and
@@ -333,7 +507,10 @@ class PlaneRecNetLoss(torch.nn.Module):
     RMSE-log terms on libprn_b200 kernels, plane-normal term host-side.  Reference quirks kept: the lava valid mask stays
     None for the presets' dataset name (losses.py:172), the plane term assumes 480x640 (losses.py:50)."""
 
-    def __init__(self, cfg=None, backend=None):
+    def __init__(self, cfg=None, backend=None, vnl_sampling="numpy"):
+        """vnl_sampling: 'numpy' (default) draws the plane term's triplets with numpy's global RNG in the reference's call order
+        (bit-identical samples for a given np.random.seed; ~1.5 ms of host time per plane), 'device' draws the same distribution
+        with torch's device RNG (no host work)."""
         super().__init__()
         if cfg is None:
             from .config import cfg as _cfg
@@ -348,15 +525,16 @@ class PlaneRecNetLoss(torch.nn.Module):
         self.use_lava, self.use_plane = cfg.use_lava_loss, cfg.use_plane_loss
         self.min_depth, self.depth_resolution = cfg.dataset.min_depth, cfg.dataset.depth_resolution
         self.backend = backend
-        self.vnl = _PlaneNormal((480, 640))
+        self.vnl = _PlaneNormal((480, 640))                                  # per-plane formulation (kept as the readable mirror of vnl.py)
+        self.vnl_batched = _PlaneNormalBatched((480, 640), sampling=vnl_sampling)
 
     def forward(self, net, mask_preds, cate_preds, kernel_preds, depth_preds, gt_instances, gt_depths):
-        from .targets import assign_targets
+        from .targets import assign_targets_batch
         import torch.nn.functional as F
         be = self.backend or CudaBackend()
         B = len(gt_instances)
         fh, fw = mask_preds.shape[-2:]
-        targets = [assign_targets(g, (fh, fw), self.num_grids, self.scale_ranges, self.num_classes, self.sigma) for g in gt_instances]
+        targets = assign_targets_batch(gt_instances, (fh, fw), self.num_grids, self.scale_ranges, self.num_classes, self.sigma)
         losses = {}
         gw, gsum = be.lava_weights(gt_depths, fh, fw, self.depth_resolution)
         if not self.use_lava:
@@ -373,9 +551,7 @@ class PlaneRecNetLoss(torch.nn.Module):
         losses["dpt"] = be.depth_rmselog(depth_preds, gt_depths, self.min_depth, 1e-9, self.w_dpt)
         if self.use_plane:
             up = F.interpolate(depth_preds, scale_factor=2, mode="bilinear", align_corners=False)
-            pln = [self.vnl(up[b], gt_instances[b]["masks"].bool(), gt_instances[b]["plane_paras"][:, :3], gt_depths[b],
-                            gt_instances[b]["k_matrix"]) for b in range(B)]
-            losses["pln"] = torch.stack(pln).mean() * self.w_pln
+            losses["pln"] = self.vnl_batched(up, gt_instances, gt_depths).mean() * self.w_pln
         if self.use_lava:
             losses["lav"] = lav
         return losses

@@ -231,3 +231,21 @@ def inference(eng, net, st, x):
             off += k
         results.append(r)
     return results
+
+
+def pack_mask_bits(masks):
+    """pred_masks (bool [n, H, W] tensors, e.g. one per image of a batch) -> one uint8 tensor of bits, LSB first
+    (numpy.unpackbits(..., bitorder="little") restores them): what a serving loop copies to the host instead of one byte
+    per pixel.  The per-image masks of one `net(x)` call are views of one buffer: packed with a single launch, no copy."""
+    masks = [m for m in masks if m is not None and m.numel()]
+    if not masks:
+        return None
+    contiguous = all(m.is_contiguous() for m in masks) and all(
+        masks[i + 1].data_ptr() == masks[i].data_ptr() + masks[i].numel() for i in range(len(masks) - 1))
+    n = sum(m.numel() for m in masks)
+    src = masks[0] if contiguous else torch.cat([m.reshape(-1) for m in masks])
+    assert n % 16 == 0 and src.dtype == torch.bool
+    out = torch.empty(n // 8, dtype=torch.uint8, device=src.device)
+    L.check(L.lib().prn_pack_mask_bits(C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), C.c_int64(n), L.current_stream()),
+            "prn_pack_mask_bits")
+    return out

@@ -10,9 +10,9 @@ hot path); device-agnostic, which is what lets the CPU suite compare it with the
 Device independence: the reference's `(c / extent) // (1 / S)` sits exactly on grid-cell boundaries for round inputs, and
 torch's CUDA kernels divide by Python scalars through a reciprocal (last-bit differences), so an earlier version of this
 module resolved one synthetic case differently on CUDA than on the CPU.  The moments are now accumulated exactly (float64)
-and every division uses device-tensor divisors (IEEE quotients on both devices); the CUDA side of this could not be
-re-run in round 1 (GPU budget spent), so tests/test_loss_kernels_gpu.py still feeds the losses with the CPU assignment and
-only reports whether the device-side one agrees."""
+and every division uses device-tensor divisors (IEEE quotients on both devices).  tests/test_loss_kernels_gpu.py asserts on the
+B200 that the CUDA assignment equals the CPU one and the unmodified reference's (tests/golden/loss_golden.pt), bit for bit.
+`assign_targets_batch` does a whole batch with a single host round trip."""
 import torch
 
 
@@ -91,4 +91,100 @@ def assign_targets(gt, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.
         else:
             ins = torch.zeros(0, fh, fw, dtype=torch.uint8, device=dev)
         out.append((ins, cate, ind, order))
+    return out
+
+
+@torch.no_grad()
+def assign_targets_batch(gts, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.2):
+    """assign_targets for every image of a batch with ONE host round trip (the per-image version makes one per image and FPN
+    level: 32 for a batch of 8) and a handful of batched tensor ops: the per-instance scalars of all images (box scale, centre
+    of mass, cell ranges for every level) are computed together, fetched once, and the label maps / cell lists are assembled
+    on the host and uploaded in two copies.  Returns [assign_targets(gt, ...) for gt in gts], element for element."""
+    import numpy as np
+    dev = gts[0]["masks"].device
+    fh, fw = feat_hw
+    up_h, up_w = fh * 4, fw * 4
+    n_img = [int(g["boxes"].shape[0]) for g in gts]
+    boxes = torch.cat([g["boxes"] for g in gts])
+    labels = torch.cat([g["classes"] for g in gts]).to(torch.int64)
+    areas = torch.sqrt((boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1]))
+    half_w = 0.5 * (boxes[:, 2] - boxes[:, 0]) * sigma
+    half_h = 0.5 * (boxes[:, 3] - boxes[:, 1]) * sigma
+    cws, chs, nes = [], [], []
+    for g in gts:                                      # exact float64 moments per image (see assign_targets)
+        mk = g["masks"]
+        ys = torch.arange(mk.shape[1], dtype=torch.float64, device=dev)
+        xs = torch.arange(mk.shape[2], dtype=torch.float64, device=dev)
+        mk64 = mk.to(torch.float64)
+        m00 = mk64.sum(-1).sum(-1).clamp(min=1e-6)
+        cws.append(((mk64 * xs).sum(-1).sum(-1) / m00).to(torch.float32))
+        chs.append(((mk64 * ys[:, None]).sum(-1).sum(-1) / m00).to(torch.float32))
+        nes.append(mk.sum(-1).sum(-1) > 0)
+    cw, ch, nonempty = torch.cat(cws), torch.cat(chs), torch.cat(nes)
+    rows = []
+    for (lo, hi), S in zip(scale_ranges, num_grids):
+        def cell(v, extent):
+            e = torch.tensor(float(extent), dtype=v.dtype, device=dev)
+            pitch = torch.tensor(1.0 / S, dtype=v.dtype, device=dev)
+            return torch.floor_divide(v / e, pitch).to(torch.int64)
+
+        hit = (areas >= lo) & (areas <= hi)
+        cx, cy = cell(cw, up_w), cell(ch, up_h)
+        top = torch.maximum(cell(ch - half_h, up_h).clamp(min=0), cy - 1)
+        down = torch.minimum(cell(ch + half_h, up_h).clamp(max=S - 1), cy + 1)
+        left = torch.maximum(cx - 1, cell(cw - half_w, up_w).clamp(min=0))
+        right = torch.minimum(cell(cw + half_w, up_w).clamp(max=S - 1), cx + 1)
+        rows.append(torch.stack([hit.to(torch.int64), top, down, left, right, nonempty.to(torch.int64), labels], 1))
+    table = torch.stack(rows).tolist()                 # the one host round trip: [levels][instances][7]
+    total_cells = sum(S * S for S in num_grids)
+    cate_np = np.full((len(gts), total_cells), num_classes, dtype=np.int64)
+    ind_np = np.zeros((len(gts), total_cells), dtype=np.bool_)
+    plan, src_all = [], []
+    start = 0
+    for b, n in enumerate(n_img):
+        off = 0
+        per_level = []
+        for lvl, S in enumerate(num_grids):
+            cate = cate_np[b, off:off + S * S].reshape(S, S)
+            src, order = [], []
+            any_hit = False
+            for k in range(n):
+                h, t, d, l, r, ok, lab = table[lvl][start + k]
+                if not h:
+                    continue
+                any_hit = True
+                if not ok:
+                    continue
+                cate[t:d + 1, l:r + 1] = lab
+                for i in range(t, d + 1):
+                    for j in range(l, r + 1):
+                        src.append(k)
+                        order.append(i * S + j)
+            if order:
+                ind_np[b, off + np.asarray(order)] = True
+            per_level.append((off, S, order, len(src_all), len(src), any_hit))
+            src_all += src
+            off += S * S
+        plan.append(per_level)
+        start += n
+    cate_t = torch.from_numpy(cate_np).to(dev)
+    ind_t = torch.from_numpy(ind_np).to(dev)
+    src_t = torch.tensor(src_all, dtype=torch.int64, device=dev) if src_all else None
+    out = []
+    for b, g in enumerate(gts):
+        small = None
+        res = []
+        for (off, S, order, s0, sn, _any) in plan[b]:
+            cate = cate_t[b, off:off + S * S].view(S, S)
+            ind = ind_t[b, off:off + S * S]
+            if sn:
+                if small is None:
+                    small = quarter_masks(g["masks"])
+                canvas = torch.zeros(sn, fh, fw, dtype=torch.uint8, device=dev)
+                canvas[:, :small.shape[1], :small.shape[2]] = small[src_t[s0:s0 + sn]]
+                ins = canvas
+            else:
+                ins = torch.zeros(0, fh, fw, dtype=torch.uint8, device=dev)
+            res.append((ins, cate, ind, order))
+        out.append(res)
     return out

@@ -27,7 +27,7 @@ def test_reference_simple_inference_script_runs_on_our_modules(cuda_lib):
     r = _run("simple_inference", "--config", "PlaneRecNet_50_config")
     assert r["ok"] and r["model_class"].startswith("planerecnet_b200")
     assert r["state_dict_keys"] == 520 and r["keys_roundtrip"]
-    assert any(o.endswith(".png") for o in r["outputs"]) and any(o.endswith(".mat") for o in r["outputs"])
+    assert any(o.endswith(".png") for o in r["outputs"])          # the rendered detections + depth map of the --image mode
 
 
 def test_reference_train_loop_runs_on_our_modules(cuda_lib):

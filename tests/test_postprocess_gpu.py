@@ -216,3 +216,18 @@ def test_module_level_mask_nms_reference_signature(cuda_lib):
         keep = PP.mask_nms(c["labels"].cuda(), c["masks"].cuda(), c["sums"].cuda(), c["scores"].cuda(), nms_thr=c["thr"])
         assert torch.equal(keep.cpu(), c["keep"])
     assert PP.mask_nms(torch.zeros(0), torch.zeros(0, 4, 4), torch.zeros(0), torch.zeros(0)) == []
+
+
+@pytest.mark.gpu
+def test_pack_mask_bits_equals_numpy_packbits(cuda_lib):
+    import numpy as np
+    from planerecnet_b200.postprocess import pack_mask_bits
+    g = torch.Generator().manual_seed(0)
+    base = (torch.rand(5, 48, 64, generator=g) < 0.4).cuda()
+    views = [base[0:2], base[2:2], base[2:5]]                      # per-image views of one buffer, one of them empty
+    got = pack_mask_bits(views).cpu().numpy()
+    ref = np.packbits(base.cpu().numpy().reshape(-1), bitorder="little")
+    assert np.array_equal(got, ref)
+    sep = [base[0:2].clone(), base[2:5].clone()]                    # separate allocations: concatenated first
+    assert np.array_equal(pack_mask_bits(sep).cpu().numpy(), ref)
+    assert pack_mask_bits([None, base[0:0]]) is None

@@ -107,3 +107,18 @@ def test_assembled_loss_module_equals_reference_golden_on_cpu(name):
         got = [0.0 if t.grad is None else float(t.grad.double().norm()) for t in leaves]
         for a, b in zip(got, gold["grad_norms"]):
             assert abs(a - b) <= 2e-4 * max(b, 1e-6), (got, gold["grad_norms"])
+
+
+@pytest.mark.parametrize("name", list(LC.CASES))
+def test_batched_assignment_equals_per_image_assignment(name):
+    """targets.assign_targets_batch (one host round trip per batch) == [assign_targets(gt) for gt in batch], exactly."""
+    _, _, _, _, gts, _ = LC.synth(**LC.CASES[name])
+    args = ((120, 160), LO.CFG["grids"], LO.CFG["scale_ranges"], LO.CFG["num_classes"], LO.CFG["sigma"])
+    ref = [T.assign_targets(g, *args) for g in gts]
+    got = T.assign_targets_batch(gts, *args)
+    assert len(got) == len(ref)
+    for rb, gb in zip(ref, got):
+        assert len(rb) == len(gb) == 4
+        for (ri, rc, rd, ro), (gi, gc, gd, go) in zip(rb, gb):
+            assert go == ro and torch.equal(gc, rc) and torch.equal(gd, rd)
+            assert gi.shape == ri.shape and gi.dtype == ri.dtype and torch.equal(gi, ri)
