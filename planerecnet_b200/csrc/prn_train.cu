@@ -643,7 +643,70 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, T* __restrict__ o
   }
 }
 
+// ---- every packed operand of a training step in ONE launch (the per-conv kernels above cost ~250 launches per step once the
+//      optimizer has touched the weights).  recs[r] describes one operand; work[b] = {record, row} for block b.
+struct PackRec {
+  const float* w;
+  void* out;
+  int kind;            // 0 forward operand (pack_fwd_kernel), 1 input-gradient operand (pack_dgrad_kernel)
+  int cout, cin, kk;
+  int a, b, c, d, e, f, g;   // fwd: cpad_tot, nsplit, s0.lo, s0.real, s0.pad, s1.lo, s1.real (s1.pad = cpad_tot - s0.pad)
+                              // dgrad: lo, nreal, cout_pad
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const PackRec* __restrict__ recs, const int2* __restrict__ work) {
+  extern __shared__ float row[];
+  const int2 wk = work[blockIdx.x];
+  const PackRec r = recs[wk.x];
+  const int n = wk.y;
+  const int kk = r.kk;
+  if (r.kind == 0) {
+    const int cpad_tot = r.a, nsplit = r.b;
+    const PackSplit s0{r.c, r.d, r.e}, s1{r.f, r.g, cpad_tot - r.e};
+    T* o = static_cast<T*>(r.out) + static_cast<long long>(n) * kk * cpad_tot;
+    if (n >= r.cout) {
+      for (int i = threadIdx.x; i < kk * cpad_tot; i += blockDim.x) o[i] = static_cast<T>(0.f);
+      return;
+    }
+    const float* src = r.w + static_cast<long long>(n) * r.cin * kk;
+    for (int i = threadIdx.x; i < r.cin * kk; i += blockDim.x) row[i] = __ldg(src + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kk * cpad_tot; i += blockDim.x) {
+      const int tap = i / cpad_tot, c = i - tap * cpad_tot;
+      float v = 0.f;
+      if (c < s0.pad) {
+        if (c < s0.real) v = row[(s0.lo + c) * kk + tap];
+      } else if (nsplit > 1) {
+        const int c1 = c - s0.pad;
+        if (c1 < s1.real) v = row[(s1.lo + c1) * kk + tap];
+      }
+      o[i] = static_cast<T>(v);
+    }
+  } else {
+    const int lo = r.a, nreal = r.b, cout_pad = r.c;
+    T* o = static_cast<T*>(r.out) + static_cast<long long>(n) * kk * cout_pad;
+    for (int i = threadIdx.x; i < kk * cout_pad; i += blockDim.x) {
+      const int tap = i / cout_pad, oc = i - tap * cout_pad;
+      float v = 0.f;
+      if (n < nreal && oc < r.cout) v = __ldg(r.w + (static_cast<long long>(oc) * r.cin + lo + n) * kk + (kk - 1 - tap));
+      o[i] = static_cast<T>(v);
+    }
+  }
+}
+
 }  // namespace prn
+
+extern "C" int prn_pack_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, int32_t dtype,
+                              void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(recs_dev && work_dev && n_blocks > 0 && smem_bytes >= 0 && smem_bytes <= 48 * 1024, "pack_multi: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_DISPATCH(dtype,
+               (pack_multi_kernel<__nv_bfloat16><<<n_blocks, 256, smem_bytes, st>>>(static_cast<const PackRec*>(recs_dev), reinterpret_cast<const int2*>(work_dev))),
+               (pack_multi_kernel<__half><<<n_blocks, 256, smem_bytes, st>>>(static_cast<const PackRec*>(recs_dev), reinterpret_cast<const int2*>(work_dev))));
+  PRN_LAUNCH_CHECK();
+}
 
 extern "C" int prn_pack_conv_weight(const float* w, void* out16, int32_t cout, int32_t cin, int32_t ksize, int32_t n_pad,
                                     int32_t nsplit, const int32_t* lo, const int32_t* real, const int32_t* pad, int32_t dtype,

@@ -413,7 +413,7 @@ class _PlaneNormalBatched:
             idx_np, ks = self._sample_host(counts, reg_rest)
             T = idx_np.shape[1]
             if self._pinned is None or self._pinned.shape[1] < T:
-                self._pinned = torch.empty(3, max(T, 1 << 20), dtype=torch.int32).pin_memory() if dev.type == "cuda" else None
+                self._pinned = torch.empty(3, max(T, 1 << 20), dtype=torch.int32, device="cpu").pin_memory() if dev.type == "cuda" else None
             if self._pinned is not None:
                 self._pinned[:, :T].copy_(torch.from_numpy(idx_np))
                 idx = self._pinned[:, :T].to(dev, non_blocking=True).long()

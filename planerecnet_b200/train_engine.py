@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _lib as L
 from . import ops
-from .engine import Engine
+from .engine import Engine, _ver
 from .models.dcn import DeformableConv2d
 
 
@@ -49,6 +49,8 @@ class TrainEngine(Engine):
         self._arena_hi = 0
         self._graphs_t = {}
         self._nbt = []
+        self._marks, self._pf_done = [], 0
+        self._pack_recs, self._pack_tab = {}, None
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
@@ -107,30 +109,89 @@ class TrainEngine(Engine):
 
     # ------------------------------------------------------------------ packed parameters (no BatchNorm folding)
     def _pack_conv_train(self, conv, c_splits, n_pad=None):
+        key = (id(conv), "train", str(c_splits), n_pad)
+
         def build():
             w = conv.weight.detach()
             npad = n_pad or ops.round_up(w.shape[0], 16)
-            if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] * w.shape[2] * w.shape[3] * 4 <= 48 * 1024:
+            dev_ok = w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] * w.shape[2] * w.shape[3] * 4 <= 48 * 1024
+            if dev_ok:
                 wp = ops.pack_conv_weight_dev(w, c_splits, npad, self.dt)
                 self.launches += 1
             else:
                 wp = ops.pack_conv_weight(w.float(), c_splits, npad, self.dt).cuda()
             bp = ops.pad_vec(conv.bias.detach().float(), npad).cuda() if conv.bias is not None else None
+            self._pack_recs.pop(key, None)
+            if dev_ok and len(c_splits) <= 2 and (bp is None or conv.bias.is_cuda):
+                # remembered for repack_all(): every operand of the step re-packed by ONE launch (+ one multi-tensor copy for
+                # the padded bias vectors) instead of one launch per conv
+                lo1 = c_splits[0][0]
+                f = [sum(p for _, p in c_splits), len(c_splits), 0, c_splits[0][0], c_splits[0][1],
+                     lo1 if len(c_splits) > 1 else 0, c_splits[1][0] if len(c_splits) > 1 else 0]
+                self._pack_recs[key] = dict(kind=0, w=conv.weight, out=wp, rows=npad, cout=w.shape[0], cin=w.shape[1],
+                                            kk=w.shape[2] * w.shape[3], f=f, params=[conv.weight, conv.bias], val=(wp, bp),
+                                            vec=[(conv.bias, bp)] if bp is not None else [])
             return wp, bp
 
-        return self._pack((id(conv), "train", str(c_splits), n_pad), [conv.weight, conv.bias], build)
+        return self._pack(key, [conv.weight, conv.bias], build)
+
+    def repack_all(self, invalidate_others=True):
+        """Refresh every remembered packed operand from the current parameter values with one prn_pack_multi launch and one
+        multi-tensor copy, writing into the SAME buffers (captured graphs and cached descriptors stay valid), and mark the
+        cache entries current.  Entries that are not covered (a handful of small per-module packs) are dropped so that their
+        builders run again.  Returns False when nothing has been remembered yet (first step)."""
+        recs = self._pack_recs
+        if not recs:
+            return False
+        import struct
+        sig = tuple((r["w"].data_ptr(), r["out"].data_ptr()) for r in recs.values())
+        if self._pack_tab is None or self._pack_tab[0] != sig:
+            assert not torch.cuda.is_current_stream_capturing(), "call repack_all() once outside the capture (it uploads its tables)"
+            blob, work, smem = b"", [], 0
+            for i, r in enumerate(recs.values()):
+                blob += struct.pack("<QQ11i4x", r["w"].data_ptr(), r["out"].data_ptr(), r["kind"], r["cout"], r["cin"], r["kk"], *r["f"])
+                work += [(i, n) for n in range(r["rows"])]
+                if r["kind"] == 0:
+                    smem = max(smem, r["cin"] * r["kk"] * 4)
+            rec_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+            work_t = torch.tensor(work, dtype=torch.int32).cuda().contiguous()
+            self._pack_tab = (sig, rec_t, work_t, len(work), smem)
+        _, rec_t, work_t, nblk, smem = self._pack_tab
+        L.check(self.lib.prn_pack_multi(C.c_void_p(rec_t.data_ptr()), C.c_void_p(work_t.data_ptr()), nblk, smem, self.dt, self._st()),
+                "prn_pack_multi")
+        self.launches += 1
+        dst, src = [], []
+        for r in recs.values():
+            for param, buf in r["vec"]:
+                dst.append(buf[:param.numel()])
+                src.append(param.detach())
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if invalidate_others:
+            for k in [k for k in self._packed if k not in recs]:
+                del self._packed[k]
+        for k, r in recs.items():
+            self._packed[k] = (_ver(*r["params"]), r["val"])
+        return True
 
     def _pack_dgrad(self, conv, real_lo, real_hi, rows_pad, cout_pad):
         """Weights of the input-gradient contraction for input channels [real_lo, real_hi) padded to rows_pad rows;
         K = (ky, kx, cout padded to cout_pad), taps flipped."""
+        key = (id(conv), "dgrad", real_lo, real_hi, rows_pad, cout_pad)
+
         def build():
             w = conv.weight.detach()
+            self._pack_recs.pop(key, None)
             if w.is_cuda and w.dtype == torch.float32 and w.is_contiguous():
                 self.launches += 1
-                return ops.pack_dgrad_weight_dev(w, real_lo, real_hi, rows_pad, cout_pad, self.dt)
+                out = ops.pack_dgrad_weight_dev(w, real_lo, real_hi, rows_pad, cout_pad, self.dt)
+                self._pack_recs[key] = dict(kind=1, w=conv.weight, out=out, rows=rows_pad, cout=w.shape[0], cin=w.shape[1],
+                                            kk=w.shape[2] * w.shape[3], f=[real_lo, real_hi - real_lo, cout_pad, 0, 0, 0, 0],
+                                            params=[conv.weight], val=out, vec=[])
+                return out
             return ops.pack_dgrad_weight(w.float()[:, real_lo:real_hi], cout_pad=cout_pad, n_pad=rows_pad, dtype=self.dt).cuda()
 
-        return self._pack((id(conv), "dgrad", real_lo, real_hi, rows_pad, cout_pad), [conv.weight], build)
+        return self._pack(key, [conv.weight], build)
 
     # ------------------------------------------------------------------ convolution with tape
     def t_conv(self, x, conv, *, src1=None, c0=None, c_splits=None, stride=None, pad=None, pad_mode=L.PAD_ZERO, upsample=1,
@@ -616,10 +677,13 @@ class TrainEngine(Engine):
         self.tape.append(bwd)
         t = self.maxpool_t(self.t_bn(y, bb.bn1, True))
         outs = []
-        for layer in bb.layers:
+        for li, layer in enumerate(bb.layers):
+            if li == 2:
+                self._marks.append(len(self.tape))       # gradient bucket boundary: stem + layers 0-1 | layers 2-3
             for blk in layer:
                 t = self.bottleneck_t(t, blk)
             outs.append(t)
+        self._marks.append(len(self.tape))               # layers 2-3 | FPN + heads + decoder
         return outs
 
     def fpn_t(self, cs, fpn):
@@ -800,6 +864,7 @@ class TrainEngine(Engine):
         """Start of a step: drop the previous tape and clear the accumulator arena (one memset)."""
         self._nbt = []
         self.tape, self.grads, self.wbufs, self.pgrads, self.pfinal, self._keep = [], {}, {}, {}, [], []
+        self._marks, self._pf_done = [], 0
         if self._arena is None:
             self._arena = torch.zeros(self._ARENA_FLOATS, dtype=torch.float32, device="cuda")
             self._arena_hi = 0
@@ -844,11 +909,49 @@ class TrainEngine(Engine):
         for fn in reversed(self.tape):
             fn()
         self._join_wgrad()
-        for fn in self.pfinal:
+        for fn in self.pfinal[self._pf_done:]:
             fn()
         grads = self.pgrads
         self.tape, self.grads, self.wbufs, self.pfinal, self._keep = [], {}, {}, [], []
+        self._marks, self._pf_done = [], 0
         return grads
+
+    # Gradient buckets for the data-parallel all-reduce (reverse execution order, decoder / heads first, backbone
+    # last): the tape is cut where forward_train entered layers 2-3 and where it left the backbone.  A bucket's parameter
+    # gradients are final once its tape segment has been replayed, its side-stream weight gradients joined and its accumulators
+    # unpacked — `backward_segment` does exactly that, so the caller can start the bucket's all-reduce while the next segment runs.
+    N_BUCKETS = 3
+
+    def bucket_of_params(self, net):
+        """{id(param): bucket}: 0 = FPN + heads + depth decoder (first to finish), 1 = backbone layers 2-3, 2 = stem + layers 0-1."""
+        out = {}
+        for name, p in net.named_parameters():
+            if not name.startswith("backbone."):
+                out[id(p)] = 0
+            elif name.startswith("backbone.layers.2.") or name.startswith("backbone.layers.3."):
+                out[id(p)] = 1
+            else:
+                out[id(p)] = 2
+        return out
+
+    def backward_segment(self, b):
+        """Replay tape segment b (0, 1, 2 in this order), join the weight-gradient streams and unpack the accumulators that
+        exist so far.  After segment b the gradients of bucket b's parameters are final.  Returns self.pgrads (live dict)."""
+        assert len(self._marks) == 2, "forward_train did not record the bucket boundaries"
+        hi = [len(self.tape), self._marks[1], self._marks[0]][b]
+        lo = [self._marks[1], self._marks[0], 0][b]
+        for fn in reversed(self.tape[lo:hi]):
+            fn()
+        self._join_wgrad()
+        for fn in self.pfinal[self._pf_done:]:
+            fn()
+        self._pf_done = len(self.pfinal)
+        if b == self.N_BUCKETS - 1:
+            grads = self.pgrads
+            self.tape, self.grads, self.wbufs, self.pfinal, self._keep = [], {}, {}, [], []
+            self._marks, self._pf_done = [], 0
+            return grads
+        return self.pgrads
 
 
 @contextlib.contextmanager
@@ -870,9 +973,10 @@ class GraphedStep:
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
     optimizer's in-place parameter updates; parameters must keep their storage (true for torch optimizers)."""
 
-    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1):
+    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1, buckets=None):
         """optimizer: a planerecnet_b200.optim.FusedAdam over net's parameters -> `optimizer_step()` replays the update
-        from a third graph (after the gradient all-reduce when world > 1)."""
+        from a third graph (after the gradient all-reduce when world > 1).  buckets: capture the backward as one graph per
+        gradient bucket (default: only when world > 1; True on one GPU exercises the same path without the collective)."""
         self.eng, self.net = eng, net
         self.sx = torch.empty_like(x)
         self.sx.copy_(x)
@@ -888,47 +992,73 @@ class GraphedStep:
             outs = eng.forward_train(net, self.sx)
             eng.seed_output_grads(torch.zeros_like(outs[0]), [torch.zeros_like(c) for c in outs[1]],
                                   [torch.zeros_like(k) for k in outs[2]], torch.zeros_like(outs[3]))
-            eng.backward()
+            warm_ids = set(eng.backward().keys())
             with torch.no_grad():
                 for b, sv in zip(bn_bufs, bn_saved):
                     b.copy_(sv)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if pack_in_graph:
+            eng.repack_all(invalidate_others=False)      # uploads the pack tables (not allowed inside a capture); same values
+            torch.cuda.synchronize()
         self.g_fwd = torch.cuda.CUDAGraph()
         n0 = eng.launches
         with _no_gc(), torch.cuda.graph(self.g_fwd):
-            if pack_in_graph:
+            if pack_in_graph and not eng.repack_all():
                 eng._packed.clear()
             self.outs = eng.forward_train(net, self.sx)
         self.fwd_launches = eng.launches - n0
         m, cs, ks, d = self.outs
         self.cots = (torch.zeros_like(m), [torch.zeros_like(c) for c in cs], [torch.zeros_like(k) for k in ks], torch.zeros_like(d))
-        self.g_bwd = torch.cuda.CUDAGraph()
-        n0 = eng.launches
-        with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
-            eng.seed_output_grads(*self.cots)
-            self.grads = eng.backward()
-        self.bwd_launches = eng.launches - n0
         self.optimizer, self.world = optimizer, world
         self.g_opt = self.g_flat = None
         self.flat = None
         self._reduced = False
-        params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
-        src = self.grads
-        if world > 1:
-            # one persistent flat fp32 buffer for the NCCL all-reduce; the optimizer reads the averaged views
+        self.g_bwd_seg = None
+        if not (world > 1 if buckets is None else buckets):
+            self.g_bwd = torch.cuda.CUDAGraph()
+            n0 = eng.launches
+            with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+                eng.seed_output_grads(*self.cots)
+                self.grads = eng.backward()
+            self.bwd_launches = eng.launches - n0
+            params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
+            src = self.grads
+        else:
+            # Data parallel: the backward is captured as N_BUCKETS graphs cut where a gradient bucket becomes final
+            # (FPN + heads + decoder | backbone layers 2-3 | stem + layers 0-1).  Each graph ends with the multi-tensor copy of
+            # its bucket into a contiguous slice of ONE persistent flat fp32 buffer; `backward` replays the graphs and, after
+            # each, starts that slice's NCCL all-reduce on a communication stream, so only the last (smallest) bucket's
+            # all-reduce is exposed — the others hide under the remaining backward.
+            bucket = eng.bucket_of_params(net)
+            params = [p for p in net.parameters() if p.requires_grad and id(p) in warm_ids]
+            params.sort(key=lambda p: bucket[id(p)])                      # stable: bucket-major, module order inside
             self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
-            views, off = {}, 0
-            for p in params:
-                views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
-                off += p.numel()
+            views, off, self.bucket_slices = {}, 0, []
+            for b in range(eng.N_BUCKETS):
+                lo = off
+                for p in params:
+                    if bucket[id(p)] == b:
+                        views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+                        off += p.numel()
+                self.bucket_slices.append((lo, off))
             self.flat_views = views
-            self.g_flat = torch.cuda.CUDAGraph()
-            dst = [views[id(p)] for p in params]
-            srcs = [self.grads[id(p)].reshape(p.shape) for p in params]
-            torch.cuda.synchronize()
-            with _no_gc(), torch.cuda.graph(self.g_flat, pool=self.g_fwd.pool()):
-                torch._foreach_copy_(dst, srcs)
+            self.g_bwd_seg = [torch.cuda.CUDAGraph() for _ in range(eng.N_BUCKETS)]
+            n0 = eng.launches
+            for b in range(eng.N_BUCKETS):
+                torch.cuda.synchronize()
+                with _no_gc(), torch.cuda.graph(self.g_bwd_seg[b], pool=self.g_fwd.pool()):
+                    if b == 0:
+                        eng.seed_output_grads(*self.cots)
+                    pg = eng.backward_segment(b)
+                    mine = [p for p in params if bucket[id(p)] == b]
+                    missing = [p for p in mine if id(p) not in pg]
+                    assert not missing, f"bucket {b}: {len(missing)} parameter gradients are not final after their tape segment"
+                    torch._foreach_copy_([views[id(p)] for p in mine], [pg[id(p)].reshape(p.shape) for p in mine])
+                    if b == eng.N_BUCKETS - 1:
+                        self.grads = pg
+            self.bwd_launches = eng.launches - n0
+            self.comm = torch.cuda.Stream()
             src = views
         if optimizer is not None:
             optimizer.prepare(src)
@@ -940,18 +1070,21 @@ class GraphedStep:
             # parameters are untouched; optimizer state starts at step 0
 
     def allreduce_grads(self):
-        """Average the gradients of the last backward over the ranks: ONE NCCL all-reduce (ReduceOp.AVG) over the persistent
-        flat fp32 buffer (gathered by one captured multi-tensor copy).  Returns {id(param): averaged view}."""
-        if self.g_flat is None:
+        """Gradients of the last backward averaged over the ranks.  With world > 1 the per-bucket NCCL all-reduces (ReduceOp.AVG
+        over slices of the persistent flat fp32 buffer) were started by `backward` as each bucket became final: this only makes
+        the caller's stream wait for the communication stream.  Returns {id(param): averaged view}."""
+        if self.g_bwd_seg is None:
             return self.grads
-        import torch.distributed as dist
-        self.g_flat.replay()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+        torch.cuda.current_stream().wait_stream(self.comm)
         self._reduced = True
         return self.flat_views
 
     def allreduce_desc(self):
-        return f"nccl, 1 all-reduce (avg) of the flat fp32 gradient buffer ({self.flat.numel() * 4 / 2 ** 20:.0f} MiB) per step" if self.flat is not None else None
+        if self.flat is None:
+            return None
+        mb = [f"{(hi - lo) * 4 / 2 ** 20:.0f}" for lo, hi in self.bucket_slices]
+        return (f"nccl all-reduce (avg) of one flat fp32 gradient buffer in {len(mb)} buckets ({' + '.join(mb)} MiB) in reverse execution "
+                f"order on a communication stream, each started as its bucket's backward segment completes")
 
     def optimizer_step(self):
         """(all-reduce the gradients of the last backward over the ranks and) apply the optimizer, from graphs."""
@@ -984,9 +1117,23 @@ class GraphedStep:
         for dst, src in zip(self.cots[2], d_kerns):
             put(dst, src)
         put(self.cots[3], d_depth)
-        self.g_bwd.replay()
         self.eng.launches += self.bwd_launches
         self._reduced = False
+        if self.g_bwd_seg is None:
+            self.g_bwd.replay()
+            return self.grads
+        import torch.distributed as dist
+        main = torch.cuda.current_stream()
+        self.comm.wait_stream(main)          # the previous step's consumers of `flat` (optimizer) are done before it is rewritten
+        for b, g in enumerate(self.g_bwd_seg):
+            g.replay()
+            lo, hi = self.bucket_slices[b]
+            if hi > lo and self.world > 1 and dist.is_initialized():
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
         return self.grads
 
 

@@ -245,3 +245,70 @@ def test_f16_training_with_loss_scaling(cuda_lib):
     net.set_train_precision("f16", grad_scale=2.0 ** 20)
     g_small = grads(1e-6)                   # a 1e-6-scaled loss: unscaled f16 gradients would underflow
     assert rel_l2(g_small, g_ref * 1e-6) < 5e-3, rel_l2(g_small, g_ref * 1e-6)
+
+
+@pytest.mark.gpu
+def test_bucketed_backward_graphs_equal_the_single_graph(cuda_lib):
+    """GraphedStep(buckets=True) — the data-parallel form: backward captured as three graphs cut where a gradient bucket becomes
+    final, each ending with the copy of its bucket into the flat all-reduce buffer — gives the single-graph gradients (frozen
+    BatchNorm statistics: stable network), every parameter lands in exactly one bucket slice, and the flat views hold them."""
+    from helpers import rel_l2
+    from planerecnet_b200.train_engine import GraphedStep
+    from planerecnet_b200.utils.synth import make_cotangents
+    net = TC._build("PlaneRecNet_50_config", cond=True).train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.eval()
+    net = net.cuda()
+    x = torch.randn(2, 3, 128, 160, generator=torch.Generator().manual_seed(5)).cuda()
+    eng = net.train_engine
+    one = GraphedStep(eng, net, x)
+    cots = make_cotangents(one.outs, seed=3, device="cuda")
+    one.forward(x)
+    g1 = {k: v.clone() for k, v in one.backward(*cots).items()}
+    seg = GraphedStep(eng, net, x, buckets=True)
+    seg.forward(x)
+    seg.backward(*cots)
+    views = seg.allreduce_grads()
+    torch.cuda.synchronize()
+    params = [p for p in net.parameters() if p.requires_grad and id(p) in g1]
+    assert set(views.keys()) == {id(p) for p in params}
+    assert sum(hi - lo for lo, hi in seg.bucket_slices) == seg.flat.numel() == sum(p.numel() for p in params)
+    assert all(hi > lo for lo, hi in seg.bucket_slices)
+    a = torch.cat([views[id(p)].flatten() for p in params])
+    b = torch.cat([g1[id(p)].flatten().float() for p in params])
+    assert bool(torch.isfinite(a).all())
+    assert rel_l2(a, b) < 2e-2, rel_l2(a, b)
+
+
+@pytest.mark.gpu
+def test_repack_all_equals_the_per_conv_pack_kernels(cuda_lib):
+    """TrainEngine.repack_all (one prn_pack_multi launch + one multi-tensor copy for every operand of the step) rewrites the
+    remembered buffers with exactly what the per-conv pack kernels produce for the CURRENT weights."""
+    from planerecnet_b200 import ops
+    net = TC._build("PlaneRecNet_50_config").train().cuda()
+    eng = net.train_engine
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    outs = eng.forward_train(net, x)
+    eng.seed_output_grads(torch.ones_like(outs[0]), [torch.ones_like(c) for c in outs[1]], [torch.ones_like(k) for k in outs[2]],
+                          torch.ones_like(outs[3]))
+    eng.backward()
+    recs = eng._pack_recs
+    assert len(recs) > 100 and {r["kind"] for r in recs.values()} == {0, 1}
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.25).add_(0.01)
+    assert eng.repack_all(invalidate_others=False)
+    torch.cuda.synchronize()
+    for key, r in recs.items():
+        w = r["w"].detach()
+        if r["kind"] == 0:
+            f = r["f"]
+            splits = [(f[3], f[4])] + ([(f[6], f[0] - f[4])] if f[1] == 2 else [])
+            ref = ops.pack_conv_weight_dev(w, splits, r["rows"], eng.dt)
+            for param, buf in r["vec"]:
+                assert torch.equal(buf[:param.numel()], param.detach().float()) and float(buf[param.numel():].abs().sum()) == 0.0
+        else:
+            lo, n, cout_pad = r["f"][0], r["f"][1], r["f"][2]
+            ref = ops.pack_dgrad_weight_dev(w, lo, lo + n, r["rows"], cout_pad, eng.dt)
+        assert torch.equal(r["out"].view(torch.int16), ref.view(torch.int16)), key
