@@ -468,14 +468,19 @@ def main():
             tot_f = sum(v[0] for v in by.values())
             tot_ms = sum(v[1] for v in by.values())
             ach = tot_f / (tot_ms / 1e3) / 1e12
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r02_traffic.json")      # dram bytes per launch from the committed ncu capture
+            traffic, traffic_detail = None, None
+            tp = os.path.join(ROOT, "profiles", "r02_traffic.json")      # dram bytes per launch from the committed ncu captures
             if os.path.exists(tp):
                 with open(tp) as fh:
-                    traffic = json.load(fh)
+                    traffic_detail = json.load(fh)
+                top = traffic_detail["per_launch"].get("fpn0_3x3_256")    # the largest conv launch of the step (181 GFLOP)
+                if top:
+                    traffic = top["dram_bytes_read"] + top["dram_bytes_write"]
             roof = {"bound": "tensor", "kernel": "conv_tma_kernel + conv_umma_kernel (every conv-like contraction of the eval forward)",
                     "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
-                    "traffic": traffic, "peak_source": f"{how} bf16_tflops_sustained",
+                    "traffic": traffic, "traffic_what": "dram__bytes_read.sum + dram__bytes_write.sum of the largest conv launch (3x3 256->256 at "
+                    "120x160, bs 8: 158.5 MB algorithmic in + out) from profiles/r02_ncu_full_summary.txt; other layers in traffic_detail",
+                    "traffic_detail": traffic_detail, "peak_source": f"{how} bf16_tflops_sustained",
                     "launches_per_step": sum(v[2] for v in by.values()), "kernel_ms_per_step": round(tot_ms, 3),
                     "algorithmic_gflop_per_step": round(tot_f / 1e9, 1),
                     "graph_step_frac": round(tot_f / (i_ms / a.steps / 1e3) / 1e12 / peak, 4),

@@ -17,6 +17,7 @@
 // call sites listed in include/prn_b200.h (models/backbone.py:56-66, models/fpn.py:55,61, planerecnet.py:386-391,
 // 478-495, 593-605).
 #include <stdio.h>
+#include <stdlib.h>
 #include "prn_internal.h"
 #include "prn_ptx.cuh"
 
@@ -45,6 +46,7 @@ struct WgradKParams {
   int stages;
   uint32_t idesc_base;   // formats + majors + M; N is added per tile
   uint32_t lbo, sbo;     // descriptor byte offsets of the MN-major operand tiles
+  int b_tma;             // 1: 1x1 / stride 1 / single source: the B operand is plain pixel rows -> TMA boxes, no LSU gather
 };
 
 __device__ __forceinline__ void wg_divmod(int m, int dv, float inv, int& q, int& r) {
@@ -68,7 +70,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
 
 template <typename T>
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ WgradKParams p) {
+wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                  const __grid_constant__ WgradKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
@@ -98,8 +101,9 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmap_dy);
+    if (p.b_tma) tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 128 + 1);
+      mbar_init(bar_full + 8 * s, p.b_tma ? 2 : 128 + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
@@ -115,6 +119,23 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 136);
 
   if (warp < 4) {
+   if (p.b_tma) {
+    // =========================================================== B producer, 1x1 convs: one TMA box {64 ch, 64 pixels} per atom
+    if (threadIdx.x == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        mbar_arrive_expect_tx(bar_full + 8 * s, static_cast<uint32_t>(na) * kWgAtomBytes);
+        const uint32_t b_stage = b_base + static_cast<uint32_t>(s) * b_stage_bytes;
+        for (int j = 0; j < na; ++j)
+          tma_load_2d(b_stage + static_cast<uint32_t>(j) * kWgAtomBytes, &tmap_x, bar_full + 8 * s, (nt * kWgMaxAtoms + j) * 64,
+                      kb * kWgKBlock);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+   } else {
     // =========================================================== B producer: im2col gather of 64 pixels x na atoms
     const int tid = threadIdx.x;
     const int chunk = tid & 7;          // 16-byte chunk (8 channels) of the 128-byte row
@@ -179,6 +200,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       cp_async_mbar_arrive_noinc(bar_full + 8 * s);
       if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
+   }
 
     // =========================================================== drain: TMEM -> fp32 reductions into dW
     mbar_wait(bar_tfull, 0);
@@ -305,11 +327,14 @@ static int wgrad_plan(const PrnWgrad& d, WgradKParams* p) {
   p->idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
   p->lbo = (d.flags & 1) ? 1024u : static_cast<uint32_t>(kWgAtomBytes);
   p->sbo = (d.flags & 1) ? static_cast<uint32_t>(kWgAtomBytes) : 1024u;
+  static const bool tma_off = [] { const char* e = getenv("PRN_WGRAD_TMA"); return e != nullptr && e[0] == '0'; }();
+  p->b_tma = (!tma_off && d.ksize == 1 && d.stride == 1 && d.upsample == 1 && d.pad == 0 && d.c1 == 0 &&
+              (reinterpret_cast<uintptr_t>(d.src0) & 15) == 0 && p->ld0 % 8 == 0) ? 1 : 0;
   return PRN_OK;
 }
 
 template <typename T>
-static int wgrad_launch_t(const CUtensorMap& tm, const WgradKParams& p, cudaStream_t st) {
+static int wgrad_launch_t(const CUtensorMap& tm, const CUtensorMap& tmx, const WgradKParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     PRN_CUDA(cudaFuncSetAttribute(wgrad_umma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBudget));
@@ -317,7 +342,7 @@ static int wgrad_launch_t(const CUtensorMap& tm, const WgradKParams& p, cudaStre
   }
   const size_t smem = 2048 + static_cast<size_t>(p.stages) * (p.m_sub * 2 * kWgAtomBytes + kWgMaxAtoms * kWgAtomBytes);
   const int grid = p.m_tiles * p.n_tiles * p.splits;
-  wgrad_umma_kernel<T><<<grid, kWgThreads, smem, st>>>(tm, p);
+  wgrad_umma_kernel<T><<<grid, kWgThreads, smem, st>>>(tm, tmx, p);
   PRN_CUDA(cudaGetLastError());
   return PRN_OK;
 }
@@ -344,7 +369,13 @@ extern "C" int prn_conv2d_wgrad(const PrnWgrad* desc, void* stream) {
   rc = encode_tmap_2d_sw128(&tm, desc->dy, static_cast<uint64_t>(p.m_rows), static_cast<uint64_t>(desc->n), kWgKBlock,
                             desc->dtype, static_cast<uint64_t>(desc->ld_dy));
   if (rc != PRN_OK) return rc;
+  CUtensorMap tmx = tm;
+  if (p.b_tma) {
+    rc = encode_tmap_2d_sw128(&tmx, desc->src0, static_cast<uint64_t>(p.m_rows), static_cast<uint64_t>(desc->c0), kWgKBlock,
+                              desc->dtype, static_cast<uint64_t>(p.ld0));
+    if (rc != PRN_OK) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (desc->dtype == PRN_BF16) return wgrad_launch_t<__nv_bfloat16>(tm, p, st);
-  return wgrad_launch_t<__half>(tm, p, st);
+  if (desc->dtype == PRN_BF16) return wgrad_launch_t<__nv_bfloat16>(tm, tmx, p, st);
+  return wgrad_launch_t<__half>(tm, tmx, p, st);
 }

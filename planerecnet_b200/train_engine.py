@@ -973,10 +973,24 @@ class GraphedStep:
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
     optimizer's in-place parameter updates; parameters must keep their storage (true for torch optimizers)."""
 
-    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1, buckets=None):
+    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1, buckets=None, dp_mode=None):
         """optimizer: a planerecnet_b200.optim.FusedAdam over net's parameters -> `optimizer_step()` replays the update
         from a third graph (after the gradient all-reduce when world > 1).  buckets: capture the backward as one graph per
-        gradient bucket (default: only when world > 1; True on one GPU exercises the same path without the collective)."""
+        gradient bucket (default: only when world > 1; True on one GPU exercises the same path without the collective).
+        dp_mode (world > 1; default from PRN_DP_MODE, else 'after'):
+          'after'        ONE backward graph that ends with the multi-tensor copy of all gradients into the persistent flat fp32
+                         buffer, then one NCCL all-reduce (avg) over it (SURVEY §8e: exactly one all-reduce per step);
+          'p2p'          backward in three bucket graphs, per-bucket mean all-reduce through peer memory with the copy engines
+                         (utils.dist.PeerAllReduce) on a communication stream, started as each bucket's graph has been enqueued;
+          'nccl_overlap' the same schedule with NCCL all-reduces.
+        Measured at N = 2 (R101 bs 8, tools/dp_check.py, profiles/r02_dp_check_2gpu.txt): cutting the backward into bucket graphs
+        costs more than the overlap wins — every graph boundary joins the side-stream weight gradients, which lag the main chain —
+        so 'after' is the default."""
+        import os
+        self.dp_mode = dp_mode or os.environ.get("PRN_DP_MODE", "after")
+        assert self.dp_mode in ("p2p", "nccl_overlap", "after")
+        if buckets is None:
+            buckets = world > 1 and self.dp_mode != "after"
         self.eng, self.net = eng, net
         self.sx = torch.empty_like(x)
         self.sx.copy_(x)
@@ -1015,15 +1029,25 @@ class GraphedStep:
         self.flat = None
         self._reduced = False
         self.g_bwd_seg = None
-        if not (world > 1 if buckets is None else buckets):
+        if not buckets:
+            params = [p for p in net.parameters() if p.requires_grad and id(p) in warm_ids]
+            if world > 1:
+                self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
+                views, off = {}, 0
+                for p in params:
+                    views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
+                    off += p.numel()
+                self.flat_views, self.bucket_slices = views, [(0, off)]
             self.g_bwd = torch.cuda.CUDAGraph()
             n0 = eng.launches
             with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
                 eng.seed_output_grads(*self.cots)
                 self.grads = eng.backward()
+                if world > 1:
+                    torch._foreach_copy_([views[id(p)] for p in params], [self.grads[id(p)].reshape(p.shape) for p in params])
             self.bwd_launches = eng.launches - n0
-            params = [p for p in net.parameters() if p.requires_grad and id(p) in self.grads]
-            src = self.grads
+            params = [p for p in params if id(p) in self.grads]
+            src = views if world > 1 else self.grads
         else:
             # Data parallel: the backward is captured as N_BUCKETS graphs cut where a gradient bucket becomes final
             # (FPN + heads + decoder | backbone layers 2-3 | stem + layers 0-1).  Each graph ends with the multi-tensor copy of
@@ -1059,6 +1083,11 @@ class GraphedStep:
                         self.grads = pg
             self.bwd_launches = eng.launches - n0
             self.comm = torch.cuda.Stream()
+            self.peer = None
+            if world > 1 and self.dp_mode == "p2p":
+                from .utils.dist import PeerAllReduce
+                torch.cuda.synchronize()
+                self.peer = PeerAllReduce(self.flat, self.bucket_slices)
             src = views
         if optimizer is not None:
             optimizer.prepare(src)
@@ -1074,7 +1103,8 @@ class GraphedStep:
         over slices of the persistent flat fp32 buffer) were started by `backward` as each bucket became final: this only makes
         the caller's stream wait for the communication stream.  Returns {id(param): averaged view}."""
         if self.g_bwd_seg is None:
-            return self.grads
+            self._reduced = self.flat is not None
+            return self.flat_views if self.flat is not None else self.grads
         torch.cuda.current_stream().wait_stream(self.comm)
         self._reduced = True
         return self.flat_views
@@ -1083,13 +1113,16 @@ class GraphedStep:
         if self.flat is None:
             return None
         mb = [f"{(hi - lo) * 4 / 2 ** 20:.0f}" for lo, hi in self.bucket_slices]
-        return (f"nccl all-reduce (avg) of one flat fp32 gradient buffer in {len(mb)} buckets ({' + '.join(mb)} MiB) in reverse execution "
-                f"order on a communication stream, each started as its bucket's backward segment completes")
+        how = {"p2p": "mean all-reduce through peer memory: copy-engine pulls over NVLink (reduce-scatter + all-gather), one small sum "
+                      "kernel and 4-byte NCCL all-reduces as inter-rank barriers",
+               "nccl_overlap": "NCCL all-reduce (avg)", "after": "ONE NCCL all-reduce (avg) over the whole buffer after the backward"}[self.dp_mode]
+        return (f"{how}; one persistent flat fp32 gradient buffer in {len(mb)} buckets ({' + '.join(mb)} MiB, reverse execution order)"
+                + ("" if self.dp_mode == "after" else ", each bucket started on a communication stream as its backward graph has been enqueued"))
 
     def optimizer_step(self):
         """(all-reduce the gradients of the last backward over the ranks and) apply the optimizer, from graphs."""
-        if self.g_flat is not None and not self._reduced:
-            self.allreduce_grads()
+        if self.g_bwd_seg is not None and not self._reduced:
+            self.allreduce_grads()          # bucket modes: make this stream wait for the communication stream
         self._reduced = False
         self.g_opt.replay()
         for p in self.net.parameters():
@@ -1121,19 +1154,34 @@ class GraphedStep:
         self._reduced = False
         if self.g_bwd_seg is None:
             self.g_bwd.replay()
+            if self.world > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
             return self.grads
         import torch.distributed as dist
         main = torch.cuda.current_stream()
+        live = self.world > 1 and dist.is_initialized()
         self.comm.wait_stream(main)          # the previous step's consumers of `flat` (optimizer) are done before it is rewritten
         for b, g in enumerate(self.g_bwd_seg):
             g.replay()
             lo, hi = self.bucket_slices[b]
-            if hi > lo and self.world > 1 and dist.is_initialized():
-                ev = torch.cuda.Event()
-                ev.record(main)
-                self.comm.wait_event(ev)
-                with torch.cuda.stream(self.comm):
+            if not live or self.dp_mode == "after":
+                continue
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.comm.wait_event(ev)
+            with torch.cuda.stream(self.comm):
+                if self.peer is not None:
+                    self.peer.reduce(b)
+                elif hi > lo:
                     dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
+        if live:
+            if self.dp_mode == "after":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)          # main stream: nothing left to overlap with
+            elif self.peer is not None:
+                with torch.cuda.stream(self.comm):
+                    self.peer.finish()
         return self.grads
 
 

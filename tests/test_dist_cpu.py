@@ -57,3 +57,16 @@ def test_single_process_identities():
     assert D.shard_range(8, 0, 1) == (0, 8)
     assert D.max_over_ranks(3.5) == 3.5 and D.sum_over_ranks(2.0) == 2.0
     assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_peer_chunks_partition_every_slice():
+    """utils.dist.peer_chunks (the reduce-scatter layout of PeerAllReduce): consecutive, disjoint, covering, 16-byte aligned starts."""
+    from planerecnet_b200.utils.dist import peer_chunks
+    for lo, hi in ((0, 14_000_003), (4096, 4096 + 7), (100, 100), (8, 1_500_000)):
+        for world in (2, 4, 8):
+            ch = peer_chunks(lo, hi, world)
+            assert len(ch) == world and ch[0][0] == lo and ch[-1][1] == hi
+            for (a0, a1), (b0, b1) in zip(ch, ch[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all((a0 - lo) % 4 == 0 for a0, a1 in ch if a1 > a0)
+            assert sum(a1 - a0 for a0, a1 in ch) == hi - lo

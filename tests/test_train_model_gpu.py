@@ -288,7 +288,7 @@ def test_repack_all_equals_the_per_conv_pack_kernels(cuda_lib):
     from planerecnet_b200 import ops
     net = TC._build("PlaneRecNet_50_config").train().cuda()
     eng = net.train_engine
-    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    x = torch.randn(1, 3, 128, 160, generator=torch.Generator().manual_seed(2)).cuda()
     outs = eng.forward_train(net, x)
     eng.seed_output_grads(torch.ones_like(outs[0]), [torch.ones_like(c) for c in outs[1]], [torch.ones_like(k) for k in outs[2]],
                           torch.ones_like(outs[3]))
