@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# more hardware work queues than the default 8: the step uses ~10 streams (side-stream weight gradients, decoder / head branches,
+# copy / forward / bookkeeping streams of the serving loop); streams that alias onto one queue serialise falsely
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "images/sec 480x640 ResNet101-DCN fwd+bwd"
 H_IMG, W_IMG = 480, 640

@@ -1,0 +1,8 @@
+
+import os as _os
+
+# The executors use ~10 CUDA streams (side-stream weight gradients, decoder / head branches, copy / forward / bookkeeping
+# streams of the serving loop).  With the driver's default of 8 hardware work queues, streams alias onto one queue and serialise
+# falsely (measured: serving loop 487 -> 1277 images/s, training step 31.4 -> 30.8 ms with 32 queues).  Only effective when set
+# before the CUDA context is created, i.e. when this package is imported before the first CUDA call.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")

@@ -128,7 +128,7 @@ class PlaneRecNet(nn.Module):
         B, Hi, Wi, _ = frames.shape
         Hp, Wp = (Hi + 31) // 32 * 32, (Wi + 31) // 32 * 32
         st = (self.engine.forward_dense_graph if self.use_cuda_graph else self.engine.forward_dense)(self, frames, False, frames=True)
-        shape_only = torch.empty(0, device=frames.device).expand(B, 3, Hp, Wp)      # the bookkeeping only reads the input size
+        shape_only = torch.empty(1, device=frames.device).expand(B, 3, Hp, Wp)      # the bookkeeping only reads the input size
         return self.engine.inference(self, st, shape_only)
 
     def infer_pipelined(self, batches, depth=3):

@@ -41,6 +41,18 @@ with torch.no_grad():
                 if r[k] is not None:
                     r[k].cpu()
     t_d2h, _ = timed(d2h)
+    from planerecnet_b200.postprocess import pack_mask_bits
+    t_pack, packed = timed(lambda: pack_mask_bits([r["pred_masks"] for r in res]))
+    t_pack_d2h, _ = timed(lambda: packed.cpu())
+    print(f"pack masks {t_pack:.3f} ms ({packed.numel()} bytes) | packed d2h (pageable) {t_pack_d2h:.3f} ms")
+    it = net.infer_pipelined(x_host for _ in range(12))
+    t0 = None
+    for i, r_ in enumerate(it):
+        torch.cuda.synchronize()
+        if i == 3:
+            t0 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"infer_pipelined, results consumed with a full sync each: {(time.perf_counter() - t0) / 8 * 1e3:.2f} ms per batch")
     t_all, _ = timed(lambda: net(x_host.cuda(non_blocking=True)))
 print(f"h2d {t_h2d:.2f} ms | dense graph {t_fwd:.2f} ms | bookkeeping {t_post:.2f} ms | d2h {t_d2h:.2f} ms | net(x) {t_all:.2f} ms")
 print("detections per image:", [0 if r["pred_scores"] is None else len(r["pred_scores"]) for r in res])
