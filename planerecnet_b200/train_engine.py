@@ -968,6 +968,19 @@ def _no_gc():
             gc.enable()
 
 
+def _allreduce_mean(t, world):
+    """NCCL mean over the ranks.  PRN_DP_OP=avg uses ReduceOp.AVG (one kernel); the default is SUM followed by an in-place scale."""
+    import os
+    import torch.distributed as dist
+    if os.environ.get("PRN_DP_OP", "sum") == "skip":      # tooling: time the step without the collective
+        return
+    if os.environ.get("PRN_DP_OP", "sum") == "avg":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(t)
+        t.mul_(1.0 / world)
+
+
 class GraphedStep:
     """Forward and backward of one training step captured as two CUDA graphs sharing a memory pool (the ~1300 launches
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
@@ -1157,7 +1170,7 @@ class GraphedStep:
             if self.world > 1:
                 import torch.distributed as dist
                 if dist.is_initialized():
-                    dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+                    _allreduce_mean(self.flat, self.world)
             return self.grads
         import torch.distributed as dist
         main = torch.cuda.current_stream()
@@ -1175,10 +1188,10 @@ class GraphedStep:
                 if self.peer is not None:
                     self.peer.reduce(b)
                 elif hi > lo:
-                    dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.AVG)
+                    _allreduce_mean(self.flat[lo:hi], self.world)
         if live:
             if self.dp_mode == "after":
-                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)          # main stream: nothing left to overlap with
+                _allreduce_mean(self.flat, self.world)                    # main stream: nothing left to overlap with
             elif self.peer is not None:
                 with torch.cuda.stream(self.comm):
                     self.peer.finish()
