@@ -314,8 +314,14 @@ static int wgrad_plan(const PrnWgrad& d, WgradKParams* p) {
   p->m_tiles = ceil_div(d.n, 128 * p->m_sub);
   p->kb_total = ceil_div(p->m_rows, kWgKBlock);
   const int tiles = p->m_tiles * p->n_tiles;
-  int splits = (2 * sm_count()) / tiles;
-  if (splits > p->kb_total / 4) splits = p->kb_total / 4;
+  // split-K factor: `waves` CTAs per SM in total.  More splits shorten the K loop of a CTA but multiply the fp32 reduction traffic
+  // (every split adds its whole 128 x 256 x m_sub accumulator into dW with red.global)
+  static const int waves = [] { const char* e = getenv("PRN_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 1; }();
+  // measured (profiles/r02_wgrad_waves.txt): one CTA per SM beats two (R101 step 30.7 -> 29.4 ms): the reduction traffic of the
+  // extra splits costs more than the shorter K loops save
+  static const int min_kb = [] { const char* e = getenv("PRN_WGRAD_MINKB"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 64 ? v : 16; }();   // >= 16 k-blocks per split: 30.7 -> 29.0 ms per R101 step together with waves = 1
+  int splits = (waves * sm_count()) / tiles;
+  if (splits > p->kb_total / min_kb) splits = p->kb_total / min_kb;
   if (splits < 1) splits = 1;
   p->kb_per_split = ceil_div(p->kb_total, splits);
   p->splits = ceil_div(p->kb_total, p->kb_per_split);
