@@ -12,7 +12,8 @@
 //   D        fp32 in TMEM: m_sub accumulators of 128 lanes x 256 columns; one work unit (M tile, N tile, K split)
 //            per CTA; partial sums leave through vectorised fp32 reductions (red.global.add.v4.f32)
 //
-// Warp roles (192 threads): warps 0-3 gather B, then drain TMEM; warp 4 = TMA producer of A; warp 5 = MMA issuer.
+// Warp roles (320 threads): warps 0-7 gather B (the cp.async path moves 12 B/clk/SM with 256 threads, 7 with 128:
+// profiles/r02_probe.txt), warps 0-3 then drain TMEM; warp 8 = TMA producer of A; warp 9 = MMA issuer.
 // The reference has no hand-written backward: this is autograd's conv weight gradient for the nn.Conv2d / F.conv2d
 // call sites listed in include/prn_b200.h (models/backbone.py:56-66, models/fpn.py:55,61, planerecnet.py:386-391,
 // 478-495, 593-605).
@@ -23,7 +24,10 @@
 
 namespace prn {
 
-constexpr int kWgThreads = 192;
+constexpr int kWgGatherWarps = 8;             // im2col gather warps (the first four also drain TMEM)
+constexpr int kWgGatherThreads = kWgGatherWarps * 32;
+constexpr int kWgRowsPerThread = 64 * 8 / kWgGatherThreads;   // 16-byte pieces per thread, atom and k-block
+constexpr int kWgThreads = kWgGatherThreads + 64;
 constexpr int kWgKBlock = 64;                 // pixels per k-block
 constexpr int kWgAtomBytes = kWgKBlock * 128; // one [64 pixels][64 channels] 16-bit atom tile
 constexpr int kWgMaxAtoms = 4;                // N tile = 4 atoms = 256 columns
@@ -99,17 +103,17 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   const int na = min(kWgMaxAtoms, p.atoms - nt * kWgMaxAtoms);
   const uint32_t tmem_cols = p.m_sub == 2 ? 512u : 256u;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kWgGatherWarps && lane == 0) {
     tma_prefetch_desc(&tmap_dy);
     if (p.b_tma) tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, p.b_tma ? 2 : 128 + 1);
+      mbar_init(bar_full + 8 * s, p.b_tma ? 2 : kWgGatherThreads + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     mbar_init(bar_tfull, 1);
     mbar_fence_init();
   }
-  if (warp == 5) {
+  if (warp == kWgGatherWarps + 1) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
@@ -118,7 +122,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + 136);
 
-  if (warp < 4) {
+  if (warp < kWgGatherWarps) {
    if (p.b_tma) {
     // =========================================================== B producer, 1x1 convs: one TMA box {64 ch, 64 pixels} per atom
     if (threadIdx.x == 0) {
@@ -139,7 +143,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     // =========================================================== B producer: im2col gather of 64 pixels x na atoms
     const int tid = threadIdx.x;
     const int chunk = tid & 7;          // 16-byte chunk (8 channels) of the 128-byte row
-    const int r0 = tid >> 3;            // rows r0, r0+16, r0+32, r0+48 of the k-block
+    const int r0 = tid >> 3;            // rows r0 + kRowStep * i of the k-block
+    constexpr int kRowStep = kWgGatherThreads / 8;
     const uint32_t swz = static_cast<uint32_t>((chunk ^ (r0 & 7)) << 4);
     const int ups_shift = d.upsample == 2 ? 1 : 0;
     const int h_eff = d.h_in << ups_shift, w_eff = d.w_in << ups_shift;
@@ -160,11 +165,11 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     int s = 0;
     uint32_t ph = 0;
     for (int kb = kb0; kb < kb1; ++kb) {
-      int img_pix[4], hy[4], wx[4];
+      int img_pix[kWgRowsPerThread], hy[kWgRowsPerThread], wx[kWgRowsPerThread];
       uint32_t valid = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = kb * kWgKBlock + r0 + 16 * i;
+      for (int i = 0; i < kWgRowsPerThread; ++i) {
+        const int m = kb * kWgKBlock + r0 + kRowStep * i;
         const bool v = m < p.m_rows;
         const int mm = v ? m : 0;
         int img, rem, ho, wo;
@@ -181,7 +186,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
       for (int j = 0; j < kWgMaxAtoms; ++j) {
         if (j < na) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kWgRowsPerThread; ++i) {
             int y = hy[i] + a_ky[j], x = wx[i] + a_kx[j];
             bool in = (valid >> i) & 1u;
             if (d.pad_mode == PRN_PAD_REFLECT) {
@@ -192,7 +197,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
                    static_cast<unsigned>(x) < static_cast<unsigned>(w_eff);
             }
             const uint32_t pix = in ? static_cast<uint32_t>(img_pix[i] + (y >> ups_shift) * d.w_in + (x >> ups_shift)) : 0u;
-            cp_async16(b_stage + static_cast<uint32_t>(j) * kWgAtomBytes + static_cast<uint32_t>(r0 + 16 * i) * 128u + swz,
+            cp_async16(b_stage + static_cast<uint32_t>(j) * kWgAtomBytes + static_cast<uint32_t>(r0 + kRowStep * i) * 128u + swz,
                        a_src[j] + static_cast<size_t>(pix) * a_pitch[j], in ? 16u : 0u);
           }
         }
@@ -202,7 +207,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
     }
    }
 
-    // =========================================================== drain: TMEM -> fp32 reductions into dW
+    // =========================================================== drain: TMEM -> fp32 reductions into dW (warps 0-3)
+    if (warp < 4) {
     mbar_wait(bar_tfull, 0);
     tc_fence_after();
     const int q = warp;   // TMEM lane quarter
@@ -227,7 +233,8 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
         }
       }
     }
-  } else if (warp == 4) {
+    }
+  } else if (warp == kWgGatherWarps) {
     // =========================================================== A producer: TMA boxes of dY
     if (lane == 0) {
       int s = 0;
@@ -273,7 +280,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 5) tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == kWgGatherWarps + 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 static int wgrad_plan(const PrnWgrad& d, WgradKParams* p) {
