@@ -24,7 +24,7 @@
 
 namespace prn {
 
-constexpr int kWgGatherWarps = 8;             // im2col gather warps (the first four also drain TMEM)
+constexpr int kWgGatherWarps = 16;            // im2col gather warps (the first four also drain TMEM)
 constexpr int kWgGatherThreads = kWgGatherWarps * 32;
 constexpr int kWgRowsPerThread = 64 * 8 / kWgGatherThreads;   // 16-byte pieces per thread, atom and k-block
 constexpr int kWgThreads = kWgGatherThreads + 64;
