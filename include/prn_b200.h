@@ -231,6 +231,11 @@ int prn_bn_finalize(const float* stats, float* mean_invstd, float* running_mean,
 /* out = [relu]((x - mean) * invstd * gamma + beta [+ residual]) over 16-bit [rows][c]. */
 int prn_bn_apply(const void* x16, void* out16, const float* mean_invstd, const float* gamma, const float* beta,
                  const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream);
+/* prn_bn_finalize + prn_bn_apply in one launch (training forward of nn.BatchNorm2d, models/backbone.py:57-65, planerecnet.py:518,543):
+ * mean / invstd from the batch sums, written to mean_invstd for the backward; running statistics updated when non-NULL. */
+int prn_bn_finalize_apply(const void* x16, void* out16, const float* stats, float* mean_invstd, float* running_mean,
+                          float* running_var, int64_t count, float eps, float momentum, const float* gamma, const float* beta,
+                          const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream);
 /* Per-channel reductions of a gradient: g = dz * (out > 0) (out16 NULL: g = dz);
  * sums[c*2] += sum g (= dbeta / conv bias gradient), sums[c*2+1] += sum g * (x - mean) * invstd (= dgamma; skipped when
  * x16 is NULL).  Caller zeroes sums. */

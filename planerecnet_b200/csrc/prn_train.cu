@@ -79,6 +79,64 @@ __global__ void __launch_bounds__(kPwThreads) bn_apply_kernel(const T* __restric
   }
 }
 
+// bn_finalize + bn_apply in one launch (training forward: 113 BatchNorms per step): every thread derives mean / invstd of its
+// 8 channels from the batch sums; the first C/8 threads of the grid also publish mean_invstd (the backward reads it) and update
+// the running statistics (nn.BatchNorm2d: momentum, unbiased variance).
+template <typename T>
+__global__ void __launch_bounds__(kPwThreads) bn_finalize_apply_kernel(const T* __restrict__ x, T* __restrict__ out,
+                                                                     const float* __restrict__ stats, float* __restrict__ mean_invstd,
+                                                                     float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                     float count, float eps, float momentum,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                     const T* __restrict__ res, long long rows, int C, int relu) {
+  const int cv = C / 8;
+  const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
+  const int c = static_cast<int>(gtid % cv) * 8;
+  const bool writer = gtid < cv;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = __ldg(stats + 2 * (c + j)) / count;
+    const float var = fmaxf(__ldg(stats + 2 * (c + j) + 1) / count - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    if (writer) {
+      mean_invstd[2 * (c + j)] = mean;
+      mean_invstd[2 * (c + j) + 1] = invstd;
+      if (running_mean != nullptr) {
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_mean[c + j] = (1.f - momentum) * running_mean[c + j] + momentum * mean;
+        running_var[c + j] = (1.f - momentum) * running_var[c + j] + momentum * unbiased;
+      }
+    }
+    sc[j] = invstd * __ldg(gamma + c + j);
+    sh[j] = __ldg(beta + c + j) - mean * sc[j];
+  }
+  const float lo = relu ? 0.f : -INFINITY;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+    const long long m2 = m + rstep;
+    const bool two = m2 < rows;
+    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
+    const uint4 x1 = two ? __ldg(reinterpret_cast<const uint4*>(x + m2 * C + c)) : zero4;
+    uint4 r0 = zero4, r1 = zero4;
+    if (res != nullptr) {
+      r0 = __ldg(reinterpret_cast<const uint4*>(res + m * C + c));
+      if (two) r1 = __ldg(reinterpret_cast<const uint4*>(res + m2 * C + c));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      float f[8], r[8];
+      unpack8<T>(h ? x1 : x0, f);
+      unpack8<T>(h ? r1 : r0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(fmaf(f[j], sc[j], sh[j]) + r[j], lo);
+      store8(out + (h ? m2 : m) * C + c, f);
+    }
+  }
+}
+
 // sums[c*2] += sum_m g, sums[c*2+1] += sum_m g * xhat with g = dz * (out > 0) (out == NULL: g = dz) and
 // xhat = (x - mean) * invstd (x == NULL: second sum skipped).  Total thread count is a multiple of C/8 so that a
 // thread keeps its 8 channels for all of its rows.
@@ -480,6 +538,21 @@ int prn_bn_apply(const void* x16, void* out16, const float* mean_invstd, const f
   PRN_DISPATCH(dtype,
                (bn_apply_kernel<__nv_bfloat16><<<grid, kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), static_cast<__nv_bfloat16*>(out16), mean_invstd, gamma, beta, static_cast<const __nv_bfloat16*>(residual16), rows, c, relu)),
                (bn_apply_kernel<__half><<<grid, kPwThreads, 0, st>>>(static_cast<const __half*>(x16), static_cast<__half*>(out16), mean_invstd, gamma, beta, static_cast<const __half*>(residual16), rows, c, relu)));
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_bn_finalize_apply(const void* x16, void* out16, const float* stats, float* mean_invstd, float* running_mean,
+                          float* running_var, int64_t count, float eps, float momentum, const float* gamma, const float* beta,
+                          const void* residual16, int64_t rows, int32_t c, int32_t relu, int32_t dtype, void* stream) {
+  PRN_REQUIRE(x16 && out16 && stats && mean_invstd && gamma && beta && rows > 0 && count > 0 && c > 0 && c % 8 == 0 &&
+                  (running_mean == nullptr) == (running_var == nullptr), "bn_finalize_apply: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = chan_reduce_grid(rows, c / 8, 4);
+  PRN_REQUIRE(static_cast<long long>(grid) * kPwThreads >= c / 8, "bn_finalize_apply: grid smaller than the channel groups");
+  const float cnt = static_cast<float>(count);
+  PRN_DISPATCH(dtype,
+               (bn_finalize_apply_kernel<__nv_bfloat16><<<grid, kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(x16), static_cast<__nv_bfloat16*>(out16), stats, mean_invstd, running_mean, running_var, cnt, eps, momentum, gamma, beta, static_cast<const __nv_bfloat16*>(residual16), rows, c, relu)),
+               (bn_finalize_apply_kernel<__half><<<grid, kPwThreads, 0, st>>>(static_cast<const __half*>(x16), static_cast<__half*>(out16), stats, mean_invstd, running_mean, running_var, cnt, eps, momentum, gamma, beta, static_cast<const __half*>(residual16), rows, c, relu)));
   PRN_LAUNCH_CHECK();
 }
 

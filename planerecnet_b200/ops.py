@@ -177,6 +177,13 @@ def bn_apply(x, out, mean_invstd, gamma, beta, residual, relu, dtype):
                                  C.c_int64(x.numel() // c), c, 1 if relu else 0, dtype, L.current_stream()), "prn_bn_apply")
 
 
+def bn_finalize_apply(x, out, stats, mean_invstd, running_mean, running_var, count, eps, momentum, gamma, beta, residual, relu, dtype):
+    c = x.shape[-1]
+    L.check(L.lib().prn_bn_finalize_apply(_vp(x), _vp(out), _vp(stats), _vp(mean_invstd), _vp(running_mean), _vp(running_var),
+                                          C.c_int64(count), C.c_float(eps), C.c_float(momentum), _vp(gamma), _vp(beta), _vp(residual),
+                                          C.c_int64(x.numel() // c), c, 1 if relu else 0, dtype, L.current_stream()), "prn_bn_finalize_apply")
+
+
 def chan_reduce(dz, out, x, mean_invstd, sums, dtype):
     c = dz.shape[-1]
     L.check(L.lib().prn_chan_reduce(_vp(dz), _vp(out), _vp(x), _vp(mean_invstd), _vp(sums), C.c_int64(dz.numel() // c), c, dtype,

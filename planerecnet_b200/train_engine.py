@@ -372,19 +372,24 @@ class TrainEngine(Engine):
             rv = bn.running_var if bn.track_running_stats else None
             assert rm is None or rm.numel() == Cc
             mom = bn.momentum if bn.momentum is not None else 0.1
-            ops.bn_finalize(y._prn_stats, mi, rm, rv, rows, bn.eps, mom)
+            fused_finalize = rm is None or rm.numel() == Cc
+            if not fused_finalize:
+                ops.bn_finalize(y._prn_stats, mi, rm, rv, rows, bn.eps, mom)
+                self.launches += 1
             if bn.track_running_stats:
                 self._nbt.append(bn.num_batches_tracked)      # advanced with one multi-tensor add at the end of the forward
                 # the kernel wrote through raw pointers: bump the version counters the weight caches key on
                 torch.autograd.graph.increment_version(bn.running_mean)
                 torch.autograd.graph.increment_version(bn.running_var)
-            self.launches += 1
         else:   # frozen statistics (freeze_bn): normalise with the running estimates
             mi = self._pack((id(bn), "bn_frozen"), [bn.running_mean, bn.running_var],
                             lambda: torch.stack([ops.pad_vec(bn.running_mean, Cc),
                                                  1.0 / torch.sqrt(ops.pad_vec(bn.running_var, Cc) + bn.eps)], 1).contiguous().cuda())
         out = self._empty(*y.shape)
-        ops.bn_apply(y, out, mi, gb[0], gb[1], residual, relu, self.dt)
+        if bn.training and fused_finalize:      # statistics finalised inside the apply pass (one launch less per BatchNorm)
+            ops.bn_finalize_apply(y, out, y._prn_stats, mi, rm, rv, rows, bn.eps, mom, gb[0], gb[1], residual, relu, self.dt)
+        else:
+            ops.bn_apply(y, out, mi, gb[0], gb[1], residual, relu, self.dt)
         self.launches += 1
         train_stats = bn.training
         nreal = gamma.numel()
@@ -1230,16 +1235,26 @@ class _DenseTrainFn(torch.autograd.Function):
         else:
             eng.seed_output_grads(*args)
             g = eng.backward()
-        out = []
-        for p in ctx.params:
+        # copies: the accumulators (and, when graphed, the static buffers) are reused by the next step.  All parameter gradients
+        # go into ONE fresh flat buffer with a multi-tensor copy (two launches instead of one per parameter: ~450); autograd
+        # receives views of it.
+        out = [None] * len(ctx.params)
+        idx, srcs = [], []
+        for i, p in enumerate(ctx.params):
             gp = g.get(id(p))
-            # copies: the accumulators (and, when graphed, the static buffers) are reused by the next step
-            if gp is None or not p.requires_grad:
-                out.append(None)
-            elif eng.grad_scale != 1.0:
-                out.append((gp / eng.grad_scale).to(p.dtype).contiguous())
-            else:
-                out.append(gp.to(p.dtype, copy=True).contiguous())
+            if gp is not None and p.requires_grad:
+                assert p.dtype == torch.float32
+                idx.append(i)
+                srcs.append(gp.reshape(p.shape))
+        if idx:
+            sizes = [ctx.params[i].numel() for i in idx]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=srcs[0].device)
+            views = [v.view(ctx.params[i].shape) for v, i in zip(flat.split(sizes), idx)]
+            torch._foreach_copy_(views, srcs)
+            if eng.grad_scale != 1.0:
+                flat.mul_(1.0 / eng.grad_scale)
+            for i, v in zip(idx, views):
+                out[i] = v
         return (None, None, *out)
 
 
