@@ -163,17 +163,26 @@ class _InsLava(torch.autograd.Function):
         n = _round_up(max(max(n_b), 1), 16)
         wsel = torch.zeros(B, n, Cc, device=dev)
         tgt = torch.zeros(B, n, P, dtype=torch.uint8, device=dev)
-        valid = torch.zeros(B, n, dtype=torch.bool, device=dev)
+        # all positive-cell indices of the batch in ONE upload (a torch.tensor(list, device=cuda) per image and level is a
+        # synchronous copy each: 32 per step)
+        flat_idx = [i for b in range(B) for l in range(n_levels) for i in targets[b][l][3]]
+        idx_all = torch.tensor(flat_idx, dtype=torch.int64, device="cpu").to(dev, non_blocking=True) if flat_idx else None
+        idx_views, pos = {}, 0
         for b in range(B):
             off = 0
             for l in range(n_levels):
                 order = targets[b][l][3]
                 if order:
-                    idx = torch.tensor(order, device=dev)
+                    idx = idx_all[pos:pos + len(order)]
+                    idx_views[(b, l)] = idx
+                    pos += len(order)
                     wsel[b, off:off + len(order)] = kernel_preds[l][b].reshape(Cc, -1)[:, idx].t()
                     tgt[b, off:off + len(order)] = targets[b][l][0].reshape(len(order), P).to(dev)
                     off += len(order)
-            valid[b, :n_b[b]] = True
+        valid_host = torch.zeros(B, n, dtype=torch.bool, device="cpu")
+        for b in range(B):
+            valid_host[b, :n_b[b]] = True
+        valid = valid_host.to(dev, non_blocking=True)
         mask16 = be.to16(mask_pred.reshape(B, Cc, P).transpose(1, 2))        # [B, P, C]
         wsel16 = be.to16(wsel)
         seg = be.seg_rows(wsel16, mask16)                                     # [B*n, P] sigmoid probabilities
@@ -183,7 +192,7 @@ class _InsLava(torch.autograd.Function):
         den = bq + c + 0.002
         dice = torch.where(valid, 1 - 2 * a / den, torch.zeros_like(a))
         loss_ins = w_dice * dice.sum() / n_total
-        nb_t = torch.tensor(n_b, dtype=torch.float32, device=dev)
+        nb_t = torch.tensor(n_b, dtype=torch.float32, device="cpu").to(dev, non_blocking=True)
         elig = (nb_t > 0) & (gsum > 0)
         n_elig = int(elig.sum())
         per_img = torch.where(elig, (lv * valid).sum(1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
@@ -194,6 +203,7 @@ class _InsLava(torch.autograd.Function):
         cl_img = torch.where(elig, w_lava / max(n_elig, 1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
         cl = cl_img[:, None] * valid
         ctx.be, ctx.targets, ctx.counts, ctx.shapes = be, targets, counts, (B, Cc, fh, fw, n, [k.shape for k in kernel_preds])
+        ctx.idx_views = idx_views
         ctx.save_for_backward(seg, tgt, gw, mask16, wsel16, ca, cb, cl)
         return loss_ins, loss_lav
 
@@ -227,7 +237,7 @@ class _InsLava(torch.autograd.Function):
                 order = ctx.targets[b][l][3]
                 if order:
                     off = sum(ctx.counts[b][:l])
-                    gk[b].view(Cc, -1).index_add_(1, torch.tensor(order, device=dev), dK[b, off:off + len(order)].t().float())
+                    gk[b].view(Cc, -1).index_add_(1, ctx.idx_views[(b, l)], dK[b, off:off + len(order)].t().float())
             d_kern.append(gk)
         return (None, None, None, None, None, None, d_mask, *d_kern)
 
@@ -407,7 +417,8 @@ class _PlaneNormalBatched:
             reg_rest += [False] * n + [True]
         member = torch.cat(stacks, 0)                                   # [R, HW] bool
         R = member.shape[0]
-        counts = member.sum(1).tolist()                                 # the one host sync of this term
+        counts_dev = member.sum(1)
+        counts = counts_dev.tolist()                                    # the one host sync of this term
         # ---- triplet indices
         if self.sampling == "numpy":
             idx_np, ks = self._sample_host(counts, reg_rest)
@@ -422,15 +433,17 @@ class _PlaneNormalBatched:
         else:
             ks = [0 if (rest and c == 0) else int(c * self.ratio) for c, rest in zip(counts, reg_rest)]
             T = sum(ks)
-        ks_t = torch.tensor(ks, device=dev)
+        # the per-region host tables in ONE upload: k, image of the region, rest flag
+        tab = torch.tensor([ks, reg_img, [int(r) for r in reg_rest]], dtype=torch.int64, device="cpu").to(dev, non_blocking=True)
+        ks_t, img_of, is_rest_r = tab[0], tab[1], tab[2].bool()
         region = torch.repeat_interleave(torch.arange(R, device=dev), ks_t, output_size=T)            # [T]
-        counts_t = torch.tensor(counts, device=dev)
+        counts_t = counts_dev
         if self.sampling == "device":
             idx = (torch.rand(3, T, device=dev, dtype=torch.float64) * counts_t[region].double()).long()
             idx = torch.minimum(idx, (counts_t[region] - 1).clamp(min=0))
         # pixel lists of the regions (row-major inside a region = the order of `pts[mask]`)
         nz = member.nonzero()
-        gpix = torch.tensor(reg_img, device=dev)[nz[:, 0]] * HW + nz[:, 1]
+        gpix = img_of[nz[:, 0]] * HW + nz[:, 1]
         base = torch.cumsum(counts_t, 0) - counts_t                      # first entry of each region in gpix
         P = gpix[(base[region][None, :] + idx).reshape(-1)].reshape(3, T)                              # global pixel of every point
         # ---- point clouds (vnl.py:20-38)
@@ -439,7 +452,7 @@ class _PlaneNormalBatched:
         pred_pts = self._points(depth_up, fx, fy)
         gt_pts = self._points(gt_depths.to(depth_up.dtype), fx, fy)
         g_pred = pred_pts[P].permute(1, 2, 0)                            # [T, xyz, p123]
-        is_rest_t = torch.tensor(reg_rest, device=dev)[region]
+        is_rest_t = is_rest_r[region]
         g_gt = gt_pts[P].permute(1, 2, 0)
         g_test = torch.where(is_rest_t[:, None, None], g_gt, g_pred)     # planes are tested on the prediction, the rest on the GT
         # ---- vnl.py:56-98: usable triplets
@@ -484,16 +497,14 @@ class _PlaneNormalBatched:
         drop = n_keep // 4                                                # int(n * 0.25)
         incl = keep & ((pos - start[region]) >= drop[region])
         contrib = torch.where(incl & ~torch.isnan(loss_t), loss_t, torch.zeros_like(loss_t))
-        is_rest_r = torch.tensor(reg_rest, device=dev)
         # the rest regions' tail is a float32 sum in the reference: accumulate it in float32, the planes' in float64
         sum_plane = torch.zeros(R, dtype=torch.float64, device=dev).index_add_(0, region, torch.where(is_rest_t, 0.0, contrib))
         sum_rest = torch.zeros(R, dtype=torch.float32, device=dev).index_add_(0, region, torch.where(is_rest_t, contrib, 0.0).float())
         den = (n_keep - drop).double()
         loss_r = torch.where(is_rest_r, sum_rest.double() / den.float().double(), sum_plane / den)       # 0 / 0 -> NaN like the reference
         # ---- per image (vnl.py:119-165)
-        img_of = torch.tensor(reg_img, device=dev)
         total = torch.zeros(B, dtype=torch.float64, device=dev).index_add_(0, img_of, torch.where(is_rest_r, 0.0, loss_r))
-        npl = torch.tensor(n_planes, dtype=torch.float64, device=dev)
+        npl = torch.tensor(n_planes, dtype=torch.float64, device="cpu").to(dev, non_blocking=True)
         rest_rows = is_rest_r.nonzero().flatten()                          # one rest region per image, in image order
         rest_used = (counts_t[rest_rows] > 0) & (n_keep[rest_rows] > 0)
         with_rest = (total + torch.where(rest_used, loss_r[rest_rows], torch.zeros_like(total))) / (npl + 1)

@@ -16,6 +16,19 @@ B200 that the CUDA assignment equals the CPU one and the unmodified reference's 
 import torch
 
 
+_SCALARS = {}
+
+
+def _dev_scalar(value, dtype, dev):
+    """A 0-dim device tensor holding `value`, cached: creating one costs a synchronous host-to-device copy, and the target
+    assignment needs the same dozen divisors every step."""
+    key = (float(value), dtype, str(dev))
+    t = _SCALARS.get(key)
+    if t is None:
+        t = _SCALARS[key] = torch.tensor(float(value), dtype=dtype, device=dev)
+    return t
+
+
 def quarter_masks(masks):
     """[n, H, W] {0,1} (any integer / bool dtype), H and W multiples of 4 -> [n, H/4, W/4] uint8, identical to
     cv2.resize(..., fx=fy=0.25, INTER_LINEAR) of the uint8 masks."""
@@ -62,8 +75,8 @@ def assign_targets(gt, feat_hw, num_grids, scale_ranges, num_classes=2, sigma=0.
             # divisors as device tensors of v's dtype: with Python-scalar divisors torch's CUDA kernels take a
             # multiply-by-reciprocal shortcut that may differ from the IEEE quotient in the last bit — enough to move a
             # centre that sits exactly on a grid-cell boundary (0.5 // 0.025) to the other cell than the CPU run
-            e = torch.tensor(float(extent), dtype=v.dtype, device=dev)
-            pitch = torch.tensor(1.0 / S, dtype=v.dtype, device=dev)
+            e = _dev_scalar(extent, v.dtype, dev)
+            pitch = _dev_scalar(1.0 / S, v.dtype, dev)
             return torch.floor_divide(v / e, pitch).to(torch.int64)
 
         cx, cy = cell(cw, up_w), cell(ch, up_h)
@@ -124,8 +137,8 @@ def assign_targets_batch(gts, feat_hw, num_grids, scale_ranges, num_classes=2, s
     rows = []
     for (lo, hi), S in zip(scale_ranges, num_grids):
         def cell(v, extent):
-            e = torch.tensor(float(extent), dtype=v.dtype, device=dev)
-            pitch = torch.tensor(1.0 / S, dtype=v.dtype, device=dev)
+            e = _dev_scalar(extent, v.dtype, dev)
+            pitch = _dev_scalar(1.0 / S, v.dtype, dev)
             return torch.floor_divide(v / e, pitch).to(torch.int64)
 
         hit = (areas >= lo) & (areas <= hi)

@@ -22,7 +22,7 @@ def main():
     torch.manual_seed(0)
     net = perturb_(PlaneRecNet(cfg)).train().cuda()
     net.use_train_graph = True
-    crit = PL.PlaneRecNetLoss(cfg)
+    crit = PL.PlaneRecNetLoss(cfg, vnl_sampling=(sys.argv[2] if len(sys.argv) > 2 else "numpy"))
     x = make_input(B, 480, 640, 0).cuda()
     gts, gtd = make_gt(B, 480, 640, 0)
     gts = [{k: v.cuda() for k, v in g.items()} for g in gts]
@@ -48,10 +48,27 @@ def main():
         t3 = T()
         print(f"iter {it}: forward {1e3 * (t1 - t0):.1f} ms | loss {1e3 * (t2 - t1):.1f} ms | backward (loss + model) {1e3 * (t3 - t2):.1f} ms"
               + (" | " + " ".join(f"{k} {1e3 * v:.1f}" for k, v in crit.timings.items()) if getattr(crit, "timings", None) else ""))
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    for p in net.parameters():
+        p.grad = None
+    outs = net(x)
+    torch.cuda.synchronize()
+    pr.enable()
+    np.random.seed(0)
+    losses = crit(net, outs[0], outs[1], outs[2], outs[3], gts, gtd)
+    tot = sum(v.mean() for v in losses.values())
+    tot.backward()
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+    outs = net(x)
     # the pieces of the loss, one by one (synchronised)
     fh, fw = outs[0].shape[-2:]
     t0 = T()
-    targets = [assign_targets(g, (fh, fw), crit.num_grids, crit.scale_ranges, crit.num_classes, crit.sigma) for g in gts]
+    from planerecnet_b200.targets import assign_targets_batch
+    targets = assign_targets_batch(gts, (fh, fw), crit.num_grids, crit.scale_ranges, crit.num_classes, crit.sigma)
     t1 = T()
     print(f"assign_targets x{B}: {1e3 * (t1 - t0):.1f} ms")
     be = PL.CudaBackend()
