@@ -493,6 +493,9 @@ static int tma_plan(const PrnConv& d, TmaKParams* p) {
   const int sms = sm_count();
   int n_tile = d.n_pad <= 256 ? d.n_pad : ((d.n_pad % 256 == 0 || d.n_pad > 1024) ? 256 : 128);
   {
+    // Empirical model (tuned on tools/conv_probe.py): waves x (k-blocks x max(MMA, operand stream) + epilogue).  A narrower tile
+    // has to win by 15 %: near ties go to the wide tile, whose MMAs run at the better rate (161 cycles per 256 columns against
+    // 116 per <= 128, §3.0 of DESIGN.md) — e.g. the 60x80 FPN conv: 320 tiles at N = 256 (46.8 us) against 640 at N = 128 (72.5 us).
     const int kb = p->ncb * p->taps;
     double best = 1e300;
     int best_t = n_tile;
@@ -503,7 +506,7 @@ static int tma_plan(const PrnConv& d, TmaKParams* p) {
       const double a_bytes = static_cast<double>(p->a_stage_bytes) / p->taps;
       const double per_kb = fmax(2.0 * t, (a_bytes + 128.0 * t) / 60.0) + 20.0;
       const double cost = waves * (kb * per_kb + 12.0 * t + 2500.0);
-      if (cost < best) { best = cost; best_t = t; }
+      if (cost < best * (t == n_tile ? 1.0 : 0.85)) { best = cost; best_t = t; }
       if (t % 2 != 0 || (t / 2) % 16 != 0) break;
     }
     n_tile = best_t;
