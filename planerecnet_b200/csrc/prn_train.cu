@@ -144,10 +144,7 @@ template <typename T>
 __global__ void __launch_bounds__(kPwThreads) chan_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out,
                                                                const T* __restrict__ x, const float* __restrict__ mean_invstd,
                                                                float* __restrict__ sums, long long rows, int C) {
-  extern __shared__ float acc[];   // [C][2]
   const int cv = C / 8;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const int c = static_cast<int>(gtid % cv) * 8;
@@ -196,25 +193,19 @@ __global__ void __launch_bounds__(kPwThreads) chan_reduce_kernel(const T* __rest
       s2[j] = inv * (s2[j] - mean * s1[j]);
     }
   }
-  // lanes l, l + cv, l + 2 cv, ... of a warp hold the same channels when cv divides 32: fold them with shuffles first
-  const int lane = threadIdx.x & 31;
-  bool writer = true;
-  if (cv < 32 && (32 % cv) == 0 && (blockDim.x % 32) == 0) {
-    for (int off = 16; off >= cv; off >>= 1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
-        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
-      }
-    }
-    writer = lane < cv;
+  if (fold_ok(cv)) {     // every BatchNorm of the ResNets: C in {64 ... 2048}
+    __shared__ float part[kFoldFloats];
+    block_fold_chan(s1, s2, cv, part, [&](int o, float tot) { atomicAdd(sums + o, tot); });
+    return;
   }
-  if (writer) {
+  // general channel counts: shared-memory atomics
+  extern __shared__ float acc[];   // [C][2]
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(acc + 2 * (c + j), s1[j]);
-      atomicAdd(acc + 2 * (c + j) + 1, s2[j]);
-    }
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(acc + 2 * (c + j), s1[j]);
+    atomicAdd(acc + 2 * (c + j) + 1, s2[j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(sums + i, acc[i]);
@@ -242,19 +233,37 @@ __global__ void __launch_bounds__(kPwThreads) bn_bwd_apply_kernel(const T* __res
     kb[j] = -ka[j] * inv * sgx;
     kk[j] = -ka[j] * sg - kb[j] * mean;
   }
-  for (long long m = gtid / cv; m < rows; m += rstep) {
-    float g[8], o[8], xv[8];
-    load8(dz + m * C + c, g);
-    load8(x + m * C + c, xv);
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  // two rows per iteration, all loads issued before the first use (latency-bound otherwise: most launches move < 30 MB)
+  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+    const long long m2 = m + rstep;
+    const bool two = m2 < rows;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(dz + m * C + c));
+    const uint4 a1 = two ? __ldg(reinterpret_cast<const uint4*>(dz + m2 * C + c)) : zero4;
+    const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
+    const uint4 c1 = two ? __ldg(reinterpret_cast<const uint4*>(x + m2 * C + c)) : zero4;
+    uint4 b0 = zero4, b1 = zero4;
     if (out != nullptr) {
-      load8(out + m * C + c, o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      b0 = __ldg(reinterpret_cast<const uint4*>(out + m * C + c));
+      if (two) b1 = __ldg(reinterpret_cast<const uint4*>(out + m2 * C + c));
     }
-    if (g_out != nullptr) store8(g_out + m * C + c, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] = fmaf(ka[j], g[j], fmaf(kb[j], xv[j], kk[j]));
-    store8(dx + m * C + c, xv);
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long mm = h ? m2 : m;
+      float g[8], o[8], xv[8];
+      unpack8<T>(h ? a1 : a0, g);
+      unpack8<T>(h ? c1 : c0, xv);
+      if (out != nullptr) {
+        unpack8<T>(h ? b1 : b0, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = o[j] > 0.f ? g[j] : 0.f;
+      }
+      if (g_out != nullptr) store8(g_out + mm * C + c, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[j] = fmaf(ka[j], g[j], fmaf(kb[j], xv[j], kk[j]));
+      store8(dx + mm * C + c, xv);
+    }
   }
 }
 
@@ -506,13 +515,13 @@ __global__ void dcn_col2im_bwd_kernel(const T* __restrict__ x, const float* __re
 // =================================================================================================== C ABI
 using namespace prn;
 
-static int chan_reduce_grid(long long rows, int cv, int rows_per_thread = 8) {
+static int chan_reduce_grid(long long rows, int cv, int rows_per_thread = 8, int ctas_per_sm = 8) {
   // total threads must be a multiple of cv: grid multiple of cv / gcd(cv, 256)
   int a = cv, b = kPwThreads;
   while (b) { const int t = a % b; a = b; b = t; }
   const int g0 = cv / a;
   long long want = (rows * cv + kPwThreads * static_cast<long long>(rows_per_thread) - 1) / (kPwThreads * static_cast<long long>(rows_per_thread));
-  const long long cap = static_cast<long long>(sm_count()) * 8;
+  const long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
   if (want > cap) want = cap;
   long long grid = want / g0 * g0;
   if (grid < g0) grid = g0;
@@ -561,7 +570,8 @@ int prn_chan_reduce(const void* dz16, const void* out16, const void* x16, const 
   PRN_REQUIRE(dz16 && sums && rows > 0 && c > 0 && c % 8 == 0 && c <= 4096 && (x16 == nullptr || mean_invstd != nullptr),
               "chan_reduce: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = chan_reduce_grid(rows, c / 8);
+  // 4 CTAs of this kernel are resident per SM (registers): a larger grid only adds a second, partial wave (reduce_probe.cu)
+  const int grid = chan_reduce_grid(rows, c / 8, 8, 4);
   const size_t smem = static_cast<size_t>(c) * 2 * sizeof(float);
   PRN_DISPATCH(dtype,
                (chan_reduce_kernel<__nv_bfloat16><<<grid, kPwThreads, smem, st>>>(static_cast<const __nv_bfloat16*>(dz16), static_cast<const __nv_bfloat16*>(out16), static_cast<const __nv_bfloat16*>(x16), mean_invstd, sums, rows, c)),

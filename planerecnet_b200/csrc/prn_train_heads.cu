@@ -26,11 +26,8 @@ template <typename T>
 __global__ void gn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restrict__ out, const T* __restrict__ x,
                                      const float* __restrict__ stats, float* __restrict__ sums_bc, float* __restrict__ dgb,
                                      int HW, int C, int cg, float eps) {
-  extern __shared__ float acc[];   // [C][2]
   const int cv = C / 8, G = C / cg;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
   const int c = static_cast<int>(gtid % cv) * 8;
@@ -60,6 +57,17 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restri
       s2[j] = fmaf(gg, (xv[j] - mean[j]) * rstd[j], s2[j]);
     }
   }
+  if (fold_ok(cv)) {
+    __shared__ float part[kFoldFloats];
+    block_fold_chan(s1, s2, cv, part, [&](int o, float tot) {
+      atomicAdd(sums_bc + static_cast<long long>(b) * C * 2 + o, tot);
+      atomicAdd(dgb + o, tot);
+    });
+    return;
+  }
+  extern __shared__ float acc[];   // [C][2]: general channel counts, shared-memory atomics
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     atomicAdd(acc + 2 * (c + j), s1[j]);
@@ -85,6 +93,29 @@ __global__ void __launch_bounds__(kPwThreads) gn_bwd_apply_kernel(const T* __res
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
   const int c = static_cast<int>(gtid % cv) * 8;
+  // per-group sums of gamma * {a, bq}: one warp per group, lanes over the group's channels (a per-thread loop over the
+  // group's channels was a 2 * cg-deep chain of L2 round trips in every thread: ~30 us of a 38 us launch)
+  __shared__ float gsum[2 * 512];
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int grp = warp; grp < G; grp += nwarps) {
+      float ga = 0.f, gb = 0.f;
+      for (int cc = grp * cg + lane; cc < (grp + 1) * cg; cc += 32) {
+        const float gm = __ldg(gamma + cc);
+        ga = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2), ga);
+        gb = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2 + 1), gb);
+      }
+      for (int off = 16; off; off >>= 1) {
+        ga += __shfl_xor_sync(0xffffffffu, ga, off);
+        gb += __shfl_xor_sync(0xffffffffu, gb, off);
+      }
+      if (lane == 0) {
+        gsum[2 * grp] = ga;
+        gsum[2 * grp + 1] = gb;
+      }
+    }
+  }
+  __syncthreads();
   float ka[8], kb[8], kk[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -92,12 +123,7 @@ __global__ void __launch_bounds__(kPwThreads) gn_bwd_apply_kernel(const T* __res
     const float m1 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2) * inv_cnt;
     const float m2 = __ldg(stats + (static_cast<long long>(b) * G + grp) * 2 + 1) * inv_cnt;
     const float rstd = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + eps);
-    float ga = 0.f, gb = 0.f;      // sum over the group's channels of gamma * {a, bq}
-    for (int cc = grp * cg; cc < (grp + 1) * cg; ++cc) {
-      const float gm = __ldg(gamma + cc);
-      ga = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2), ga);
-      gb = fmaf(gm, __ldg(sums_bc + (static_cast<long long>(b) * C + cc) * 2 + 1), gb);
-    }
+    const float ga = gsum[2 * grp], gb = gsum[2 * grp + 1];      // sum over the group's channels of gamma * {a, bq}
     ka[j] = rstd * __ldg(gamma + c + j);
     kb[j] = -rstd * rstd * gb * inv_cnt;
     kk[j] = -rstd * ga * inv_cnt - kb[j] * m1;
@@ -302,7 +328,7 @@ int prn_gn_bwd_apply(const void* dz16, const void* out16, const void* x16, const
                      const float* sums_bc, void* dx16, int32_t batch, int32_t hw, int32_t c, int32_t ch_per_group, float eps,
                      int32_t dtype, void* stream) {
   PRN_REQUIRE(dz16 && out16 && x16 && stats && gamma && sums_bc && dx16 && batch > 0 && hw > 0 && c > 0 && c % 8 == 0 &&
-                  ch_per_group > 0 && c % ch_per_group == 0, "gn_bwd_apply: bad arguments");
+                  ch_per_group > 0 && c % ch_per_group == 0 && c / ch_per_group <= 512, "gn_bwd_apply: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int cv = c / 8;
   int a = cv, b = kPwThreads;
