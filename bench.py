@@ -322,50 +322,80 @@ def main():
         params = [p for p in tnet.parameters() if p.requires_grad]
         loss_host = torch.empty(5).pin_memory()
 
-        def user_step():
-            x = x_host.cuda(non_blocking=True)
-            gts = [{k: v.cuda(non_blocking=True) for k, v in g.items()} for g in gts_h]
-            gtd = gtd_h.cuda(non_blocking=True)
+        copy_stream = torch.cuda.Stream()
+
+        def upload():
+            """One batch: pinned host -> device on the copy stream, and the ground-truth-only part of its loss started."""
+            with torch.cuda.stream(copy_stream):
+                x = x_host.cuda(non_blocking=True)
+                gts = [{k: v.cuda(non_blocking=True) for k, v in g.items()} for g in gts_h]
+                gtd = gtd_h.cuda(non_blocking=True)
+                crit.prepare(gts)              # targets + triplet sampling: worker thread + side stream, returns at once
+            return x, gts, gtd
+
+        def consume(batch):
+            main = torch.cuda.current_stream()
+            main.wait_stream(copy_stream)
+            x, gts, gtd = batch
+            for t in [x, gtd] + [v for g in gts for v in g.values()]:
+                t.record_stream(main)
+            return x, gts, gtd
+
+        def step_body(x, gts, gtd, prefetch):
             for p in params:
                 p.grad = None
             mask, cate, kern, depth = tnet(x)
-            np.random.seed(0)
             losses = crit(tnet, mask, cate, kern, depth, gts, gtd)
             losses = {k: v.mean() for k, v in losses.items()}          # train.py:347-348
+            nxt = upload() if prefetch else None                       # next batch: H2D + its GT-only work overlap this backward
             sum(losses[k] for k in losses).backward()
             if world > 1:
                 D.allreduce_mean_grads({id(p): p.grad for p in params if p.grad is not None}, params)
             vals = torch.stack([losses[k].detach().float() for k in ("ins", "cat", "dpt", "pln", "lav")])
             loss_host.copy_(vals, non_blocking=True)
             torch.cuda.current_stream().synchronize()                  # the losses are on the host when the step ends
-            return loss_host.tolist()
+            return loss_host.tolist(), nxt
 
-        def timed_user_steps():
-            for _ in range(3):
-                lv_ = user_step()
+        def user_loop(n, lookahead):
+            """n steps of the loop a user writes.  lookahead: one batch of prefetch (the next batch's upload and the
+            ground-truth-only part of its loss are started before this step's backward, like a prefetching DataLoader);
+            otherwise every step uploads its own batch first.  n uploads and n loss read-backs either way."""
+            np.random.seed(0)
+            nxt = upload() if lookahead else None
+            for i in range(n):
+                batch = consume(nxt if lookahead else upload())
+                lv_, nxt = step_body(*batch, prefetch=lookahead and i + 1 < n)
+            return lv_
+
+        def timed_user_steps(lookahead=True):
+            user_loop(3, lookahead)
             sync_all()
             n = max(3, min(a.steps, 8))
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
-            for _ in range(n):
-                lv_ = user_step()
+            lv_ = user_loop(n, lookahead)
             t1.record()
             sync_all()
             return max_over_ranks(t0.elapsed_time(t1)) / n, n, lv_
 
         u_ms, u_steps, lv = timed_user_steps()
-        # the same step with the plane term's triplets drawn on the device (same distribution, no numpy RNG on the host):
-        # the default above spends ~85 ms per step of host time in numpy's RNG to reproduce the reference's samples bit for bit
+        # the same step with the plane term's triplets drawn on the device (same distribution, no numpy RNG stream on the host):
+        # the default above reproduces the reference's samples bit for bit (C restatement of numpy's legacy choice + shuffle on
+        # numpy's own MT19937 state, ~25 ms per step on a worker thread, overlapped with the forward)
+        s_ms, _, _ = timed_user_steps(lookahead=False)
         crit = PlaneRecNetLoss(cfg, vnl_sampling="device")
         f_ms, _, _ = timed_user_steps()
         e2e = {"value": round(world * B / (u_ms / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,
                "steps": u_steps, "ms_per_step": round(u_ms, 3),
+               "no_lookahead": {"value": round(world * B / (s_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(s_ms, 3),
+                                "what": "same loop without the one-batch look-ahead: every step uploads its own batch and starts its loss "
+                                        "preparation right before its forward"},
                "device_sampling": {"value": round(world * B / (f_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(f_ms, 3),
                                    "what": "same step with PlaneRecNetLoss(vnl_sampling='device'): plane-term triplets from torch's device RNG "
                                            "(same distribution) instead of numpy's global RNG in the reference's call order"},
                "losses": {k: round(v, 5) for k, v in zip(("ins", "cat", "dpt", "pln", "lav"), lv)},
-               "path": "pinned host images + ground truth -> H2D -> net(x) [train mode, graphed fwd] -> planerecnet_b200.losses.PlaneRecNetLoss "
-                       "(device-side target assignment, kernel-backed dice/lava/focal/depth terms, host-side plane term) -> loss.backward() "
+               "path": "training loop with one batch of look-ahead: pinned host images + ground truth -> H2D (copy stream) -> net(x) "
+                       "[train mode, graphed fwd] -> planerecnet_b200.losses.PlaneRecNetLoss (crit.prepare(gts) at upload time: device-side target assignment + numpy-stream-exact triplet sampling on a worker thread; kernel-backed dice/lava/focal/depth terms, batched plane term) -> loss.backward() "
                        "[graphed bwd]" + (" -> NCCL all-reduce of the gradients" if world > 1 else "") + " -> D2H of the 5 loss terms"}
     except Exception as exc:
         e2e = {"value": None, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -185,6 +185,14 @@ int prn_upsample_mask_box(const float* seg, const int32_t* sel, void* masks_bool
  * (out byte i, bit j = mask byte 8 i + j); n_bool a multiple of 16.  8x fewer bytes over PCIe for the serving loop's D2H. */
 int prn_pack_mask_bits(const void* masks_bool, void* out_bits, int64_t n_bool, void* stream);
 
+/* HOST function (no device work): the triplet sampling of the plane surface-normal loss term, models/functions/vnl.py:48-53 —
+ *   p = np.random.choice(n, k, replace=True); np.random.shuffle(p)       `repeats` (= 3) times per region, region after region
+ * — restated on numpy's legacy MT19937 stream: mt_key624 / mt_pos are np.random.get_state()[1:3] and come back advanced (put them
+ * back with np.random.set_state), so the draws, and the global stream afterwards, are bit-identical to the reference's.
+ * out[j * out_stride + off_r + i] = i-th index of repeat j of region r, off_r = sum of k over the regions before r. */
+int prn_numpy_choice_shuffle(uint32_t* mt_key624, int32_t* mt_pos, const int64_t* n_of_region, const int64_t* k_of_region,
+                             int32_t n_regions, int32_t repeats, int32_t* out, int64_t out_stride);
+
 /* Greedy mask-NMS (models/functions/nms.py:53-80, selected by nms_type == 'mask', planerecnet.py:249-252) over the
  * score-sorted candidates of each image: inter fp32 [B][n][n] = mask intersections, area fp32 [B][n], labels int64 [B][n],
  * valid/keep uint8 [B][n].  keep[j] = valid[j] and no kept earlier candidate of the same label has IoU > thr with j. */

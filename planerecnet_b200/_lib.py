@@ -97,7 +97,7 @@ EXPORTS = [
     "prn_stem_im2col", "prn_stem_im2col_image", "prn_maxpool3x3s2", "prn_avgpool2x2", "prn_resize_bilinear", "prn_append_coord",
     "prn_groupnorm_apply", "prn_upsample2x_bilinear", "prn_mul", "prn_ppa_gather",
     "prn_nhwc_to_nchw_f32", "prn_nchw_f32_to_nhwc",
-    "prn_conv3x3_to1_reflect", "prn_conv3x3_to1_reflect_devbias", "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box", "prn_pack_mask_bits", "prn_mask_nms_greedy",
+    "prn_conv3x3_to1_reflect", "prn_conv3x3_to1_reflect_devbias", "prn_point_nms_sigmoid", "prn_mask_stats", "prn_upsample_mask_box", "prn_pack_mask_bits", "prn_mask_nms_greedy", "prn_numpy_choice_shuffle",
     "prn_conv2d_wgrad", "prn_conv2d_wgrad_plan", "prn_bn_finalize", "prn_bn_apply", "prn_bn_finalize_apply", "prn_chan_reduce", "prn_bn_bwd_apply",
     "prn_relu_bwd", "prn_add_strided", "prn_add_f32", "prn_add16", "prn_maxpool3x3s2_bwd", "prn_dcn_im2col",
     "prn_dcn_col2im_bwd", "prn_gn_bwd_reduce", "prn_gn_bwd_apply", "prn_avgpool2x2_bwd", "prn_upsample2x_bilinear_bwd",

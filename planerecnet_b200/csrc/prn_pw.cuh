@@ -28,6 +28,16 @@ __device__ __forceinline__ void load8(const T* p, float* f) {
   }
 }
 template <typename T>
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = Pack2<T>::unpack(w[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+template <typename T>
 __device__ __forceinline__ void store8(T* p, const float* f) {
   uint4 o;
   o.x = Pack2<T>::pack(f[0], f[1]);

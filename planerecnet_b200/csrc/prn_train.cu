@@ -25,16 +25,6 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
-  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 v = Pack2<T>::unpack(w[j]);
-    f[2 * j] = v.x;
-    f[2 * j + 1] = v.y;
-  }
-}
 
 // Channel-stationary threads: a thread keeps its 8 channels (scale/shift in registers) and walks rows with a stride of
 // (total threads / (C/8)); total thread count is a multiple of C/8 (chan_grid).  One 16-byte load per operand and row.
@@ -338,49 +328,89 @@ __global__ void add16_kernel(const T* __restrict__ a, const T* __restrict__ b, T
 // ---------------------------------------------------------------- MaxPool2d(3, 2, 1) backward (models/backbone.py:104)
 // Gather form, deterministic: an input pixel receives the gradient of every window in which it is the FIRST maximum
 // in (dy, dx) scan order (torch's strict `>` update rule), so ties resolve like the reference.
+// One thread owns a 2x2 block of input pixels (8 channels): the four windows that can select them — (k, l), (k, l+1), (k+1, l),
+// (k+1, l+1) — cover a 5x5 input patch, scanned once in row-major order (= every window's own scan order): 25 loads for four
+// input pixels instead of 2.25 windows x 9 loads for each one (the per-pixel form ran at 1/13 of the HBM rate).
 template <typename T>
-__global__ void maxpool3s2_bwd_kernel(const T* __restrict__ in, const T* __restrict__ dout, T* __restrict__ din, int B, int H,
-                                      int W, int C) {
+__global__ void __launch_bounds__(kPwThreads) maxpool3s2_bwd_kernel(const T* __restrict__ in, const T* __restrict__ dout,
+                                                                  T* __restrict__ din, int B, int H, int W, int C) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, cv = C / 8;
-  const long long total = static_cast<long long>(B) * H * W * cv;
+  const int Hb = (H + 1) / 2, Wb = (W + 1) / 2;
+  const long long total = static_cast<long long>(B) * Hb * Wb * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % cv) * 8;
     const long long m = i / cv;
-    const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
-    const int b = static_cast<int>(m / (static_cast<long long>(W) * H));
+    const int l = static_cast<int>(m % Wb), k = static_cast<int>((m / Wb) % Hb);
+    const int b = static_cast<int>(m / (static_cast<long long>(Wb) * Hb));
     const T* img = in + static_cast<long long>(b) * H * W * C + c;
-    float acc[8];
+    float best[2][2][8];
+    int arg[2][2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    const int ho_hi = min((y + 1) >> 1, Ho - 1), wo_hi = min((x + 1) >> 1, Wo - 1);
-    for (int ho = y >> 1; ho <= ho_hi; ++ho) {
-      for (int wo = x >> 1; wo <= wo_hi; ++wo) {
-        const int my = (y - (2 * ho - 1)) * 3 + (x - (2 * wo - 1));   // my position in the window's scan order
-        float best[8];
-        int arg[8];
+    for (int wy = 0; wy < 2; ++wy)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = -1; }
-        for (int dy = 0; dy < 3; ++dy) {
-          const int yy = 2 * ho - 1 + dy;
-          if (yy < 0 || yy >= H) continue;
-          for (int dx = 0; dx < 3; ++dx) {
-            const int xx = 2 * wo - 1 + dx;
-            if (xx < 0 || xx >= W) continue;
-            float f[8];
-            load8(img + (static_cast<long long>(yy) * W + xx) * C, f);
+      for (int wx = 0; wx < 2; ++wx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[wy][wx][j] = -INFINITY; arg[wy][wx][j] = -1; }
+#pragma unroll
+    for (int py = -1; py <= 3; ++py) {
+      const int yy = 2 * k + py;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int px = -1; px <= 3; ++px) {
+        const int xx = 2 * l + px;
+        if (xx < 0 || xx >= W) continue;
+        float f[8];
+        load8(img + (static_cast<long long>(yy) * W + xx) * C, f);
+#pragma unroll
+        for (int wy = 0; wy < 2; ++wy) {
+          const int dy = py - (2 * wy - 1);
+          if (dy < 0 || dy > 2) continue;
+#pragma unroll
+          for (int wx = 0; wx < 2; ++wx) {
+            const int dx = px - (2 * wx - 1);
+            if (dx < 0 || dx > 2) continue;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (f[j] > best[j]) { best[j] = f[j]; arg[j] = dy * 3 + dx; }
+              if (f[j] > best[wy][wx][j]) { best[wy][wx][j] = f[j]; arg[wy][wx][j] = dy * 3 + dx; }
           }
         }
-        float g[8];
-        load8(dout + ((static_cast<long long>(b) * Ho + ho) * Wo + wo) * C + c, g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += arg[j] == my ? g[j] : 0.f;
       }
     }
-    store8(din + m * C + c, acc);
+    float g[2][2][8];
+#pragma unroll
+    for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+      for (int wx = 0; wx < 2; ++wx) {
+        const int ho = k + wy, wo = l + wx;
+        if (ho < Ho && wo < Wo) load8(dout + ((static_cast<long long>(b) * Ho + ho) * Wo + wo) * C + c, g[wy][wx]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { g[wy][wx][j] = 0.f; arg[wy][wx][j] = -1; }
+        }
+      }
+#pragma unroll
+    for (int iy = 0; iy < 2; ++iy) {
+      const int y = 2 * k + iy;
+      if (y >= H) continue;
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) {
+        const int x = 2 * l + ix;
+        if (x >= W) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+        for (int wy = 0; wy <= iy; ++wy)            // even rows / columns lie in one window only, odd ones in two
+#pragma unroll
+          for (int wx = 0; wx <= ix; ++wx) {
+            const int my = (iy - (2 * wy - 1)) * 3 + (ix - (2 * wx - 1));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += arg[wy][wx][j] == my ? g[wy][wx][j] : 0.f;
+          }
+        store8(din + ((static_cast<long long>(b) * H + y) * W + x) * C + c, acc);
+      }
+    }
   }
 }
 
@@ -633,7 +663,7 @@ int prn_maxpool3x3s2_bwd(const void* in16, const void* dout16, void* din16, int3
                          int32_t dtype, void* stream) {
   PRN_REQUIRE(in16 && dout16 && din16 && batch > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "maxpool_bwd: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long work = static_cast<long long>(batch) * h * w * (c / 8);
+  const long long work = static_cast<long long>(batch) * ((h + 1) / 2) * ((w + 1) / 2) * (c / 8);
   PRN_DISPATCH(dtype,
                (maxpool3s2_bwd_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(in16), static_cast<const __nv_bfloat16*>(dout16), static_cast<__nv_bfloat16*>(din16), batch, h, w, c)),
                (maxpool3s2_bwd_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(in16), static_cast<const __half*>(dout16), static_cast<__half*>(din16), batch, h, w, c)));
@@ -734,7 +764,7 @@ struct PackRec {
   int kind;            // 0 forward operand (pack_fwd_kernel), 1 input-gradient operand (pack_dgrad_kernel)
   int cout, cin, kk;
   int a, b, c, d, e, f, g;   // fwd: cpad_tot, nsplit, s0.lo, s0.real, s0.pad, s1.lo, s1.real (s1.pad = cpad_tot - s0.pad)
-                              // dgrad: lo, nreal, cout_pad
+                              // dgrad: lo, nreal, cout_pad, rows (work row = first of 8 rows)
 };
 
 template <typename T>
@@ -767,13 +797,19 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackRec* __restri
       o[i] = static_cast<T>(v);
     }
   } else {
-    const int lo = r.a, nreal = r.b, cout_pad = r.c;
-    T* o = static_cast<T*>(r.out) + static_cast<long long>(n) * kk * cout_pad;
+    // a block packs 8 consecutive input-channel rows [n, n + 8): a thread's 8 source words w[oc][lo + n .. n + 7][tap] are
+    // kk floats apart (one 32-byte sector for a 1x1 kernel), where one row per block read 4 bytes of every sector
+    const int lo = r.a, nreal = r.b, cout_pad = r.c, rows = r.d;
+    const int nq = min(8, rows - n);
     for (int i = threadIdx.x; i < kk * cout_pad; i += blockDim.x) {
       const int tap = i / cout_pad, oc = i - tap * cout_pad;
-      float v = 0.f;
-      if (n < nreal && oc < r.cout) v = __ldg(r.w + (static_cast<long long>(oc) * r.cin + lo + n) * kk + (kk - 1 - tap));
-      o[i] = static_cast<T>(v);
+      const float* src = r.w + (static_cast<long long>(oc) * r.cin + lo + n) * kk + (kk - 1 - tap);
+      T* o = static_cast<T*>(r.out) + static_cast<long long>(n) * kk * cout_pad + i;
+      for (int q = 0; q < nq; ++q) {
+        float v = 0.f;
+        if (n + q < nreal && oc < r.cout) v = __ldg(src + q * kk);
+        o[static_cast<long long>(q) * kk * cout_pad] = static_cast<T>(v);
+      }
     }
   }
 }

@@ -239,10 +239,10 @@ __global__ void resize_bilinear_bwd_kernel(const T* __restrict__ dout, float* __
 // dpad [B, He+2, We+2, ld] = gradient w.r.t. the padded (and upsampled) tensor, He = h*up, We = w*up (the "full"
 // correlation of dY with the flipped weights).  din[b,y,x] = sum over effective rows ye in {up*y .. up*y+up-1} of
 // dpad rows {ye+1} + {0 if ye == 1} + {He+1 if ye == He-2}; same along x.  Gather form.
-template <typename T>
-__global__ void reflect_fold_kernel(const T* __restrict__ dpad, T* __restrict__ din, int B, int h, int w, int C, int ld, int up,
+template <typename T, int kUp>
+__global__ void reflect_fold_kernel(const T* __restrict__ dpad, T* __restrict__ din, int B, int h, int w, int C, int ld,
                                     int accumulate) {
-  const int cv = C / 8, He = h * up, We = w * up, Hp = He + 2, Wp = We + 2;
+  const int cv = C / 8, He = h * kUp, We = w * kUp, Hp = He + 2, Wp = We + 2;
   const long long total = static_cast<long long>(B) * h * w * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -250,31 +250,58 @@ __global__ void reflect_fold_kernel(const T* __restrict__ dpad, T* __restrict__ 
     const long long m = i / cv;
     const int x = static_cast<int>(m % w), y = static_cast<int>((m / w) % h);
     const int b = static_cast<int>(m / (static_cast<long long>(w) * h));
-    int rows[6], cols[6], nr = 0, ncol = 0;
-    for (int ye = y * up; ye < y * up + up; ++ye) {
-      rows[nr++] = ye + 1;
-      if (ye == 1) rows[nr++] = 0;
-      if (ye == He - 2) rows[nr++] = He + 1;
-    }
-    for (int xe = x * up; xe < x * up + up; ++xe) {
-      cols[ncol++] = xe + 1;
-      if (xe == 1) cols[ncol++] = 0;
-      if (xe == We - 2) cols[ncol++] = We + 1;
-    }
     float acc[8];
-    if (accumulate) load8(din + m * C + c, acc);
-    else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    }
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const T* img = dpad + static_cast<long long>(b) * Hp * Wp * ld + c;
-    for (int r = 0; r < nr; ++r)
-      for (int q = 0; q < ncol; ++q) {
+    // the kUp x kUp interior taps first (unconditional: their loads are all in flight together), then the rare border folds;
+    // no index arrays (dynamically indexed ones live in local memory)
+    uint4 q[kUp][kUp];
+#pragma unroll
+    for (int dy = 0; dy < kUp; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < kUp; ++dx)
+        q[dy][dx] = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<long long>(y * kUp + dy + 1) * Wp + (x * kUp + dx + 1)) * ld));
+    uint4 prev = make_uint4(0, 0, 0, 0);
+    if (accumulate) prev = __ldg(reinterpret_cast<const uint4*>(din + m * C + c));
+#pragma unroll
+    for (int dy = 0; dy < kUp; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < kUp; ++dx) {
         float g[8];
-        load8(img + (static_cast<long long>(rows[r]) * Wp + cols[q]) * ld, g);
+        unpack8<T>(q[dy][dx], g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += g[j];
       }
+    if (accumulate) {
+      float g[8];
+      unpack8<T>(prev, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+    const int ye0 = y * kUp, xe0 = x * kUp;
+    const bool row_edge = ye0 <= 1 || ye0 + kUp - 1 >= He - 2, col_edge = xe0 <= 1 || xe0 + kUp - 1 >= We - 2;
+    if (row_edge || col_edge) {
+      auto add = [&](int r, int col) {
+        float g[8];
+        load8(img + (static_cast<long long>(r) * Wp + col) * ld, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g[j];
+      };
+      for (int dy = 0; dy < kUp; ++dy) {
+        const int ye = ye0 + dy;
+        const int er0 = ye == 1 ? 0 : -1, er1 = ye == He - 2 ? He + 1 : -1;      // extra (reflected) rows of this row
+        for (int dx = 0; dx < kUp; ++dx) {
+          const int xe = xe0 + dx;
+          const int ec0 = xe == 1 ? 0 : -1, ec1 = xe == We - 2 ? We + 1 : -1;
+          // (row set) x (column set) minus the interior tap already taken
+          if (ec0 >= 0) add(ye + 1, ec0);
+          if (ec1 >= 0) add(ye + 1, ec1);
+          if (er0 >= 0) { add(er0, xe + 1); if (ec0 >= 0) add(er0, ec0); if (ec1 >= 0) add(er0, ec1); }
+          if (er1 >= 0) { add(er1, xe + 1); if (ec0 >= 0) add(er1, ec0); if (ec1 >= 0) add(er1, ec1); }
+        }
+      }
+    }
     store8(din + m * C + c, acc);
   }
 }
@@ -386,9 +413,11 @@ int prn_reflect_fold(const void* dpad16, void* din16, int32_t batch, int32_t h, 
                   (upsample == 1 || upsample == 2) && h * upsample >= 3 && w * upsample >= 3, "reflect_fold: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long work = static_cast<long long>(batch) * h * w * (c / 8);
-  PRN_DISPATCH(dtype,
-               (reflect_fold_kernel<__nv_bfloat16><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(dpad16), static_cast<__nv_bfloat16*>(din16), batch, h, w, c, ld_dpad, upsample, accumulate)),
-               (reflect_fold_kernel<__half><<<pw_grid(work), kPwThreads, 0, st>>>(static_cast<const __half*>(dpad16), static_cast<__half*>(din16), batch, h, w, c, ld_dpad, upsample, accumulate)));
+  const int grid = pw_grid(work);
+#define PRN_FOLD(T_, UP_) reflect_fold_kernel<T_, UP_><<<grid, kPwThreads, 0, st>>>(static_cast<const T_*>(dpad16), static_cast<T_*>(din16), batch, h, w, c, ld_dpad, accumulate)
+  if (upsample == 2) PRN_DISPATCH(dtype, (PRN_FOLD(__nv_bfloat16, 2)), (PRN_FOLD(__half, 2)));
+  else PRN_DISPATCH(dtype, (PRN_FOLD(__nv_bfloat16, 1)), (PRN_FOLD(__half, 1)));
+#undef PRN_FOLD
   PRN_LAUNCH_CHECK();
 }
 

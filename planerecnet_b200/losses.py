@@ -194,13 +194,15 @@ class _InsLava(torch.autograd.Function):
         loss_ins = w_dice * dice.sum() / n_total
         nb_t = torch.tensor(n_b, dtype=torch.float32, device="cpu").to(dev, non_blocking=True)
         elig = (nb_t > 0) & (gsum > 0)
-        n_elig = int(elig.sum())
+        # number of eligible images stays on the device: an int() here would stall the host until the network's forward has
+        # finished (every host sync between net(x) and loss.backward() is a bubble on the GPU later)
+        n_elig = elig.sum().to(torch.float32).clamp(min=1.0)
         per_img = torch.where(elig, (lv * valid).sum(1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
-        loss_lav = w_lava * per_img.sum() / n_elig if n_elig else torch.zeros((), device=dev)
+        loss_lav = w_lava * per_img.sum() / n_elig                      # no eligible image: per_img == 0 -> 0
         # d(loss)/d{a, b, lv} per row
         ca = torch.where(valid, -w_dice / n_total * 2 / den, torch.zeros_like(a))
         cb = torch.where(valid, w_dice / n_total * 2 * a / (den * den), torch.zeros_like(a))
-        cl_img = torch.where(elig, w_lava / max(n_elig, 1) / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
+        cl_img = torch.where(elig, w_lava / n_elig / (gsum * nb_t).clamp(min=1e-30), torch.zeros_like(gsum))
         cl = cl_img[:, None] * valid
         ctx.be, ctx.targets, ctx.counts, ctx.shapes = be, targets, counts, (B, Cc, fh, fw, n, [k.shape for k in kernel_preds])
         ctx.idx_views = idx_views
@@ -216,8 +218,10 @@ class _InsLava(torch.autograd.Function):
         dev = seg.device
         coef = torch.stack([ca * g_ins, cb * g_ins, cl * g_lav], -1).reshape(B * n, 3)
         # power-of-two scale that puts the largest possible |dx| near 2^12 (16-bit storage of the gradient rows)
-        bound = float(((coef[:, 0].abs() + 2 * coef[:, 1].abs()).max() + coef[:, 2].abs().max() * gw.max()) * 0.25)
-        scale = 2.0 ** math.floor(math.log2(4096.0 / bound)) if bound > 0 and math.isfinite(bound) else 1.0
+        # (computed on the device: no host round trip in the middle of the backward)
+        bound = ((coef[:, 0].abs() + 2 * coef[:, 1].abs()).max() + coef[:, 2].abs().max() * gw.max()) * 0.25
+        usable = (bound > 0) & torch.isfinite(bound)
+        scale = torch.where(usable, torch.exp2(torch.floor(torch.log2(4096.0 / bound.clamp(min=1e-38)))), torch.ones_like(bound))
         coef = (coef * scale).contiguous()
         dx16 = be.row_bwd(seg, tgt.view(B * n, P), gw, coef, n).view(B, n, P)        # scaled gradient of the pre-sigmoid rows
         # w.r.t. the selected kernels: dK[b] = dX[b] (n x P) . mask[b] (P x C)
@@ -345,7 +349,9 @@ class _PlaneNormalBatched:
 
       sampling="numpy"   with numpy's GLOBAL RNG in exactly the reference's call order (image by image, plane by plane, then the
                          non-planar rest: `choice` + `shuffle`, three times, vnl.py:48-53) — bit-identical triplets, hence loss
-                         values and gradients equal to the reference's for a given `np.random.seed`; ~1.5 ms of host time per plane;
+                         values and gradients equal to the reference's for a given `np.random.seed`.  The draws are made by a C
+                         restatement of numpy's legacy choice + shuffle on numpy's own MT19937 state (prn_numpy_choice_shuffle;
+                         "numpy_py" makes the literal numpy calls instead: 3x slower, the checker of the C path);
       sampling="device"  with torch's device RNG (i.i.d. uniform indices: the reference's shuffle of i.i.d. draws is a
                          statistical no-op) — same distribution, no host work;
 
@@ -353,11 +359,11 @@ class _PlaneNormalBatched:
     |cos| against the plane normal resp. the ground-truth normals, worst-75 % tail per region) is evaluated for all triplets of
     all regions at once; the per-region sort of the tail is one global sort on the composite key (region, loss)."""
 
-    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4, sampling="numpy"):
-        assert sampling in ("numpy", "device")
-        self.size, self.ratio, self.delta_z, self.sampling = size, sample_ratio, delta_z, sampling
+    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4, sampling="numpy", threaded=True):
+        assert sampling in ("numpy", "numpy_py", "device")
+        self.size, self.ratio, self.delta_z, self.sampling, self.threaded = size, sample_ratio, delta_z, sampling, threaded
         self._grid = {}
-        self._pinned = None
+        self._pinned, self._pinned_ev = None, None
 
     def _uv(self, dev):
         if dev not in self._grid:
@@ -375,40 +381,66 @@ class _PlaneNormalBatched:
         y = v * d.abs() / fy
         return torch.stack([x, y, d], -1).reshape(-1, 3)
 
-    def _sample_host(self, counts, is_rest):
-        """Triplet indices of every region, drawn in the reference's RNG call order.  Returns (int32 array [3, T], per-region k)."""
-        import numpy as np
-        ks, parts = [], [[], [], []]
+    def _region_ks(self, counts, is_rest):
+        """k = int(n * ratio) per region; 0 for an empty rest region (vnl.py:137: the rest term only exists when there are
+        non-planar pixels)."""
+        ks = []
         for c, rest in zip(counts, is_rest):
-            if rest and c == 0:                      # vnl.py:137: the rest term only exists when there are non-planar pixels
-                ks.append(0)
-                continue
             assert c <= self.size[0] * self.size[1]
-            k = int(c * self.ratio)
-            ks.append(k)
+            ks.append(0 if (rest and c == 0) else int(c * self.ratio))
+        return ks
+
+    def _sample_host_numpy(self, counts, is_rest, out):
+        """The reference's own calls (np.random.choice + np.random.shuffle, three times per region): ~30 ns per index.  Kept as
+        the checker of the C restatement below (tests/test_plane_normal_cpu.py) and selectable with sampling="numpy_py"."""
+        import numpy as np
+        ks = self._region_ks(counts, is_rest)
+        off = 0
+        for c, k in zip(counts, ks):
+            if k == 0 and c == 0:
+                continue                                 # the reference never reaches choice() for such a region
             for j in range(3):
                 p = np.random.choice(c, k, replace=True)
                 np.random.shuffle(p)
-                parts[j].append(p)
-        T = sum(ks)
-        out = np.empty((3, T), dtype=np.int32)
-        for j in range(3):
-            if parts[j]:
-                np.concatenate(parts[j], out=out[j], casting="unsafe")
-        return out, ks
+                out[j, off:off + k] = p
+            off += k
+        return ks
 
-    def __call__(self, depth_up, gt_instances, gt_depths):
-        """depth_up [B,1,H,W] (x2 bilinear of the prediction), gt_depths [B,1,H,W].  Returns the per-image losses [B] (float64; NaN
-        where the reference yields NaN)."""
+    def _sample_host(self, counts, is_rest, out):
+        """Triplet indices of every region, drawn from numpy's GLOBAL RNG stream in the reference's call order, by the C
+        restatement of legacy choice + shuffle (prn_numpy_choice_shuffle, csrc/prn_hostrng.cu): same indices, same stream
+        position afterwards, ~3x less host time.  `out`: int32 numpy array [3, >= sum k].  Returns the per-region k."""
+        import ctypes as C
         import numpy as np
-        import torch.nn.functional as F
-        B, _, H, W = depth_up.shape
-        assert (H, W) == tuple(self.size), "the plane term assumes the configured image size (losses.py:50)"
+        from . import _lib as L
+        ks = self._region_ks(counts, is_rest)
+        st = np.random.get_state()
+        assert st[0] == "MT19937"
+        key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        pos = C.c_int32(int(st[2]))
+        # regions with n == 0 draw nothing in the reference either (k == 0)
+        n_arr = np.asarray(counts, dtype=np.int64)
+        k_arr = np.asarray(ks, dtype=np.int64)
+        assert out.dtype == np.int32 and out.ndim == 2 and out.strides[1] == 4
+        L.check(L.lib().prn_numpy_choice_shuffle(key.ctypes.data_as(C.c_void_p), C.byref(pos), n_arr.ctypes.data_as(C.c_void_p),
+                                                 k_arr.ctypes.data_as(C.c_void_p), len(ks), 3, out.ctypes.data_as(C.c_void_p),
+                                                 out.strides[0] // 4), "prn_numpy_choice_shuffle")
+        np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+        return ks
+
+    def prepare(self, gt_instances):
+        """Everything of the term that depends on the ground truth only: the region list, the pixel count of every region (the
+        one host sync of this term) and — for the numpy-exact sampling — the triplet draws, started on a worker thread (the C
+        sampler releases the GIL; ~25 ms per batch of 8 that now overlap the network's forward and the other loss terms).
+        No np.random call may be made by the caller between prepare() and the __call__ that consumes it (the worker owns the
+        global stream in between).  Returns an opaque dict for __call__(..., prep=...)."""
+        H, W = self.size
         HW = H * W
-        dev = depth_up.device
+        dev = gt_instances[0]["masks"].device
         # ---- regions in the reference's order: per image its planes, then the non-planar rest
         stacks, reg_img, reg_rest, n_planes = [], [], [], []
         for b, g in enumerate(gt_instances):
+            assert tuple(g["masks"].shape[-2:]) == (H, W), "the plane term assumes the configured image size (losses.py:50)"
             m = g["masks"].bool().reshape(-1, HW)
             stacks += [m, torch.logical_not(m.any(0, keepdim=True))]
             n = m.shape[0]
@@ -416,23 +448,73 @@ class _PlaneNormalBatched:
             reg_img += [b] * (n + 1)
             reg_rest += [False] * n + [True]
         member = torch.cat(stacks, 0)                                   # [R, HW] bool
-        R = member.shape[0]
         counts_dev = member.sum(1)
         counts = counts_dev.tolist()                                    # the one host sync of this term
-        # ---- triplet indices
-        if self.sampling == "numpy":
-            idx_np, ks = self._sample_host(counts, reg_rest)
-            T = idx_np.shape[1]
-            if self._pinned is None or self._pinned.shape[1] < T:
-                self._pinned = torch.empty(3, max(T, 1 << 20), dtype=torch.int32, device="cpu").pin_memory() if dev.type == "cuda" else None
-            if self._pinned is not None:
-                self._pinned[:, :T].copy_(torch.from_numpy(idx_np))
-                idx = self._pinned[:, :T].to(dev, non_blocking=True).long()
+        prep = dict(key=tuple(id(g["masks"]) for g in gt_instances), keep=[g["masks"] for g in gt_instances], R=member.shape[0],
+                    counts_dev=counts_dev, counts=counts, reg_img=reg_img, reg_rest=reg_rest, n_planes=n_planes, dev=dev,
+                    thread=None, ks=None, error=None)
+        if self.sampling in ("numpy", "numpy_py"):
+            T_max = sum(int(c * self.ratio) for c in counts)
+            cuda = dev.type == "cuda"
+            if self._pinned is None or self._pinned.shape[1] < T_max:
+                self._pinned = torch.empty(3, max(T_max, 1 << 20), dtype=torch.int32, device="cpu")
+                if cuda:
+                    self._pinned = self._pinned.pin_memory()
+            elif cuda and self._pinned_ev is not None:
+                # the previous step's upload reads this buffer asynchronously: it has long finished (a whole backward lies in
+                # between), but make that explicit before overwriting it
+                self._pinned_ev.synchronize()
+            sampler = self._sample_host if self.sampling == "numpy" else self._sample_host_numpy
+            out = self._pinned.numpy()                                   # written straight into the (pinned) staging buffer
+
+            def work():
+                try:
+                    prep["ks"] = sampler(counts, reg_rest, out)
+                except BaseException as exc:                             # re-raised by the consumer
+                    prep["error"] = exc
+
+            if self.sampling == "numpy" and self.threaded:
+                import threading
+                prep["thread"] = threading.Thread(target=work, name="prn-vnl-sampler", daemon=True)
+                prep["thread"].start()
             else:
-                idx = torch.from_numpy(idx_np).long()
+                work()
         else:
-            ks = [0 if (rest and c == 0) else int(c * self.ratio) for c, rest in zip(counts, reg_rest)]
-            T = sum(ks)
+            prep["ks"] = self._region_ks(counts, reg_rest)
+        # pixel lists of the regions (row-major inside a region = the order of `pts[mask]`); nonzero() is a host sync, which is
+        # why it lives here (ground truth only) and not after the forward has been enqueued
+        img_of = torch.tensor(reg_img, dtype=torch.int64, device="cpu").to(dev, non_blocking=True)
+        nz = member.nonzero()
+        prep["gpix"] = img_of[nz[:, 0]] * HW + nz[:, 1]
+        prep["base"] = torch.cumsum(counts_dev, 0) - counts_dev          # first entry of each region in gpix
+        prep["rest_rows"] = torch.tensor([i for i, r in enumerate(reg_rest) if r], dtype=torch.int64,
+                                         device="cpu").to(dev, non_blocking=True)   # one rest region per image, in image order
+        return prep
+
+    def __call__(self, depth_up, gt_instances, gt_depths, prep=None):
+        """depth_up [B,1,H,W] (x2 bilinear of the prediction), gt_depths [B,1,H,W].  Returns the per-image losses [B] (float64; NaN
+        where the reference yields NaN).  prep: the result of prepare(gt_instances) when the caller made it ahead of time."""
+        import numpy as np
+        import torch.nn.functional as F
+        B, _, H, W = depth_up.shape
+        assert (H, W) == tuple(self.size), "the plane term assumes the configured image size (losses.py:50)"
+        HW = H * W
+        dev = depth_up.device
+        if prep is None or prep["key"] != tuple(id(g["masks"]) for g in gt_instances):
+            prep = self.prepare(gt_instances)
+        if prep["thread"] is not None:
+            prep["thread"].join()
+            prep["thread"] = None
+        if prep["error"] is not None:
+            raise prep["error"]
+        R, counts_dev, reg_img, reg_rest, n_planes, ks = (prep[k] for k in ("R", "counts_dev", "reg_img", "reg_rest", "n_planes", "ks"))
+        T = sum(ks)
+        # ---- triplet indices
+        if self.sampling in ("numpy", "numpy_py"):
+            idx = self._pinned[:, :T].to(dev, non_blocking=True).long()
+            if dev.type == "cuda":
+                self._pinned_ev = torch.cuda.Event()
+                self._pinned_ev.record()
         # the per-region host tables in ONE upload: k, image of the region, rest flag
         tab = torch.tensor([ks, reg_img, [int(r) for r in reg_rest]], dtype=torch.int64, device="cpu").to(dev, non_blocking=True)
         ks_t, img_of, is_rest_r = tab[0], tab[1], tab[2].bool()
@@ -441,10 +523,7 @@ class _PlaneNormalBatched:
         if self.sampling == "device":
             idx = (torch.rand(3, T, device=dev, dtype=torch.float64) * counts_t[region].double()).long()
             idx = torch.minimum(idx, (counts_t[region] - 1).clamp(min=0))
-        # pixel lists of the regions (row-major inside a region = the order of `pts[mask]`)
-        nz = member.nonzero()
-        gpix = img_of[nz[:, 0]] * HW + nz[:, 1]
-        base = torch.cumsum(counts_t, 0) - counts_t                      # first entry of each region in gpix
+        gpix, base = prep["gpix"], prep["base"]
         P = gpix[(base[region][None, :] + idx).reshape(-1)].reshape(3, T)                              # global pixel of every point
         # ---- point clouds (vnl.py:20-38)
         fx = torch.stack([g["k_matrix"][0, 0] for g in gt_instances]).to(device=dev, dtype=torch.float32)[:, None, None]
@@ -456,16 +535,21 @@ class _PlaneNormalBatched:
         g_gt = gt_pts[P].permute(1, 2, 0)
         g_test = torch.where(is_rest_t[:, None, None], g_gt, g_pred)     # planes are tested on the prediction, the rest on the GT
         # ---- vnl.py:56-98: usable triplets
-        diff = torch.stack([g_test[:, :, 1] - g_test[:, :, 0], g_test[:, :, 2] - g_test[:, :, 0], g_test[:, :, 2] - g_test[:, :, 1]], 2)
-        q = diff.permute(0, 2, 1)
-        qn = q.norm(2, dim=2)
-        cosm = (torch.bmm(q, diff) / (torch.bmm(qn.unsqueeze(2), qn.unsqueeze(1)) + 1e-8)).reshape(T, -1)
-        colinear = ((cosm > 0.985) | (cosm < -0.985)).sum(1) > 3
-        in_front = (g_test[:, 2, :] > self.delta_z).sum(1) == 3
-        dd = torch.where(is_rest_t, 0.1, 0.005).to(diff.dtype)[:, None]
-        near = (((diff[:, 0, :].abs() < dd).sum(1) > 0) & ((diff[:, 1, :].abs() < dd).sum(1) > 0) &
-                ((diff[:, 2, :].abs() < dd).sum(1) > 0))
-        keep = in_front & ~(near | colinear)
+        # (a selection mask: no gradient flows through it.  The 3x3 products are written out element-wise — torch.bmm with
+        # 7e5 batches of 3x3 matrices runs as 36 SIMT sgemm launches of 32x32 tiles, 5 ms per step)
+        with torch.no_grad():
+            gt_ = g_test.detach()
+            diff = torch.stack([gt_[:, :, 1] - gt_[:, :, 0], gt_[:, :, 2] - gt_[:, :, 0], gt_[:, :, 2] - gt_[:, :, 1]], 2)   # [T, xyz, 3]
+            q = diff.permute(0, 2, 1)                                    # [T, 3, xyz]
+            qn = q.norm(2, dim=2)                                        # [T, 3]
+            dots = (q[:, :, None, :] * q[:, None, :, :]).sum(3)          # q . diff: [T, 3, 3]
+            cosm = (dots / (qn[:, :, None] * qn[:, None, :] + 1e-8)).reshape(T, -1)
+            colinear = ((cosm > 0.985) | (cosm < -0.985)).sum(1) > 3
+            in_front = (gt_[:, 2, :] > self.delta_z).sum(1) == 3
+            dd = torch.where(is_rest_t, 0.1, 0.005).to(diff.dtype)[:, None]
+            near = (((diff[:, 0, :].abs() < dd).sum(1) > 0) & ((diff[:, 1, :].abs() < dd).sum(1) > 0) &
+                    ((diff[:, 2, :].abs() < dd).sum(1) > 0))
+            keep = in_front & ~(near | colinear)
 
         def normals(g):
             nv = torch.cross(g[:, :, 1] - g[:, :, 0], g[:, :, 2] - g[:, :, 0], dim=1)
@@ -492,20 +576,28 @@ class _PlaneNormalBatched:
         order = torch.argsort(key)
         pos = torch.empty_like(order)
         pos[order] = torch.arange(T, device=dev)
-        n_keep = torch.zeros(R, dtype=torch.long, device=dev).index_add_(0, region, keep.long())
+        # per-region sums: T ~ 7e5 values into R ~ 60 rows.  index_add_ straight into [R] serialises on 60 addresses (3 ms per
+        # step); spread every region over 128 slots first and fold the slots afterwards
+        slots = 128
+        slot_of = region * slots + (torch.arange(T, device=dev) & (slots - 1))
+
+        def region_sum(values, dtype):
+            return torch.zeros(R * slots, dtype=dtype, device=dev).index_add_(0, slot_of, values).view(R, slots).sum(1)
+
+        n_keep = region_sum(keep.long(), torch.long)
         start = torch.cumsum(n_keep, 0) - n_keep
         drop = n_keep // 4                                                # int(n * 0.25)
         incl = keep & ((pos - start[region]) >= drop[region])
         contrib = torch.where(incl & ~torch.isnan(loss_t), loss_t, torch.zeros_like(loss_t))
         # the rest regions' tail is a float32 sum in the reference: accumulate it in float32, the planes' in float64
-        sum_plane = torch.zeros(R, dtype=torch.float64, device=dev).index_add_(0, region, torch.where(is_rest_t, 0.0, contrib))
-        sum_rest = torch.zeros(R, dtype=torch.float32, device=dev).index_add_(0, region, torch.where(is_rest_t, contrib, 0.0).float())
+        sum_plane = region_sum(torch.where(is_rest_t, 0.0, contrib), torch.float64)
+        sum_rest = region_sum(torch.where(is_rest_t, contrib, 0.0).float(), torch.float32)
         den = (n_keep - drop).double()
         loss_r = torch.where(is_rest_r, sum_rest.double() / den.float().double(), sum_plane / den)       # 0 / 0 -> NaN like the reference
         # ---- per image (vnl.py:119-165)
         total = torch.zeros(B, dtype=torch.float64, device=dev).index_add_(0, img_of, torch.where(is_rest_r, 0.0, loss_r))
         npl = torch.tensor(n_planes, dtype=torch.float64, device="cpu").to(dev, non_blocking=True)
-        rest_rows = is_rest_r.nonzero().flatten()                          # one rest region per image, in image order
+        rest_rows = prep["rest_rows"]
         rest_used = (counts_t[rest_rows] > 0) & (n_keep[rest_rows] > 0)
         with_rest = (total + torch.where(rest_used, loss_r[rest_rows], torch.zeros_like(total))) / (npl + 1)
         return torch.where(rest_used, with_rest, total / npl)
@@ -520,8 +612,8 @@ class PlaneRecNetLoss(torch.nn.Module):
 
     def __init__(self, cfg=None, backend=None, vnl_sampling="numpy"):
         """vnl_sampling: 'numpy' (default) draws the plane term's triplets with numpy's global RNG in the reference's call order
-        (bit-identical samples for a given np.random.seed; ~1.5 ms of host time per plane), 'device' draws the same distribution
-        with torch's device RNG (no host work)."""
+        (bit-identical samples for a given np.random.seed; C restatement of numpy's legacy choice + shuffle, ~25 ms per batch of 8
+        on a worker thread), 'device' draws the same distribution with torch's device RNG (no host work)."""
         super().__init__()
         if cfg is None:
             from .config import cfg as _cfg
@@ -538,14 +630,106 @@ class PlaneRecNetLoss(torch.nn.Module):
         self.backend = backend
         self.vnl = _PlaneNormal((480, 640))                                  # per-plane formulation (kept as the readable mirror of vnl.py)
         self.vnl_batched = _PlaneNormalBatched((480, 640), sampling=vnl_sampling)
+        self._prep, self._side = None, None
+
+    def prepare(self, gt_instances, feat_hw=None, background=None):
+        """The ground-truth-only part of a step — SOLOv2 target assignment and the plane term's region counts, pixel lists and
+        triplet sampling — started BEFORE the network's forward is enqueued (or, prefetching, for the NEXT batch before this
+        step's backward):
+
+            crit.prepare(gts); outs = net(x); losses = crit(net, *outs, gts, gt_depths)
+
+        On a CUDA device the work runs on a worker thread and a side stream (`background`, default there): its host round trips
+        wait for the ground truth's upload only, not for the forward, the C sampler (~25 ms per batch of 8, GIL released)
+        overlaps the forward / the previous backward, and prepare() itself returns at once.  forward() joins it.  Optional:
+        forward() does the same work inline when no matching preparation exists (the reference's call pattern, train.py:339-346).
+        feat_hw: size of the mask feature map (default: a quarter of the ground-truth masks — the mask head runs at stride 4).
+        No np.random call may be made between prepare() and the forward() that consumes it (the sampler owns numpy's global
+        stream in between)."""
+        from .targets import assign_targets_batch
+        if feat_hw is None:
+            h, w = gt_instances[0]["masks"].shape[-2:]
+            feat_hw = (h // 4, w // 4)
+        feat_hw = tuple(feat_hw)
+        dev = gt_instances[0]["masks"].device
+        if background is None:
+            background = dev.type == "cuda"
+        prep = dict(key=tuple(id(g["masks"]) for g in gt_instances), keep=[g["masks"] for g in gt_instances], feat_hw=feat_hw,
+                    targets=None, vnl=None, thread=None, error=None, done=None)
+
+        def work():
+            prep["vnl"] = self.vnl_batched.prepare(gt_instances) if self.use_plane else None   # first: its sampler starts earliest
+            prep["targets"] = assign_targets_batch(gt_instances, feat_hw, self.num_grids, self.scale_ranges, self.num_classes, self.sigma)
+
+        if background and dev.type == "cuda":
+            import threading
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(dev)
+            side = self._side
+            uploaded = torch.cuda.Event()
+            uploaded.record(torch.cuda.current_stream(dev))              # the ground truth's H2D copies precede this point
+
+            def run():
+                try:
+                    torch.cuda.set_device(dev)
+                    with torch.cuda.stream(side):
+                        side.wait_event(uploaded)
+                        work()
+                        prep["done"] = torch.cuda.Event()
+                        prep["done"].record(side)
+                except BaseException as exc:                              # re-raised by the consumer
+                    prep["error"] = exc
+
+            prep["thread"] = threading.Thread(target=run, name="prn-loss-prepare", daemon=True)
+            prep["thread"].start()
+        else:
+            work()
+        self._prep = prep
+        return prep
+
+    @staticmethod
+    def _finish(prep, dev):
+        """Join a background preparation and order the consumer's stream after it."""
+        if prep["thread"] is not None:
+            prep["thread"].join()
+            prep["thread"] = None
+        if prep["error"] is not None:
+            raise prep["error"]
+        if prep["done"] is not None:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(prep["done"])
+
+            def rec(o):                    # tensors allocated under the side stream, consumed on this one
+                if torch.is_tensor(o):
+                    if o.is_cuda:
+                        o.record_stream(cur)
+                elif isinstance(o, dict):
+                    for k, v in o.items():
+                        if k != "keep":
+                            rec(v)
+                elif isinstance(o, (list, tuple)):
+                    for v in o:
+                        rec(v)
+
+            rec(prep["targets"])
+            rec(prep["vnl"])
+            prep["done"] = None
+        return prep
 
     def forward(self, net, mask_preds, cate_preds, kernel_preds, depth_preds, gt_instances, gt_depths):
-        from .targets import assign_targets_batch
         import torch.nn.functional as F
         be = self.backend or CudaBackend()
         B = len(gt_instances)
         fh, fw = mask_preds.shape[-2:]
-        targets = assign_targets_batch(gt_instances, (fh, fw), self.num_grids, self.scale_ranges, self.num_classes, self.sigma)
+        prep, self._prep = self._prep, None
+        if prep is not None and (prep["key"] != tuple(id(g["masks"]) for g in gt_instances) or prep["feat_hw"] != (fh, fw)):
+            self._finish(prep, mask_preds.device)                        # a stale preparation: let it end, then ignore it
+            prep = None
+        if prep is None:
+            prep = self.prepare(gt_instances, (fh, fw), background=False)
+            self._prep = None
+        self._finish(prep, mask_preds.device)
+        targets = prep["targets"]
         losses = {}
         gw, gsum = be.lava_weights(gt_depths, fh, fw, self.depth_resolution)
         if not self.use_lava:
@@ -557,12 +741,13 @@ class PlaneRecNetLoss(torch.nn.Module):
         labels = torch.cat([torch.cat([targets[b][l][1].flatten() for b in range(B)]) for l in range(n_levels)])
         logits = torch.cat([c.permute(0, 2, 3, 1).reshape(-1, self.num_classes) for c in cate_preds]).contiguous()
         # number of distinct positive cells (losses.py:114: sum of the boolean cell map, not of the instance rows)
-        num_ins = sum(int(targets[b][l][2].sum()) for b in range(B) for l in range(n_levels))
+        # (counted from the host-side cell lists: the device maps would cost 32 host syncs)
+        num_ins = sum(len(set(targets[b][l][3])) for b in range(B) for l in range(n_levels))
         losses["cat"] = self.w_cat * be.focal_sum(logits, labels, self.focal_alpha, self.focal_gamma, self.num_classes) / (num_ins + 1)
         losses["dpt"] = be.depth_rmselog(depth_preds, gt_depths, self.min_depth, 1e-9, self.w_dpt)
         if self.use_plane:
             up = F.interpolate(depth_preds, scale_factor=2, mode="bilinear", align_corners=False)
-            losses["pln"] = self.vnl_batched(up, gt_instances, gt_depths).mean() * self.w_pln
+            losses["pln"] = self.vnl_batched(up, gt_instances, gt_depths, prep=prep["vnl"]).mean() * self.w_pln
         if self.use_lava:
             losses["lav"] = lav
         return losses

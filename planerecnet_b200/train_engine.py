@@ -150,7 +150,7 @@ class TrainEngine(Engine):
             blob, work, smem = b"", [], 0
             for i, r in enumerate(recs.values()):
                 blob += struct.pack("<QQ11i4x", r["w"].data_ptr(), r["out"].data_ptr(), r["kind"], r["cout"], r["cin"], r["kk"], *r["f"])
-                work += [(i, n) for n in range(r["rows"])]
+                work += [(i, n) for n in range(0, r["rows"], 8 if r["kind"] == 1 else 1)]   # dgrad blocks take 8 rows
                 if r["kind"] == 0:
                     smem = max(smem, r["cin"] * r["kk"] * 4)
             rec_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
@@ -186,7 +186,7 @@ class TrainEngine(Engine):
                 self.launches += 1
                 out = ops.pack_dgrad_weight_dev(w, real_lo, real_hi, rows_pad, cout_pad, self.dt)
                 self._pack_recs[key] = dict(kind=1, w=conv.weight, out=out, rows=rows_pad, cout=w.shape[0], cin=w.shape[1],
-                                            kk=w.shape[2] * w.shape[3], f=[real_lo, real_hi - real_lo, cout_pad, 0, 0, 0, 0],
+                                            kk=w.shape[2] * w.shape[3], f=[real_lo, real_hi - real_lo, cout_pad, rows_pad, 0, 0, 0],
                                             params=[conv.weight], val=out, vec=[])
                 return out
             return ops.pack_dgrad_weight(w.float()[:, real_lo:real_hi], cout_pad=cout_pad, n_pad=rows_pad, dtype=self.dt).cuda()

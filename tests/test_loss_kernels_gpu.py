@@ -166,3 +166,53 @@ def test_assembled_loss_module_matches_reference_golden_on_gpu(cuda_lib, name):
             assert got != got, (name, tuple(t.shape), got)
         else:
             assert abs(got - ref) <= 2e-2 * abs(ref) + 1e-7, (name, tuple(t.shape), got, ref)
+
+
+def test_background_preparation_and_lookahead_give_the_same_losses(cuda_lib):
+    """crit.prepare(gts) (worker thread + side stream + C sampler) followed by crit(...) returns what crit(...) alone returns:
+    same targets, the same numpy-stream triplets, same loss terms and gradients; and a preparation made for the NEXT batch
+    while the current one is still in use (the look-ahead of bench.py's e2e loop) is picked up by the next call."""
+    import numpy as np
+    import loss_cases as LC
+    from planerecnet_b200.config import cfg, set_cfg
+    set_cfg("PlaneRecNet_101_config")
+    names = list(LC.CASES)[:2]
+    data = []
+    for name in names:
+        mask, cate, kern, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+        data.append(([t.cuda() for t in [mask] + cate + kern + [depth]], [{k: v.cuda() for k, v in g.items()} for g in gts],
+                     gt_depth.cuda()))
+
+    def run(mode):
+        crit = PL.PlaneRecNetLoss(cfg)
+        np.random.seed(0)
+        res = []
+        if mode == "lookahead":
+            crit.prepare(data[0][1])
+        for i, (tens, gts, gtd) in enumerate(data):
+            leaves = [t.clone().requires_grad_(True) for t in tens]
+            if mode == "prepare":
+                crit.prepare(gts)
+            out = crit(None, leaves[0], leaves[1:5], leaves[5:9], leaves[9], gts, gtd)
+            if mode == "lookahead" and i + 1 < len(data):
+                crit.prepare(data[i + 1][1])                  # next batch's preparation overlaps this backward
+            torch.nansum(torch.stack([v.sum() for v in out.values()])).backward()
+            res.append(({k: v.detach().double().sum().cpu() for k, v in out.items()},
+                        [None if t.grad is None else t.grad.double().norm().cpu() for t in leaves]))
+        tail = np.random.randint(0, 1 << 30, size=4)          # numpy's global stream ends at the same position
+        return res, tail
+
+    ref, tail_ref = run("inline")
+    for mode in ("prepare", "lookahead"):
+        got, tail = run(mode)
+        assert np.array_equal(tail, tail_ref), mode
+        for (lo_r, gr_r), (lo_g, gr_g) in zip(ref, got):
+            for k in lo_r:
+                a, b = float(lo_g[k]), float(lo_r[k])
+                assert (a != a and b != b) or abs(a - b) <= 1e-5 * abs(b) + 1e-7, (mode, k, a, b)
+            for a, b in zip(gr_g, gr_r):
+                if b is None:
+                    assert a is None
+                    continue
+                a, b = float(a), float(b)
+                assert (a != a and b != b) or abs(a - b) <= 1e-4 * abs(b) + 1e-9, (mode, a, b)

@@ -54,3 +54,39 @@ def test_device_sampling_is_statistically_equivalent():
         vals.append(got)
     got = torch.stack(vals).mean(0)
     assert torch.allclose(got.double(), ref.double(), rtol=5e-2), (ref, got)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 7, 12345])
+def test_c_restatement_of_numpy_choice_shuffle_is_bit_identical(seed):
+    """prn_numpy_choice_shuffle (host C, csrc/prn_hostrng.cu) against the literal np.random.choice + np.random.shuffle calls of
+    vnl.py:48-53: same indices for every region and repeat, and the same global RNG stream afterwards (a pure host function of
+    the C-ABI library: no device involved)."""
+    rs = np.random.RandomState(seed)
+    counts = [int(c) for c in rs.randint(0, 120000, size=23)] + [0, 1, 2, 3, 4, 7, 307200, 65536, 65537]
+    is_rest = [bool(i % 5 == 4) for i in range(len(counts))]
+    fn = PL._PlaneNormalBatched((480, 640), sampling="numpy")
+    T = sum(int(c * 0.3) for c in counts)
+    a = np.full((3, T + 5), -1, dtype=np.int32)
+    b = np.full((3, T + 5), -1, dtype=np.int32)
+    np.random.seed(seed)
+    np.random.random_sample(seed % 613)                      # move the stream position off a block boundary
+    ks_a = fn._sample_host_numpy(counts, is_rest, a)
+    after_a = np.random.get_state()
+    tail_a = np.random.randint(0, 1 << 30, size=8)
+    np.random.seed(seed)
+    np.random.random_sample(seed % 613)
+    ks_b = fn._sample_host(counts, is_rest, b)
+    after_b = np.random.get_state()
+    tail_b = np.random.randint(0, 1 << 30, size=8)
+    assert ks_a == ks_b and sum(ks_a) > 0
+    assert np.array_equal(a, b)
+    assert after_a[2] == after_b[2] and np.array_equal(after_a[1], after_b[1])
+    assert np.array_equal(tail_a, tail_b)
+    for k, c, rest in zip(ks_a, counts, is_rest):
+        assert k == (0 if (rest and c == 0) else int(c * 0.3))
+
+
+def test_numpy_py_sampling_gives_the_same_loss_as_the_c_sampler():
+    _, got_c, _, _ = _both("loss_seed0", sampling="numpy")
+    _, got_py, _, _ = _both("loss_seed0", sampling="numpy_py")
+    assert torch.equal(torch.nan_to_num(got_c), torch.nan_to_num(got_py))

@@ -82,6 +82,25 @@ def main():
              f"{'kernel':72s} {'launches':>8s} {'ms/step':>9s} {'share':>7s}"]
     for n, (c, d) in sorted(by_name.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"{n:72s} {c // reps:8d} {d / reps / 1e3:9.3f} {100 * d / total:6.1f}%")
+    # timeline: how much of the span has no kernel running at all, and how busy each stream is
+    iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in kern)
+    busy, cur_s, cur_e, gaps = 0.0, iv[0][0], iv[0][1], []
+    for s_, e_ in iv[1:]:
+        if s_ > cur_e:
+            busy += cur_e - cur_s
+            gaps.append(s_ - cur_e)
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    busy += cur_e - cur_s
+    small = [g for g in gaps if g < 50]
+    lines.append("")
+    lines.append(f"# timeline per step: some kernel running {busy / reps / 1e3:.3f} ms; no kernel running (gaps < 50 us, i.e. inside a replay) "
+                 f"{sum(small) / reps / 1e3:.3f} ms in {len(small) // reps} gaps (mean {sum(small) / max(len(small), 1):.2f} us)")
+    per_stream = collections.defaultdict(float)
+    for e in kern:
+        per_stream[e.get("args", {}).get("stream", -1)] += e["dur"]
+    lines.append("# kernel time per stream (ms/step): " + ", ".join(f"{k}: {v / reps / 1e3:.3f}" for k, v in sorted(per_stream.items(), key=lambda kv: -kv[1])))
     lines.append("")
     lines.append(f"{'kernel, grid':92s} {'launches':>8s} {'mean us':>9s} {'ms/step':>9s}")
     for (n, g), (c, d) in sorted(by_grid.items(), key=lambda kv: -kv[1][1])[:90]:
@@ -89,7 +108,8 @@ def main():
     os.makedirs(os.path.dirname(prefix), exist_ok=True)
     with open(prefix + "_kernels.txt", "w") as f:
         f.write("\n".join(lines) + "\n")
-    print("\n".join(lines[:45]))
+    print("\n".join(lines[:30]))
+    print("\n".join(l for l in lines if l.startswith("# ")))
 
 
 if __name__ == "__main__":
