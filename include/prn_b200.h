@@ -312,9 +312,15 @@ int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin
                           int32_t rows_pad, int32_t cout_pad, int32_t dtype, void* stream);
 /* Every packed operand of a training step in one launch.  recs_dev: device array of 64-byte records
  * {const float* w; void* out; int32 kind (0 = prn_pack_conv_weight, 1 = prn_pack_dgrad_weight), cout, cin, k*k,
- *  then 7 int32: kind 0: cpad_tot, nsplit, lo0, real0, pad0, lo1, real1;  kind 1: lo, hi - lo, cout_pad, 0...};
- * work_dev: int32 pairs {record, output row}, one per thread block; smem_bytes = max over records of cin*k*k*4. */
+ *  then 7 int32: kind 0: cpad_tot, nsplit, lo0, real0, pad0, lo1, real1;  kind 1: lo, hi - lo, cout_pad, rows_pad, 0...};
+ * work_dev: int32 pairs {record, output row (kind 1: first of 8 rows)}, one per thread block; smem_bytes = max over records of
+ * cin*k*k*4. */
 int prn_pack_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, int32_t dtype, void* stream);
+/* Many fp32 vectors gathered in one launch (the parameter gradients of a training step into one flat buffer: the operand of the
+ * data-parallel all-reduce, torch's DDP bucket copy).  recs_dev: device array of 32-byte records
+ * {const float* src; float* dst; int64 n; int32 src_stride (elements); int32 pad}: dst[i] = scale * src[i * src_stride], i < n;
+ * work_dev: int32 pairs {record, chunk}, one per thread block, chunk c covering elements [2048 c, 2048 (c + 1)). */
+int prn_copy_multi_f32(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, float scale, void* stream);
 
 /* torch.optim.Adam over all parameters in one launch (train.py:251-256: betas (0.9, 0.999), eps 1e-8, no weight decay, one
  * learning rate per parameter group).  table int64 [n][5] = {param, grad, exp_avg, exp_avg_sq device pointers (fp32), grad

@@ -814,7 +814,45 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(const PackRec* __restri
   }
 }
 
+// ---- many strided fp32 vectors -> contiguous destinations in one launch (parameter gradients -> the flat all-reduce buffer)
+struct CopyRec {
+  const float* src;
+  float* dst;
+  long long n;
+  int stride, pad_;
+};
+constexpr int kCopyChunk = 2048;
+
+__global__ void __launch_bounds__(256) copy_multi_kernel(const CopyRec* __restrict__ recs, const int2* __restrict__ work, float scale) {
+  const int2 wk = work[blockIdx.x];
+  const CopyRec r = recs[wk.x];
+  const long long lo = static_cast<long long>(wk.y) * kCopyChunk;
+  const long long hi = min(lo + kCopyChunk, r.n);
+  if (r.stride == 1 && ((reinterpret_cast<uintptr_t>(r.src) | reinterpret_cast<uintptr_t>(r.dst)) & 15) == 0) {
+    const long long i4 = lo + threadIdx.x * 4LL;                 // lo is a multiple of 2048: 16-byte aligned on both sides
+    for (long long i = i4; i < hi; i += 256 * 4) {
+      if (i + 4 <= hi) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(r.src + i));
+        v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+        *reinterpret_cast<float4*>(r.dst + i) = v;
+      } else {
+        for (long long j = i; j < hi; ++j) r.dst[j] = scale * __ldg(r.src + j);
+      }
+    }
+  } else {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) r.dst[i] = scale * __ldg(r.src + i * r.stride);
+  }
+}
+
 }  // namespace prn
+
+extern "C" int prn_copy_multi_f32(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, float scale, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(recs_dev && work_dev && n_blocks > 0, "copy_multi_f32: bad arguments");
+  copy_multi_kernel<<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const CopyRec*>(recs_dev),
+                                                                            reinterpret_cast<const int2*>(work_dev), scale);
+  PRN_LAUNCH_CHECK();
+}
 
 extern "C" int prn_pack_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, int32_t dtype,
                               void* stream) {

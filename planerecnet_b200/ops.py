@@ -297,3 +297,46 @@ def pack_dgrad_weight_dev(w, lo, hi, rows_pad, cout_pad, dtype):
     L.check(L.lib().prn_pack_dgrad_weight(_vp(w), _vp(out), cout, cin, k, lo, hi, rows_pad, cout_pad, dtype, L.current_stream()),
             "prn_pack_dgrad_weight")
     return out
+
+
+class CopyMulti:
+    """Many fp32 vectors -> contiguous destinations with ONE launch (prn_copy_multi_f32): the parameter gradients of a training
+    step gathered into the flat buffer the data-parallel all-reduce (and autograd's hand-over) works on.  torch._foreach_copy_
+    falls back to one copy per tensor as soon as one source is strided (bias / BatchNorm gradients are column views of their
+    accumulators): ~400 launches per step.
+
+    For CUDA graphs: construct with the destinations (allocates the device tables), call normalise() + run() inside the capture
+    (the launch only references the tables), and set_sources() after the capture has ended (uploads the table contents, which the
+    kernel reads at replay time; source addresses are only known once the captured backward has allocated them)."""
+    CHUNK = 2048
+
+    def __init__(self, dsts):
+        self.dsts = list(dsts)
+        work = []
+        for i, d in enumerate(self.dsts):
+            assert d.dtype == torch.float32 and d.is_contiguous()
+            work += [(i, c) for c in range((d.numel() + self.CHUNK - 1) // self.CHUNK)]
+        self.recs = torch.zeros(32 * len(self.dsts), dtype=torch.uint8, device="cuda")
+        self.work = torch.tensor(work, dtype=torch.int32).cuda().contiguous()
+        self.n_blocks = len(work)
+        self.srcs = None
+
+    @staticmethod
+    def normalise(srcs):
+        """Sources the kernel can read: contiguous, or 1-D with a stride; anything else is made contiguous (one copy)."""
+        return [s if (s.is_contiguous() or s.dim() == 1) else s.contiguous() for s in srcs]
+
+    def set_sources(self, srcs):
+        import struct
+        assert not torch.cuda.is_current_stream_capturing(), "set_sources uploads the tables: call it outside the capture"
+        assert len(srcs) == len(self.dsts)
+        blob = b""
+        for d, s in zip(self.dsts, srcs):
+            assert s.dtype == torch.float32 and s.numel() == d.numel() and (s.is_contiguous() or s.dim() == 1)
+            blob += struct.pack("<QQqii", s.data_ptr(), d.data_ptr(), d.numel(), 1 if s.is_contiguous() else s.stride(0), 0)
+        self.recs.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        self.srcs = list(srcs)                       # keeps the sources alive for as long as the tables point at them
+
+    def run(self, scale=1.0):
+        L.check(L.lib().prn_copy_multi_f32(_vp(self.recs), _vp(self.work), self.n_blocks, C.c_float(scale), L.current_stream()),
+                "prn_copy_multi_f32")

@@ -991,7 +991,7 @@ class GraphedStep:
     of a step cost more host time than GPU time otherwise).  Weight packing is captured too, so that replays see the
     optimizer's in-place parameter updates; parameters must keep their storage (true for torch optimizers)."""
 
-    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1, buckets=None, dp_mode=None):
+    def __init__(self, eng, net, x, pack_in_graph=True, optimizer=None, world=1, buckets=None, dp_mode=None, flat_grads=None):
         """optimizer: a planerecnet_b200.optim.FusedAdam over net's parameters -> `optimizer_step()` replays the update
         from a third graph (after the gradient all-reduce when world > 1).  buckets: capture the backward as one graph per
         gradient bucket (default: only when world > 1; True on one GPU exercises the same path without the collective).
@@ -1001,6 +1001,9 @@ class GraphedStep:
           'p2p'          backward in three bucket graphs, per-bucket mean all-reduce through peer memory with the copy engines
                          (utils.dist.PeerAllReduce) on a communication stream, started as each bucket's graph has been enqueued;
           'nccl_overlap' the same schedule with NCCL all-reduces.
+        flat_grads: end the (single) backward graph with the gather of every parameter gradient into ONE persistent flat fp32
+        buffer (ops.CopyMulti: one launch) — default when world > 1 (the all-reduce operand); the autograd boundary asks for
+        it too and hands autograd views of one clone of that buffer instead of ~400 per-parameter copies.
         Measured at N = 2 (R101 bs 8, tools/dp_check.py, profiles/r02_dp_check_2gpu.txt): cutting the backward into bucket graphs
         costs more than the overlap wins — every graph boundary joins the side-stream weight gradients, which lag the main chain —
         so 'after' is the default."""
@@ -1049,23 +1052,32 @@ class GraphedStep:
         self.g_bwd_seg = None
         if not buckets:
             params = [p for p in net.parameters() if p.requires_grad and id(p) in warm_ids]
-            if world > 1:
+            use_flat = world > 1 if flat_grads is None else bool(flat_grads)
+            gather = None
+            if use_flat:
                 self.flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device="cuda")
                 views, off = {}, 0
                 for p in params:
                     views[id(p)] = self.flat[off:off + p.numel()].view(p.shape)
                     off += p.numel()
                 self.flat_views, self.bucket_slices = views, [(0, off)]
+                self.flat_params = params
+                gather = ops.CopyMulti([views[id(p)] for p in params])
             self.g_bwd = torch.cuda.CUDAGraph()
             n0 = eng.launches
             with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
                 eng.seed_output_grads(*self.cots)
                 self.grads = eng.backward()
-                if world > 1:
-                    torch._foreach_copy_([views[id(p)] for p in params], [self.grads[id(p)].reshape(p.shape) for p in params])
+                if use_flat:
+                    srcs = gather.normalise([self.grads[id(p)].reshape(p.shape) for p in params])
+                    gather.run()
+                    eng.launches += 1
+            if use_flat:
+                gather.set_sources(srcs)              # table contents: read by the launch at replay time
+                self._gather = gather
             self.bwd_launches = eng.launches - n0
             params = [p for p in params if id(p) in self.grads]
-            src = views if world > 1 else self.grads
+            src = views if use_flat else self.grads
         else:
             # Data parallel: the backward is captured as N_BUCKETS graphs cut where a gradient bucket becomes final
             # (FPN + heads + decoder | backbone layers 2-3 | stem + layers 0-1).  Each graph ends with the multi-tensor copy of
@@ -1215,7 +1227,7 @@ class _DenseTrainFn(torch.autograd.Function):
                    tuple(m.training for m in net.modules() if isinstance(m, nn.BatchNorm2d)))
             step = eng._graphs_t.get(key)
             if step is None:
-                step = eng._graphs_t[key] = GraphedStep(eng, net, x)
+                step = eng._graphs_t[key] = GraphedStep(eng, net, x, flat_grads=True)
             mask, cates, kerns, depth = step.forward(x)
             # the graph's static buffers are overwritten by the next step: hand out copies
             mask, cates, kerns, depth = mask.clone(), [c.clone() for c in cates], [k.clone() for k in kerns], depth.clone()
@@ -1239,6 +1251,22 @@ class _DenseTrainFn(torch.autograd.Function):
         # go into ONE fresh flat buffer with a multi-tensor copy (two launches instead of one per parameter: ~450); autograd
         # receives views of it.
         out = [None] * len(ctx.params)
+        step = ctx.step
+        if step is not None and step.flat is not None and step.g_bwd_seg is None:
+            # graphed: the backward graph has gathered every gradient into the step's persistent flat buffer; autograd gets views
+            # of ONE clone of it (the buffer itself is rewritten by the next replay)
+            flat = step.flat.clone()
+            if eng.grad_scale != 1.0:
+                flat.mul_(1.0 / eng.grad_scale)
+            pos = {id(p): i for i, p in enumerate(ctx.params)}
+            off = 0
+            for p in step.flat_params:
+                i = pos.get(id(p))
+                if i is not None and p.requires_grad:
+                    assert p.dtype == torch.float32
+                    out[i] = flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            return (None, None, *out)
         idx, srcs = [], []
         for i, p in enumerate(ctx.params):
             gp = g.get(id(p))

@@ -312,3 +312,65 @@ def test_repack_all_equals_the_per_conv_pack_kernels(cuda_lib):
             lo, n, cout_pad = r["f"][0], r["f"][1], r["f"][2]
             ref = ops.pack_dgrad_weight_dev(w, lo, lo + n, r["rows"], cout_pad, eng.dt)
         assert torch.equal(r["out"].view(torch.int16), ref.view(torch.int16)), key
+
+
+@pytest.mark.gpu
+def test_copy_multi_gathers_strided_and_contiguous_vectors(cuda_lib):
+    """ops.CopyMulti (prn_copy_multi_f32): contiguous sources of odd lengths / unaligned offsets and strided column views into
+    slices of one flat buffer, bit for bit, with and without a scale; tables filled after the launch was recorded."""
+    from planerecnet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    srcs = [torch.randn(n, generator=g).cuda() for n in (1, 7, 2048, 2049, 5000, 12345)]
+    acc = torch.randn(300, 2, generator=g).cuda()
+    srcs += [acc[:257, 0], acc[:, 1], torch.randn(64, 3, 3, 3, generator=g).cuda(), torch.randn(9, 4, generator=g).cuda().t()]
+    total = sum(s.numel() for s in srcs)
+    flat = torch.full((total + 3,), -7.0, device="cuda")
+    dsts, off = [], 3                                     # an odd offset: unaligned destinations
+    for s in srcs:
+        dsts.append(flat[off:off + s.numel()].view(s.shape))
+        off += s.numel()
+    cm = ops.CopyMulti(dsts)
+    norm = cm.normalise(srcs)
+    cm.set_sources(norm)
+    cm.run()
+    want = torch.cat([s.reshape(-1) for s in srcs])
+    assert torch.equal(flat[3:], want) and float(flat[0]) == -7.0
+    cm.run(scale=0.5)
+    assert torch.equal(flat[3:], want * 0.5)
+
+
+@pytest.mark.gpu
+def test_flat_gradient_buffer_of_the_graphed_step_and_autograd_handover(cuda_lib):
+    """GraphedStep(flat_grads=True): the backward graph's last launch gathers every parameter gradient into one flat buffer whose
+    views equal the per-parameter gradients bit for bit; the autograd boundary (use_train_graph) hands out views of ONE clone of
+    it: .grad of every parameter equals the graph's gradient and does not alias the step's static buffer."""
+    from planerecnet_b200.train_engine import GraphedStep
+    from planerecnet_b200.utils.synth import make_cotangents
+    net = TC._build("PlaneRecNet_50_config", cond=True).train().cuda()
+    x = torch.randn(2, 3, 128, 160, generator=torch.Generator().manual_seed(5)).cuda()
+    eng = net.train_engine
+    step = GraphedStep(eng, net, x, flat_grads=True)
+    cots = make_cotangents(step.outs, seed=3, device="cuda")
+    step.forward(x)
+    grads = step.backward(*cots)
+    torch.cuda.synchronize()
+    params = [p for p in net.parameters() if p.requires_grad]
+    assert step.flat is not None and step.flat.numel() == sum(p.numel() for p in params)
+    for p in params:
+        assert torch.equal(step.flat_views[id(p)], grads[id(p)].reshape(p.shape).float()), p.shape
+    # autograd boundary
+    net.use_train_graph = True
+    outs = net(x)
+    loss = (outs[0] * cots[0]).sum() + sum((c * d).sum() for c, d in zip(outs[1], cots[1])) + \
+        sum((k * d).sum() for k, d in zip(outs[2], cots[2])) + (outs[3] * cots[3]).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    st = next(iter(eng._graphs_t.values()))
+    lo, hi = st.flat.data_ptr(), st.flat.data_ptr() + st.flat.numel() * 4
+    n_checked = 0
+    for p in params:
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all())
+        assert not (lo <= p.grad.data_ptr() < hi)
+        assert torch.equal(p.grad, st.flat_views[id(p)]), p.shape
+        n_checked += 1
+    assert n_checked == len(params)

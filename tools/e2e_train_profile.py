@@ -34,45 +34,59 @@ def main():
     loss_host = torch.empty(5).pin_memory()
     marks = {}
 
-    def step(prepare=True):
-        t = [time.perf_counter()]
-        x = x_host.cuda(non_blocking=True)
-        gts = [{k: v.cuda(non_blocking=True) for k, v in g.items()} for g in gts_h]
-        gtd = gtd_h.cuda(non_blocking=True)
-        for p in params:
-            p.grad = None
-        t.append(time.perf_counter())
-        np.random.seed(0)
-        if prepare:
+    copy_stream = torch.cuda.Stream()
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            x = x_host.cuda(non_blocking=True)
+            gts = [{k: v.cuda(non_blocking=True) for k, v in g.items()} for g in gts_h]
+            gtd = gtd_h.cuda(non_blocking=True)
             crit.prepare(gts)
-        t.append(time.perf_counter())
-        outs = net(x)
-        t.append(time.perf_counter())
-        losses = crit(net, outs[0], outs[1], outs[2], outs[3], gts, gtd)
-        t.append(time.perf_counter())
-        losses = {k: v.mean() for k, v in losses.items()}
-        sum(losses[k] for k in losses).backward()
-        t.append(time.perf_counter())
-        vals = torch.stack([losses[k].detach().float() for k in ("ins", "cat", "dpt", "pln", "lav")])
-        loss_host.copy_(vals, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        t.append(time.perf_counter())
-        for name, a, b in zip(("h2d issue", "prepare", "net(x)", "loss", "backward", "d2h + final sync"), t[:-1], t[1:]):
-            marks[name] = marks.get(name, 0.0) + (b - a)
+        return x, gts, gtd
+
+    def loop(n, lookahead):
+        """bench.py's e2e loop (user_loop) with host time stamps between the phases."""
+        np.random.seed(0)
+        nxt = upload() if lookahead else None
+        for i in range(n):
+            t = [time.perf_counter()]
+            batch = nxt if lookahead else upload()
+            main = torch.cuda.current_stream()
+            main.wait_stream(copy_stream)
+            x, gts, gtd = batch
+            for p in params:
+                p.grad = None
+            t.append(time.perf_counter())
+            outs = net(x)
+            t.append(time.perf_counter())
+            losses = crit(net, outs[0], outs[1], outs[2], outs[3], gts, gtd)
+            losses = {k: v.mean() for k, v in losses.items()}
+            t.append(time.perf_counter())
+            nxt = upload() if (lookahead and i + 1 < n) else None
+            t.append(time.perf_counter())
+            sum(losses[k] for k in losses).backward()
+            t.append(time.perf_counter())
+            vals = torch.stack([losses[k].detach().float() for k in ("ins", "cat", "dpt", "pln", "lav")])
+            loss_host.copy_(vals, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            t.append(time.perf_counter())
+            for name, a, b in zip(("upload / wait", "net(x)", "loss", "prefetch next", "backward", "d2h + final sync"), t[:-1], t[1:]):
+                marks[name] = marks.get(name, 0.0) + (b - a)
         return loss_host.tolist()
 
-    for prepare in (True, False):
-        for _ in range(3):
-            step(prepare)
+    def step(_prepare=True):
+        return loop(1, False)
+
+    for lookahead in (True, False):
+        loop(3, lookahead)
         marks.clear()
         torch.cuda.synchronize()
         n = 6
         t0 = time.perf_counter()
-        for _ in range(n):
-            lv = step(prepare)
+        lv = loop(n, lookahead)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / n * 1e3
-        print(f"[{mode}, prepare ahead of the forward: {prepare}] {dt:.1f} ms per step = {B / dt * 1e3:.1f} images/s | " +
+        print(f"[{mode}, look-ahead {lookahead}] {dt:.1f} ms per step = {B / dt * 1e3:.1f} images/s | host: " +
               " | ".join(f"{k} {v / n * 1e3:.1f}" for k, v in marks.items()) + f" | losses {[round(v, 4) for v in lv]}")
     # device side of the same step: kernel time by name (CUPTI through torch.profiler), network graphs vs everything else
     import collections
@@ -80,9 +94,9 @@ def main():
     import tempfile
     from torch.profiler import ProfilerActivity, profile
     reps = 2
+    reps = 3
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(reps):
-            step(True)
+        loop(reps, True)
         torch.cuda.synchronize()
     tmp = tempfile.mktemp(suffix=".json")
     prof.export_chrome_trace(tmp)
@@ -111,8 +125,7 @@ def main():
         print(f"  {n:100s} {c // reps:5d} {d / reps / 1e3:8.3f} ms")
     pr = cProfile.Profile()
     pr.enable()
-    for _ in range(3):
-        step(True)
+    loop(3, True)
     pr.disable()
     pstats.Stats(pr).sort_stats("tottime").print_stats(30)
 
