@@ -213,12 +213,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           for (int cc = 0; cc < p.kb_per_tap; ++cc) {
             const uint8_t* srcb = src + static_cast<size_t>(cc * 64 + chunk * 8) * 2;
             uint4 q[kRows][4];
+            if (p.dcn_dbg != 2) {
 #pragma unroll
-            for (int i = 0; i < kRows; ++i)
+              for (int i = 0; i < kRows; ++i)
 #pragma unroll
-              for (int cnr = 0; cnr < 4; ++cnr) q[i][cnr] = __ldg(reinterpret_cast<const uint4*>(srcb + po[i][cnr]));
+                for (int cnr = 0; cnr < 4; ++cnr) q[i][cnr] = __ldg(reinterpret_cast<const uint4*>(srcb + po[i][cnr]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < kRows; ++i)
+#pragma unroll
+                for (int cnr = 0; cnr < 4; ++cnr) q[i][cnr] = make_uint4(po[i][cnr], cc, tap, i);
+            }
             mbar_wait_acc(bar_empty + 8 * s, ph ^ 1u, prof, w_empty);
             const uint32_t a_stage = a_base + static_cast<uint32_t>(s) * kATileBytes;
+            if (p.dcn_dbg == 1) {
+#pragma unroll
+              for (int i = 0; i < kRows; ++i) {
+                const uint4 v = make_uint4(q[i][0].x ^ q[i][1].x, q[i][0].y ^ q[i][2].y, q[i][0].z ^ q[i][3].z, q[i][0].w ^ q[i][1].w ^ q[i][2].w ^ q[i][3].w);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_stage + row_off[i]), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+              }
+            } else
 #pragma unroll
             for (int i = 0; i < kRows; ++i) {
               float acc[8];
@@ -538,6 +552,8 @@ static int plan(const PrnConv& d, ConvKParams* p) {
   p->kb_per_tap = (d.c0 + d.c1) / 64;
   p->num_kb = d.ksize * d.ksize * p->kb_per_tap;
   p->dbg = nullptr;
+  static const int dcn_dbg = [] { const char* e = getenv("PRN_DCN_DEBUG"); return e ? atoi(e) : 0; }();
+  p->dcn_dbg = dcn_dbg;
   // dense 16-bit output rows (row index == m) can go through the smem-staged TMA store
   p->tma_store = (d.out16 != nullptr && d.out32 == nullptr && d.act != PRN_ACT_SIGMOID_AVG4 && p->groups == 1 &&
                   p->out_img_rows == p->hw_out && (reinterpret_cast<uintptr_t>(d.out16) & 15) == 0 && d.ld_out16 % 8 == 0)

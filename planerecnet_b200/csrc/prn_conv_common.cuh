@@ -44,6 +44,7 @@ struct ConvKParams {
   int tma_store;      // 1: 16-bit output rows are dense -> epilogue stages 32x64 sub-tiles in smem and TMA-stores them
   uint32_t idesc;
   long long* dbg;   // optional role-level cycle counters of CTA 0 (prn_conv2d_fwd_profile)
+  int dcn_dbg;      // timing experiments (env PRN_DCN_DEBUG): 1 = deformable producer without the blend, 2 = without the loads
 };
 
 // prn_conv_tma.cu: the TMA-fed kernel (3x3 stride 1 pad 1 through shared-memory halo tiles, 1x1 stride 1)

@@ -320,16 +320,30 @@ static int wgrad_plan(const PrnWgrad& d, WgradKParams* p) {
   p->m_sub = d.n > 128 ? 2 : 1;
   p->m_tiles = ceil_div(d.n, 128 * p->m_sub);
   p->kb_total = ceil_div(p->m_rows, kWgKBlock);
-  const int tiles = p->m_tiles * p->n_tiles;
   // split-K factor: `waves` CTAs per SM in total.  More splits shorten the K loop of a CTA but multiply the fp32 reduction traffic
   // (every split adds its whole 128 x 256 x m_sub accumulator into dW with red.global)
   static const int waves = [] { const char* e = getenv("PRN_WGRAD_WAVES"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 8 ? v : 1; }();
   // measured (profiles/r02_wgrad_waves.txt): one CTA per SM beats two (R101 step 30.7 -> 29.4 ms): the reduction traffic of the
   // extra splits costs more than the shorter K loops save
   static const int min_kb = [] { const char* e = getenv("PRN_WGRAD_MINKB"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 64 ? v : 16; }();   // >= 16 k-blocks per split: 30.7 -> 29.0 ms per R101 step together with waves = 1
-  int splits = (waves * sm_count()) / tiles;
-  if (splits > p->kb_total / min_kb) splits = p->kb_total / min_kb;
-  if (splits < 1) splits = 1;
+  auto splits_for = [&](int tiles_) {
+    int s_ = (waves * sm_count()) / tiles_;
+    if (s_ > p->kb_total / min_kb) s_ = p->kb_total / min_kb;
+    return s_ < 1 ? 1 : s_;
+  };
+  // 256-row CTA tiles (two 128-row accumulators sharing one gathered operand) halve the gather traffic, but the small maps
+  // (30x40, 15x20: few k-blocks to split) then fill a quarter of the SMs with CTAs that issue twice the MMAs each: when the
+  // 256-row plan cannot occupy half of the machine, use 128-row tiles (same reduction traffic, twice the CTAs)
+  static const bool msub_auto = [] { const char* e = getenv("PRN_WGRAD_MSUB_AUTO"); return !(e != nullptr && e[0] == '0'); }();
+  if (msub_auto && p->m_sub == 2) {
+    const int tiles2 = p->m_tiles * p->n_tiles;
+    if (tiles2 * splits_for(tiles2) * 2 <= sm_count()) {
+      p->m_sub = 1;
+      p->m_tiles = ceil_div(d.n, 128);
+    }
+  }
+  const int tiles = p->m_tiles * p->n_tiles;
+  int splits = splits_for(tiles);
   p->kb_per_split = ceil_div(p->kb_total, splits);
   p->splits = ceil_div(p->kb_total, p->kb_per_split);
   const int stage_bytes = p->m_sub * 2 * kWgAtomBytes + kWgMaxAtoms * kWgAtomBytes;
@@ -389,6 +403,10 @@ extern "C" int prn_conv2d_wgrad(const PrnWgrad* desc, void* stream) {
     if (rc != PRN_OK) return rc;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // timing experiments only (tools/graph_profile.py): PRN_WGRAD_SKIP=1 drops the launch, which shows what the weight-gradient
+  // kernels on the side streams cost the main chain (gradients are then wrong, of course)
+  static const bool skip = [] { const char* e = getenv("PRN_WGRAD_SKIP"); return e != nullptr && e[0] == '1'; }();
+  if (skip) return PRN_OK;
   if (desc->dtype == PRN_BF16) return wgrad_launch_t<__nv_bfloat16>(tm, tmx, p, st);
   return wgrad_launch_t<__half>(tm, tmx, p, st);
 }

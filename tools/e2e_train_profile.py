@@ -26,6 +26,10 @@ def main():
     net = perturb_(PlaneRecNet(cfg)).train().cuda()
     net.use_train_graph = True
     crit = PlaneRecNetLoss(cfg, vnl_sampling=mode)
+    if os.environ.get("PRN_NO_PLANE") == "1":          # experiment: what the plane term costs the step
+        crit.use_plane = False
+    if os.environ.get("PRN_NO_LAVA") == "1":
+        crit.use_lava = False
     x_host = make_input(B, 480, 640, 0).pin_memory()
     gts_h, gtd_h = make_gt(B, 480, 640, seed=0)
     gts_h = [{k: v.pin_memory() for k, v in g.items()} for g in gts_h]
