@@ -323,6 +323,11 @@ def main():
         loss_host = torch.empty(5).pin_memory()
 
         copy_stream = torch.cuda.Stream()
+        # the loss preparation of the NEXT batch runs on worker threads while this thread launches the backward: with CPython's
+        # default 5 ms switch interval every GIL hand-over can stall the launching thread for up to 5 ms (measured: 37 -> 54 ms
+        # per step on an unlucky run); 0.2 ms keeps the hand-overs out of the way.  Restored after the e2e measurement.
+        switch_interval = sys.getswitchinterval()
+        sys.setswitchinterval(2e-4)
 
         def upload():
             """One batch: pinned host -> device on the copy stream, and the ground-truth-only part of its loss started."""
@@ -385,6 +390,7 @@ def main():
         s_ms, _, _ = timed_user_steps(lookahead=False)
         crit = PlaneRecNetLoss(cfg, vnl_sampling="device")
         f_ms, _, _ = timed_user_steps()
+        sys.setswitchinterval(switch_interval)
         e2e = {"value": round(world * B / (u_ms / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,
                "steps": u_steps, "ms_per_step": round(u_ms, 3),
                "no_lookahead": {"value": round(world * B / (s_ms / 1e3), 2), "unit": "images/s", "ms_per_step": round(s_ms, 3),
