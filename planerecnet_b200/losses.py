@@ -221,7 +221,8 @@ class _InsLava(torch.autograd.Function):
         # (computed on the device: no host round trip in the middle of the backward)
         bound = ((coef[:, 0].abs() + 2 * coef[:, 1].abs()).max() + coef[:, 2].abs().max() * gw.max()) * 0.25
         usable = (bound > 0) & torch.isfinite(bound)
-        scale = torch.where(usable, torch.exp2(torch.floor(torch.log2(4096.0 / bound.clamp(min=1e-38)))), torch.ones_like(bound))
+        # (torch.pow, not torch.exp2: exp2 is a jiterator op — an NVRTC compile on its first call)
+        scale = torch.where(usable, torch.pow(2.0, torch.floor(torch.log2(4096.0 / bound.clamp(min=1e-38)))), torch.ones_like(bound))
         coef = (coef * scale).contiguous()
         dx16 = be.row_bwd(seg, tgt.view(B * n, P), gw, coef, n).view(B, n, P)        # scaled gradient of the pre-sigmoid rows
         # w.r.t. the selected kernels: dK[b] = dX[b] (n x P) . mask[b] (P x C)
