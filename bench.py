@@ -346,24 +346,39 @@ def main():
                 t.record_stream(main)
             return x, gts, gtd
 
+        # where the next batch's upload + loss preparation start: after this step's backward has been launched (default: the
+        # preparation threads then run while this thread only waits for the device; 33-35 ms per step, steady) or before it
+        # (PRN_PREFETCH_EARLY=1: 32.7 ms at best, but the threads then compete with the backward's launches for the GIL and an
+        # occasional run falls back to 45 ms)
+        prefetch_early = os.environ.get("PRN_PREFETCH_EARLY") == "1"
+
         def step_body(x, gts, gtd, prefetch):
             for p in params:
                 p.grad = None
             mask, cate, kern, depth = tnet(x)
             losses = crit(tnet, mask, cate, kern, depth, gts, gtd)
             losses = {k: v.mean() for k, v in losses.items()}          # train.py:347-348
-            nxt = upload() if prefetch else None                       # next batch: H2D + its GT-only work overlap this backward
+            nxt = upload() if (prefetch and prefetch_early) else None   # next batch: H2D + its GT-only work overlap this backward
             sum(losses[k] for k in losses).backward()
             if world > 1:
                 D.allreduce_mean_grads({id(p): p.grad for p in params if p.grad is not None}, params)
+            if prefetch and not prefetch_early:
+                nxt = upload()                                         # ... or only the device's share of it (host is done launching)
             vals = torch.stack([losses[k].detach().float() for k in ("ins", "cat", "dpt", "pln", "lav")])
             loss_host.copy_(vals, non_blocking=True)
-            torch.cuda.current_stream().synchronize()                  # the losses are on the host when the step ends
+            # the losses are on the host when the step ends.  A blocking event instead of stream.synchronize(): the latter spins on
+            # a core for the ~15 ms the GPU still needs, next to the sampler / preparation threads of the next batch
+            if os.environ.get("PRN_BLOCKING_SYNC") == "1":
+                done = torch.cuda.Event(blocking=True)
+                done.record()
+                done.synchronize()
+            else:
+                torch.cuda.current_stream().synchronize()
             return loss_host.tolist(), nxt
 
         def user_loop(n, lookahead):
             """n steps of the loop a user writes.  lookahead: one batch of prefetch (the next batch's upload and the
-            ground-truth-only part of its loss are started before this step's backward, like a prefetching DataLoader);
+            ground-truth-only part of its loss are started while this step's backward runs, like a prefetching DataLoader);
             otherwise every step uploads its own batch first.  n uploads and n loss read-backs either way."""
             np.random.seed(0)
             nxt = upload() if lookahead else None

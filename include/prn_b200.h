@@ -361,6 +361,18 @@ int prn_dice_lava_bwd(const float* seg, const uint8_t* target, const float* gw, 
 int prn_lava_weights(const float* gt, float* gw, float* gsum, int32_t batch, int32_t H, int32_t W, int32_t h, int32_t w, float depth_res,
                      void* stream);
 
+/* Plane surface-normal term, per-triplet geometry (models/functions/vnl.py:20-165) for all sampled triplets of a batch: pred / gt
+ * fp32 [B][h][w] (x2-upsampled prediction, ground-truth depth), fxfy fp32 [B][2], pix int64 [3][T] = global pixel of the triplets'
+ * points, region int64 [T], rest uint8 [R] (1 = the non-planar rest region of an image), tgt float64 [R][3] = ground-truth plane
+ * normals.  fwd: loss_t float64 [T] = 1 - |cos(normal, target)| and keep uint8 [T] = the selection mask of vnl.py:56-98.
+ * bwd: d_pred fp32 [B][h][w] += coef[t] * d(loss_t)/d(pred) (coef float64 [T]; 0 / NaN entries skipped). */
+int prn_vnl_triplets_fwd(const float* pred, const float* gt, const float* fxfy, const int64_t* pix, const int64_t* region,
+                         const uint8_t* rest, const double* tgt, double* loss_t, uint8_t* keep, int64_t n_triplets, int32_t h, int32_t w,
+                         float delta_z, void* stream);
+int prn_vnl_triplets_bwd(const float* pred, const float* gt, const float* fxfy, const int64_t* pix, const int64_t* region,
+                         const uint8_t* rest, const double* tgt, const double* coef, float* d_pred, int64_t n_triplets, int32_t h,
+                         int32_t w, float delta_z, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,236 @@ int prn_lava_weights(const float* gt, float* gw, float* gsum, int32_t batch, int
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- plane surface-normal term: per-triplet geometry
+// models/functions/vnl.py:20-165 for ALL sampled triplets of a batch (one thread per triplet): the three 3-D points of the
+// prediction and of the ground truth (u0 / v0 = image centre), the selection mask (in front, not colinear, not too close:
+// vnl.py:56-98) and the per-triplet loss 1 - |cos| between the triplet's normal and the plane's ground-truth normal (plane
+// regions, float64 like the reference's plane parameters) resp. the ground-truth triplet's normal (the non-planar rest, fp32).
+// pix int64 [3][T] = global pixel (image * H * W + y * W + x) of the three points; region int64 [T]; rest uint8 [R];
+// tgt float64 [R][3]; fxfy fp32 [B][2].  The backward recomputes the geometry from the depth map and adds
+// c[t] * d(loss_t)/d(depth) into d_depth with fp32 reductions (three pixels per triplet).
+namespace prn {
+
+struct VnlGeom {
+  int H, W;
+  float delta_z;
+};
+
+__device__ __forceinline__ void vnl_point(const float* __restrict__ depth, const float* __restrict__ fxfy, long long g, const VnlGeom& q,
+                                          float* p, float* jac) {
+  const long long hw = static_cast<long long>(q.H) * q.W;
+  const int b = static_cast<int>(g / hw);
+  const int r = static_cast<int>(g - b * hw);
+  const int y = r / q.W, x = r - y * q.W;
+  const float u = static_cast<float>(x - q.W / 2), v = static_cast<float>(y - q.H / 2);
+  const float fx = __ldg(fxfy + 2 * b), fy = __ldg(fxfy + 2 * b + 1);
+  const float d = __ldg(depth + g);
+  p[0] = __fdiv_rn(__fmul_rn(u, fabsf(d)), fx);
+  p[1] = __fdiv_rn(__fmul_rn(v, fabsf(d)), fy);
+  p[2] = d;
+  if (jac != nullptr) {       // d(point)/d(depth)
+    const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    jac[0] = u * sg / fx;
+    jac[1] = v * sg / fy;
+    jac[2] = 1.f;
+  }
+}
+
+__device__ __forceinline__ float sum3(float a, float b, float c) { return __fadd_rn(__fadd_rn(a, b), c); }
+
+// nv = (p1 - p0) x (p2 - p0), unit-ish normal n = nv / (|nv| + (|nv| == 0) * 0.01)      (vnl.py:100-108)
+__device__ __forceinline__ void vnl_normal(const float (*p)[3], float* nv, float* n, float* nrm_out, float* s_out) {
+  const float a0 = p[1][0] - p[0][0], a1 = p[1][1] - p[0][1], a2 = p[1][2] - p[0][2];
+  const float b0 = p[2][0] - p[0][0], b1 = p[2][1] - p[0][1], b2 = p[2][2] - p[0][2];
+  nv[0] = __fsub_rn(__fmul_rn(a1, b2), __fmul_rn(a2, b1));
+  nv[1] = __fsub_rn(__fmul_rn(a2, b0), __fmul_rn(a0, b2));
+  nv[2] = __fsub_rn(__fmul_rn(a0, b1), __fmul_rn(a1, b0));
+  const float nrm = sqrtf(sum3(__fmul_rn(nv[0], nv[0]), __fmul_rn(nv[1], nv[1]), __fmul_rn(nv[2], nv[2])));
+  const float s = nrm + (nrm == 0.f ? 0.01f : 0.f);
+  n[0] = nv[0] / s; n[1] = nv[1] / s; n[2] = nv[2] / s;
+  *nrm_out = nrm;
+  *s_out = s;
+}
+
+// vnl.py:146 quirk: a predicted point i with z == 0 sets COORDINATE i of all three points to 1e-4 (never true behind a softplus)
+__device__ __forceinline__ void vnl_rest_quirk(float (*p)[3], bool* fixed) {
+  const bool z0 = p[0][2] == 0.f, z1 = p[1][2] == 0.f, z2 = p[2][2] == 0.f;
+  fixed[0] = z0; fixed[1] = z1; fixed[2] = z2;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    if (fixed[c]) { p[0][c] = 0.0001f; p[1][c] = 0.0001f; p[2][c] = 0.0001f; }
+}
+
+__global__ void vnl_triplet_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const float* __restrict__ fxfy,
+                                       const long long* __restrict__ pix, const long long* __restrict__ region,
+                                       const unsigned char* __restrict__ rest, const double* __restrict__ tgt, double* __restrict__ loss_t,
+                                       unsigned char* __restrict__ keep, long long T, VnlGeom q) {
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < T;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = __ldg(region + t);
+    const bool is_rest = __ldg(rest + r) != 0;
+    float pp[3][3], pg[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const long long g = __ldg(pix + i * T + t);
+      vnl_point(pred, fxfy, g, q, pp[i], nullptr);
+      vnl_point(gt, fxfy, g, q, pg[i], nullptr);
+    }
+    const float (*ts)[3] = is_rest ? pg : pp;            // planes are tested on the prediction, the rest on the ground truth
+    // ---- selection (vnl.py:56-98)
+    float df[3][3];                                       // [pair][xyz]: p1 - p0, p2 - p0, p2 - p1
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      df[0][c] = ts[1][c] - ts[0][c];
+      df[1][c] = ts[2][c] - ts[0][c];
+      df[2][c] = ts[2][c] - ts[1][c];
+    }
+    float qn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) qn[k] = sqrtf(sum3(__fmul_rn(df[k][0], df[k][0]), __fmul_rn(df[k][1], df[k][1]), __fmul_rn(df[k][2], df[k][2])));
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float dot = sum3(__fmul_rn(df[i][0], df[j][0]), __fmul_rn(df[i][1], df[j][1]), __fmul_rn(df[i][2], df[j][2]));
+        const float cs = __fdiv_rn(dot, __fadd_rn(__fmul_rn(qn[i], qn[j]), 1e-8f));
+        cnt += (cs > 0.985f || cs < -0.985f) ? 1 : 0;
+      }
+    const bool colinear = cnt > 3;
+    const bool in_front = ts[0][2] > q.delta_z && ts[1][2] > q.delta_z && ts[2][2] > q.delta_z;
+    const float dd = is_rest ? 0.1f : 0.005f;
+    bool near = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) near = near && (fabsf(df[0][c]) < dd || fabsf(df[1][c]) < dd || fabsf(df[2][c]) < dd);
+    keep[t] = (in_front && !(near || colinear)) ? 1 : 0;
+    // ---- loss of the triplet
+    float nv[3], n[3], nrm, s;
+    double l;
+    if (!is_rest) {
+      vnl_normal(pp, nv, n, &nrm, &s);
+      const double t0 = __ldg(tgt + 3 * r), t1 = __ldg(tgt + 3 * r + 1), t2 = __ldg(tgt + 3 * r + 2);
+      const double n1 = fmax(sqrt(static_cast<double>(n[0]) * n[0] + static_cast<double>(n[1]) * n[1] + static_cast<double>(n[2]) * n[2]), 1e-8);
+      const double n2 = fmax(sqrt(t0 * t0 + t1 * t1 + t2 * t2), 1e-8);
+      const double cs = (n[0] / n1) * (t0 / n2) + (n[1] / n1) * (t1 / n2) + (n[2] / n1) * (t2 / n2);
+      l = 1.0 - fabs(cs);
+    } else {
+      bool fixed[3];
+      vnl_rest_quirk(pp, fixed);
+      vnl_normal(pp, nv, n, &nrm, &s);
+      float gv[3], gn[3], gnrm, gs;
+      vnl_normal(pg, gv, gn, &gnrm, &gs);
+      const float n1 = fmaxf(sqrtf(sum3(n[0] * n[0], n[1] * n[1], n[2] * n[2])), 1e-8f);
+      const float n2 = fmaxf(sqrtf(sum3(gn[0] * gn[0], gn[1] * gn[1], gn[2] * gn[2])), 1e-8f);
+      const float cs = sum3((n[0] / n1) * (gn[0] / n2), (n[1] / n1) * (gn[1] / n2), (n[2] / n1) * (gn[2] / n2));
+      l = static_cast<double>(1.f - fabsf(cs));
+    }
+    loss_t[t] = l;
+  }
+}
+
+__global__ void vnl_triplet_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt, const float* __restrict__ fxfy,
+                                       const long long* __restrict__ pix, const long long* __restrict__ region,
+                                       const unsigned char* __restrict__ rest, const double* __restrict__ tgt, const double* __restrict__ coef,
+                                       float* __restrict__ d_pred, long long T, VnlGeom q) {
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < T;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double c = __ldg(coef + t);
+    if (c == 0.0 || c != c) continue;
+    const long long r = __ldg(region + t);
+    const bool is_rest = __ldg(rest + r) != 0;
+    float pp[3][3], jac[3][3];
+    long long gpix[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      gpix[i] = __ldg(pix + i * T + t);
+      vnl_point(pred, fxfy, gpix[i], q, pp[i], jac[i]);
+    }
+    bool fixed[3] = {false, false, false};
+    double x2[3];
+    if (is_rest) {
+      float pg[3][3], gv[3], gn[3], gnrm, gs;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) vnl_point(gt, fxfy, gpix[i], q, pg[i], nullptr);
+      vnl_normal(pg, gv, gn, &gnrm, &gs);
+      x2[0] = gn[0]; x2[1] = gn[1]; x2[2] = gn[2];
+      vnl_rest_quirk(pp, fixed);
+    } else {
+      x2[0] = __ldg(tgt + 3 * r); x2[1] = __ldg(tgt + 3 * r + 1); x2[2] = __ldg(tgt + 3 * r + 2);
+    }
+    float nvf[3], nf[3], nrmf, sf;
+    vnl_normal(pp, nvf, nf, &nrmf, &sf);
+    const double x1[3] = {nf[0], nf[1], nf[2]};
+    const double n1 = sqrt(x1[0] * x1[0] + x1[1] * x1[1] + x1[2] * x1[2]), n2 = sqrt(x2[0] * x2[0] + x2[1] * x2[1] + x2[2] * x2[2]);
+    const double n1c = fmax(n1, 1e-8), n2c = fmax(n2, 1e-8);
+    const double cs = (x1[0] / n1c) * (x2[0] / n2c) + (x1[1] / n1c) * (x2[1] / n2c) + (x1[2] / n1c) * (x2[2] / n2c);
+    const double sg = cs > 0.0 ? 1.0 : (cs < 0.0 ? -1.0 : 0.0);
+    if (sg == 0.0) continue;
+    // d(loss)/d(x1): loss = 1 - |cos|, cos = sum (x1 / N1) (x2 / N2) with N1 = |x1| (its clamp carries no gradient)
+    double g1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g1[k] = -sg * c * ((x2[k] / n2c) / n1c - (n1 > 0.0 ? cs * x1[k] / (n1c * n1) : 0.0));
+    // through n = nv / s, s = |nv| + const
+    const double s = sf, nrm = nrmf;
+    const double nv[3] = {nvf[0], nvf[1], nvf[2]};
+    const double gdotn = g1[0] * nv[0] + g1[1] * nv[1] + g1[2] * nv[2];
+    double gnv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gnv[k] = g1[k] / s - (nrm > 0.0 ? gdotn / (s * s) * nv[k] / nrm : 0.0);
+    // through the cross product nv = A x B, A = p1 - p0, B = p2 - p0
+    const double A[3] = {static_cast<double>(pp[1][0]) - pp[0][0], static_cast<double>(pp[1][1]) - pp[0][1], static_cast<double>(pp[1][2]) - pp[0][2]};
+    const double Bv[3] = {static_cast<double>(pp[2][0]) - pp[0][0], static_cast<double>(pp[2][1]) - pp[0][1], static_cast<double>(pp[2][2]) - pp[0][2]};
+    const double gA[3] = {Bv[1] * gnv[2] - Bv[2] * gnv[1], Bv[2] * gnv[0] - Bv[0] * gnv[2], Bv[0] * gnv[1] - Bv[1] * gnv[0]};
+    const double gB[3] = {gnv[1] * A[2] - gnv[2] * A[1], gnv[2] * A[0] - gnv[0] * A[2], gnv[0] * A[1] - gnv[1] * A[0]};
+    double gp[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      gp[1][k] = gA[k];
+      gp[2][k] = gB[k];
+      gp[0][k] = -(gA[k] + gB[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double gd = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (!fixed[k]) gd += gp[i][k] * jac[i][k];
+      atomicAdd(d_pred + gpix[i], static_cast<float>(gd));
+    }
+  }
+}
+
+}  // namespace prn
+
+extern "C" {
+
+int prn_vnl_triplets_fwd(const float* pred, const float* gt, const float* fxfy, const int64_t* pix, const int64_t* region,
+                         const uint8_t* rest, const double* tgt, double* loss_t, uint8_t* keep, int64_t n_triplets, int32_t h, int32_t w,
+                         float delta_z, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(pred && gt && fxfy && pix && region && rest && tgt && loss_t && keep && n_triplets >= 0 && h > 0 && w > 0,
+              "vnl_triplets_fwd: bad arguments");
+  if (n_triplets == 0) return PRN_OK;
+  VnlGeom q{h, w, delta_z};
+  vnl_triplet_fwd_kernel<<<pw_grid(n_triplets), kPwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, gt, fxfy, reinterpret_cast<const long long*>(pix), reinterpret_cast<const long long*>(region), rest, tgt, loss_t, keep,
+      n_triplets, q);
+  PRN_LAUNCH_CHECK();
+}
+
+int prn_vnl_triplets_bwd(const float* pred, const float* gt, const float* fxfy, const int64_t* pix, const int64_t* region,
+                         const uint8_t* rest, const double* tgt, const double* coef, float* d_pred, int64_t n_triplets, int32_t h,
+                         int32_t w, float delta_z, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(pred && gt && fxfy && pix && region && rest && tgt && coef && d_pred && n_triplets >= 0 && h > 0 && w > 0,
+              "vnl_triplets_bwd: bad arguments");
+  if (n_triplets == 0) return PRN_OK;
+  VnlGeom q{h, w, delta_z};
+  vnl_triplet_bwd_kernel<<<pw_grid(n_triplets), kPwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      pred, gt, fxfy, reinterpret_cast<const long long*>(pix), reinterpret_cast<const long long*>(region), rest, tgt, coef, d_pred,
+      n_triplets, q);
+  PRN_LAUNCH_CHECK();
+}
+
+}  // extern "C"

@@ -153,21 +153,16 @@ class _InsLava(torch.autograd.Function):
     over instances) from the same grouped contraction.  Per-row scalar algebra (a few hundred numbers) stays in torch."""
 
     @staticmethod
-    def forward(ctx, be, targets, gw, gsum, w_dice, w_lava, mask_pred, *kernel_preds):
-        B, Cc, fh, fw = mask_pred.shape
-        P = fh * fw
-        dev = mask_pred.device
+    def _gather_rows(targets, kernel_preds, wsel, tgt, n_b, idx_views, dev):
+        """Per-(image, level) form (targets from the per-image assign_targets): fills wsel / tgt row blocks in a loop."""
+        B, n, Cc = wsel.shape
+        P = tgt.shape[2]
         n_levels = len(kernel_preds)
-        counts = [[len(targets[b][l][3]) for l in range(n_levels)] for b in range(B)]
-        n_b = [sum(c) for c in counts]
-        n = _round_up(max(max(n_b), 1), 16)
-        wsel = torch.zeros(B, n, Cc, device=dev)
-        tgt = torch.zeros(B, n, P, dtype=torch.uint8, device=dev)
         # all positive-cell indices of the batch in ONE upload (a torch.tensor(list, device=cuda) per image and level is a
         # synchronous copy each: 32 per step)
         flat_idx = [i for b in range(B) for l in range(n_levels) for i in targets[b][l][3]]
         idx_all = torch.tensor(flat_idx, dtype=torch.int64, device="cpu").to(dev, non_blocking=True) if flat_idx else None
-        idx_views, pos = {}, 0
+        pos = 0
         for b in range(B):
             off = 0
             for l in range(n_levels):
@@ -182,7 +177,34 @@ class _InsLava(torch.autograd.Function):
         valid_host = torch.zeros(B, n, dtype=torch.bool, device="cpu")
         for b in range(B):
             valid_host[b, :n_b[b]] = True
-        valid = valid_host.to(dev, non_blocking=True)
+        return wsel, tgt, valid_host.to(dev, non_blocking=True)
+
+    @staticmethod
+    def forward(ctx, be, targets, gw, gsum, w_dice, w_lava, mask_pred, *kernel_preds):
+        B, Cc, fh, fw = mask_pred.shape
+        P = fh * fw
+        dev = mask_pred.device
+        n_levels = len(kernel_preds)
+        counts = [[len(targets[b][l][3]) for l in range(n_levels)] for b in range(B)]
+        n_b = [sum(c) for c in counts]
+        dense = getattr(targets, "dense", None)
+        if dense is not None and dense["tgt"].shape[2] == P and dense["tgt"].device == dev:
+            # batch layout prepared by targets.assign_targets_batch: one gather for the positive cells' kernels of all images and
+            # levels (the per-(image, level) loop below costs ~5 launches per pair), targets already in place
+            n = dense["n"]
+            kern_all = torch.cat([k.reshape(B, Cc, -1) for k in kernel_preds], 2)                   # [B, C, sum S^2]
+            gsel = dense["gidx"][:, None, :].expand(B, Cc, n)
+            wsel = kern_all.gather(2, gsel).transpose(1, 2) * dense["valid"][:, :, None]            # [B, n, C]; padding rows 0
+            tgt, valid = dense["tgt"], dense["valid"]
+            idx_views = None
+            ctx.gsel = gsel
+        else:
+            n = _round_up(max(max(n_b), 1), 16)
+            wsel = torch.zeros(B, n, Cc, device=dev)
+            tgt = torch.zeros(B, n, P, dtype=torch.uint8, device=dev)
+            ctx.gsel = None
+            idx_views = {}
+            wsel, tgt, valid = _InsLava._gather_rows(targets, kernel_preds, wsel, tgt, n_b, idx_views, dev)
         mask16 = be.to16(mask_pred.reshape(B, Cc, P).transpose(1, 2))        # [B, P, C]
         wsel16 = be.to16(wsel)
         seg = be.seg_rows(wsel16, mask16)                                     # [B*n, P] sigmoid probabilities
@@ -206,6 +228,7 @@ class _InsLava(torch.autograd.Function):
         cl = cl_img[:, None] * valid
         ctx.be, ctx.targets, ctx.counts, ctx.shapes = be, targets, counts, (B, Cc, fh, fw, n, [k.shape for k in kernel_preds])
         ctx.idx_views = idx_views
+        ctx.valid = valid
         ctx.save_for_backward(seg, tgt, gw, mask16, wsel16, ca, cb, cl)
         return loss_ins, loss_lav
 
@@ -236,6 +259,16 @@ class _InsLava(torch.autograd.Function):
         dM = be.grouped_nt(dxT, kT) / scale                                           # [B, P, C]
         d_mask = dM.transpose(1, 2).reshape(B, Cc, fh, fw).contiguous()
         d_kern = []
+        if ctx.gsel is not None:
+            # one scatter-add over the level-concatenated kernel map (duplicated cells accumulate), then per-level views
+            total = sum(shp[2] * shp[3] for shp in kshapes)
+            dk_rows = (dK.float() * ctx.valid[:, :, None]).transpose(1, 2)                            # [B, C, n]
+            d_all = torch.zeros(B, Cc, total, device=dev).scatter_add_(2, ctx.gsel, dk_rows)
+            off = 0
+            for shp in kshapes:
+                d_kern.append(d_all[:, :, off:off + shp[2] * shp[3]].reshape(shp))
+                off += shp[2] * shp[3]
+            return (None, None, None, None, None, None, d_mask, *d_kern)
         for l, shp in enumerate(kshapes):
             gk = torch.zeros(shp, device=dev)
             for b in range(B):
@@ -343,6 +376,39 @@ class _PlaneNormal:
         return total / n_planes
 
 
+class _VnlTriplets(torch.autograd.Function):
+    """Per-triplet geometry of the plane term on the device (prn_vnl_triplets_fwd / _bwd, csrc/prn_loss.cu): points, selection
+    mask and 1 - |cos| for every triplet in one launch; the backward recomputes the geometry and adds the depth gradient with fp32
+    reductions.  Replaces ~80 torch launches forward and ~200 autograd launches backward of the tensor formulation below (which
+    stays as the CPU / reference form: tests compare the two on the GPU)."""
+
+    @staticmethod
+    def forward(ctx, depth_up, gt32, fxfy, P, region, rest_u8, tgt64, delta_z):
+        B, _, H, W = depth_up.shape
+        T = region.numel()
+        dev = depth_up.device
+        assert depth_up.dtype == torch.float32 and depth_up.is_contiguous() and gt32.is_contiguous() and P.is_contiguous()
+        loss_t = torch.empty(T, dtype=torch.float64, device=dev)
+        keep = torch.empty(T, dtype=torch.uint8, device=dev)
+        L.check(L.lib().prn_vnl_triplets_fwd(_p(depth_up), _p(gt32), _p(fxfy), _p(P), _p(region), _p(rest_u8), _p(tgt64), _p(loss_t),
+                                             _p(keep), C.c_int64(T), H, W, C.c_float(delta_z), L.current_stream()), "prn_vnl_triplets_fwd")
+        ctx.save_for_backward(depth_up, gt32, fxfy, P, region, rest_u8, tgt64)
+        ctx.delta_z = delta_z
+        ctx.mark_non_differentiable(keep)
+        return loss_t, keep
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_keep):
+        depth_up, gt32, fxfy, P, region, rest_u8, tgt64 = ctx.saved_tensors
+        B, _, H, W = depth_up.shape
+        coef = g_loss.to(torch.float64).contiguous()
+        d = torch.zeros_like(depth_up)
+        L.check(L.lib().prn_vnl_triplets_bwd(_p(depth_up), _p(gt32), _p(fxfy), _p(P), _p(region), _p(rest_u8), _p(tgt64), _p(coef), _p(d),
+                                             C.c_int64(region.numel()), H, W, C.c_float(ctx.delta_z), L.current_stream()),
+                "prn_vnl_triplets_bwd")
+        return d, None, None, None, None, None, None, None
+
+
 class _PlaneNormalBatched:
     """The same plane surface-normal term (models/functions/vnl.py:6-165) for a whole batch in a few dozen tensor ops instead of a
     Python loop over every plane of every image (48 planes + 8 "rest" regions per batch of 8: ~1000 tiny launches and a host
@@ -360,9 +426,10 @@ class _PlaneNormalBatched:
     |cos| against the plane normal resp. the ground-truth normals, worst-75 % tail per region) is evaluated for all triplets of
     all regions at once; the per-region sort of the tail is one global sort on the composite key (region, loss)."""
 
-    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4, sampling="numpy", threaded=True):
+    def __init__(self, size=(480, 640), sample_ratio=0.3, delta_z=1e-4, sampling="numpy", threaded=True, kernels=True):
         assert sampling in ("numpy", "numpy_py", "device")
         self.size, self.ratio, self.delta_z, self.sampling, self.threaded = size, sample_ratio, delta_z, sampling, threaded
+        self.kernels = kernels        # CUDA tensors: per-triplet geometry by prn_vnl_triplets_* instead of the tensor formulation
         self._grid = {}
         self._pinned, self._pinned_ev = None, None
 
@@ -529,10 +596,21 @@ class _PlaneNormalBatched:
         # ---- point clouds (vnl.py:20-38)
         fx = torch.stack([g["k_matrix"][0, 0] for g in gt_instances]).to(device=dev, dtype=torch.float32)[:, None, None]
         fy = torch.stack([g["k_matrix"][1, 1] for g in gt_instances]).to(device=dev, dtype=torch.float32)[:, None, None]
+        is_rest_t = is_rest_r[region]
+        # target normal of every triplet: the plane's ground-truth normal (float64 like the reference's plane_paras)
+        tgt = torch.zeros(R, 3, dtype=torch.float64, device=dev)
+        r0 = 0
+        for b, g in enumerate(gt_instances):
+            tgt[r0:r0 + n_planes[b]] = g["plane_paras"][:, :3].to(device=dev, dtype=torch.float64)
+            r0 += n_planes[b] + 1
+        if self.kernels and dev.type == "cuda" and depth_up.dtype == torch.float32:
+            fxfy = torch.stack([fx.flatten(), fy.flatten()], 1).contiguous()
+            loss_t, keep_u8 = _VnlTriplets.apply(depth_up.contiguous(), gt_depths.to(torch.float32).contiguous(), fxfy, P.contiguous(),
+                                                 region, is_rest_r.to(torch.uint8), tgt, float(self.delta_z))
+            return self._tail(loss_t, keep_u8.bool(), region, is_rest_t, is_rest_r, img_of, counts_t, prep, n_planes, R, T, B, dev)
         pred_pts = self._points(depth_up, fx, fy)
         gt_pts = self._points(gt_depths.to(depth_up.dtype), fx, fy)
         g_pred = pred_pts[P].permute(1, 2, 0)                            # [T, xyz, p123]
-        is_rest_t = is_rest_r[region]
         g_gt = gt_pts[P].permute(1, 2, 0)
         g_test = torch.where(is_rest_t[:, None, None], g_gt, g_pred)     # planes are tested on the prediction, the rest on the GT
         # ---- vnl.py:56-98: usable triplets
@@ -562,15 +640,13 @@ class _PlaneNormalBatched:
         n_plane = normals(g_pred)
         n_rest = normals(g_pred_rest)
         n_gt = normals(g_gt)
-        # target normal of every triplet: the plane's ground-truth normal (float64 like the reference's plane_paras)
-        tgt = torch.zeros(R, 3, dtype=torch.float64, device=dev)
-        r0 = 0
-        for b, g in enumerate(gt_instances):
-            tgt[r0:r0 + n_planes[b]] = g["plane_paras"][:, :3].to(device=dev, dtype=torch.float64)
-            r0 += n_planes[b] + 1
         cos_plane = F.cosine_similarity(n_plane, tgt[region], dim=1).abs()            # float64
         cos_rest = F.cosine_similarity(n_rest, n_gt, dim=1).abs()                     # float32
         loss_t = torch.where(is_rest_t, (1 - cos_rest).double(), 1 - cos_plane)        # [T] float64 (rest values are exact fp32)
+        return self._tail(loss_t, keep, region, is_rest_t, is_rest_r, img_of, counts_t, prep, n_planes, R, T, B, dev)
+
+    def _tail(self, loss_t, keep, region, is_rest_t, is_rest_r, img_of, counts_t, prep, n_planes, R, T, B, dev):
+        """Per-region worst-75 % tails and per-image means (vnl.py:100-165) from the per-triplet losses and selection mask."""
         # ---- vnl.py:100-117: worst 75 % per region: one global sort on (region, loss); NaNs sort last inside their region
         key = torch.where(keep, region.double() * 2 + torch.where(torch.isnan(loss_t), torch.full_like(loss_t, 1.5), loss_t),
                           torch.full_like(loss_t, float("inf")))
@@ -739,7 +815,12 @@ class PlaneRecNetLoss(torch.nn.Module):
         losses["ins"] = ins
         # category: rows ordered (level, image, cell) like losses.py:121-133
         n_levels = len(self.num_grids)
-        labels = torch.cat([torch.cat([targets[b][l][1].flatten() for b in range(B)]) for l in range(n_levels)])
+        dense = getattr(targets, "dense", None)
+        if dense is not None:                     # [B, all cells] label map of the batch: one slice per level instead of 32 tensors
+            offs = dense["level_off"]
+            labels = torch.cat([dense["cate"][:, o:o + S * S].reshape(-1) for o, S in zip(offs, self.num_grids)])
+        else:
+            labels = torch.cat([torch.cat([targets[b][l][1].flatten() for b in range(B)]) for l in range(n_levels)])
         logits = torch.cat([c.permute(0, 2, 3, 1).reshape(-1, self.num_classes) for c in cate_preds]).contiguous()
         # number of distinct positive cells (losses.py:114: sum of the boolean cell map, not of the instance rows)
         # (counted from the host-side cell lists: the device maps would cost 32 host syncs)

@@ -206,6 +206,13 @@ class PlaneRecNet(nn.Module):
         p2 = eng.to_nhwc(feats[0])
         return (eng.to_nchw(eng.avgpool2(p2), feats[0].shape[1]), feats[1], feats[2], feats[3])
 
+    def _apply(self, fn, *args, **kwargs):
+        """Device / dtype moves may replace parameter tensors: drop the cached parameter and BatchNorm lists of the training
+        boundary (train_engine.forward_train_autograd)."""
+        self._params_cache = None
+        self._bn_modules_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
     # ------------------------------------------------------------------ weights (planerecnet.py:121-153)
     def save_weights(self, path):
         torch.save(self.state_dict(), path)

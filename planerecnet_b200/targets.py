@@ -183,21 +183,37 @@ def assign_targets_batch(gts, feat_hw, num_grids, scale_ranges, num_classes=2, s
     cate_t = torch.from_numpy(cate_np).to(dev)
     ind_t = torch.from_numpy(ind_np).to(dev)
     src_t = torch.tensor(src_all, dtype=torch.int64, device=dev) if src_all else None
-    out = []
+    # dense batch form for the dice / lava node (losses._InsLava): the positive rows of image b — level after level, the order
+    # of the per-level lists — are rows [0, n_b) of ONE [B, n, fh * fw] target tensor; gidx[b, r] is the row's cell in the
+    # level-concatenated kernel map (level offset + cell).  The per-level tensors handed out below are views of it.
+    n_b = [sum(sn for (_o, _S, _ord, _s0, sn, _a) in plan[b]) for b in range(len(gts))]
+    n_rows = max(16, (max(n_b) + 15) // 16 * 16)
+    dense_tgt = torch.zeros(len(gts), n_rows, fh, fw, dtype=torch.uint8, device=dev)
+    gidx_np = np.zeros((len(gts), n_rows), dtype=np.int64)
+    valid_np = np.zeros((len(gts), n_rows), dtype=np.bool_)
+    out = TargetsBatch()
     for b, g in enumerate(gts):
-        small = None
-        res = []
+        if n_b[b]:
+            small = quarter_masks(g["masks"])
+            s_lo = plan[b][0][3]
+            dense_tgt[b, :n_b[b], :small.shape[1], :small.shape[2]] = small[src_t[s_lo:s_lo + n_b[b]]]
+            valid_np[b, :n_b[b]] = True
+        res, row = [], 0
         for (off, S, order, s0, sn, _any) in plan[b]:
             cate = cate_t[b, off:off + S * S].view(S, S)
             ind = ind_t[b, off:off + S * S]
             if sn:
-                if small is None:
-                    small = quarter_masks(g["masks"])
-                canvas = torch.zeros(sn, fh, fw, dtype=torch.uint8, device=dev)
-                canvas[:, :small.shape[1], :small.shape[2]] = small[src_t[s0:s0 + sn]]
-                ins = canvas
-            else:
-                ins = torch.zeros(0, fh, fw, dtype=torch.uint8, device=dev)
-            res.append((ins, cate, ind, order))
+                gidx_np[b, row:row + sn] = off + np.asarray(order, dtype=np.int64)
+            res.append((dense_tgt[b, row:row + sn], cate, ind, order))
+            row += sn
         out.append(res)
+    out.dense = dict(tgt=dense_tgt.view(len(gts), n_rows, fh * fw), gidx=torch.from_numpy(gidx_np).to(dev, non_blocking=True),
+                     valid=torch.from_numpy(valid_np).to(dev, non_blocking=True), n_b=n_b, n=n_rows, cate=cate_t,
+                     level_off=[p_[0] for p_ in plan[0]] if plan else [], num_grids=list(num_grids))
     return out
+
+
+class TargetsBatch(list):
+    """[per image][per level] (ins_label, cate_label, ins_ind, grid_order) like a list of assign_targets results, plus `.dense`: the
+    same targets in the batch layout the loss node consumes without a per-(image, level) loop."""
+    dense = None

@@ -1223,8 +1223,10 @@ class _DenseTrainFn(torch.autograd.Function):
         eng = net.train_engine
         ctx.step = None
         if getattr(net, "use_train_graph", False):
-            key = (id(net), tuple(x.shape), tuple(p.requires_grad for p in params),
-                   tuple(m.training for m in net.modules() if isinstance(m, nn.BatchNorm2d)))
+            bns = getattr(net, "_bn_modules_cache", None)
+            if bns is None:        # walking the module tree costs 1.7 ms per call (R101: 17 000 named_modules visits) with the GPU idle
+                bns = net._bn_modules_cache = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
+            key = (id(net), tuple(x.shape), tuple(p.requires_grad for p in params), tuple(m.training for m in bns))
             step = eng._graphs_t.get(key)
             if step is None:
                 step = eng._graphs_t[key] = GraphedStep(eng, net, x, flat_grads=True)
@@ -1287,7 +1289,11 @@ class _DenseTrainFn(torch.autograd.Function):
 
 
 def forward_train_autograd(net, x):
-    params = [p for p in net.parameters()]
+    # net.parameters() walks the module tree (R101: ~1 ms per call, with the GPU idle at the start of a step): the list is cached
+    # on the module and dropped by PlaneRecNet._apply / load_state_dict (device moves, checkpoint loads)
+    params = getattr(net, "_params_cache", None)
+    if params is None:
+        params = net._params_cache = [p for p in net.parameters()]
     outs = _DenseTrainFn.apply(net, x, *params)
     nl = (len(outs) - 2) // 2
     return outs[0], list(outs[1:1 + nl]), list(outs[1 + nl:1 + 2 * nl]), outs[-1]

@@ -216,3 +216,35 @@ def test_background_preparation_and_lookahead_give_the_same_losses(cuda_lib):
                     continue
                 a, b = float(a), float(b)
                 assert (a != a and b != b) or abs(a - b) <= 1e-4 * abs(b) + 1e-9, (mode, a, b)
+
+
+@pytest.mark.parametrize("name", ["loss_seed0", "loss_seed1_b1", "loss_seed2_many_tiny"])
+def test_plane_term_triplet_kernels_match_the_tensor_formulation(cuda_lib, name):
+    """prn_vnl_triplets_fwd / _bwd (per-triplet geometry, selection mask, 1 - |cos|, analytic depth gradient) against the tensor
+    formulation of the same term (itself pinned to the per-plane mirror of vnl.py on the CPU and to the reference's golden values):
+    same numpy-stream triplets, per-image losses within 1e-5, depth gradient within 1e-4 (fp32 reductions in another order; a
+    triplet that sits on a selection threshold to the last bit may flip)."""
+    import numpy as np
+    import torch.nn.functional as F
+    import loss_cases as LC
+    _, _, _, depth, gts, gt_depth = LC.synth(**LC.CASES[name])
+    gts_d = [{k: v.cuda() for k, v in g.items()} for g in gts]
+    res = {}
+    for kernels in (False, True):
+        d = depth.cuda().clone().requires_grad_(True)
+        up = F.interpolate(d, scale_factor=2, mode="bilinear", align_corners=False)
+        np.random.seed(0)
+        out = PL._PlaneNormalBatched((480, 640), kernels=kernels)(up, gts_d, gt_depth.cuda())
+        torch.nansum(out).backward()
+        res[kernels] = (out.detach().double().cpu(), d.grad.double().cpu())
+    (lo_t, g_t), (lo_k, g_k) = res[False], res[True]
+    assert torch.equal(torch.isnan(lo_t), torch.isnan(lo_k)), (lo_t, lo_k)
+    ok = ~torch.isnan(lo_t)
+    if not bool(ok.any()):                      # every image degenerate (tiny planes): the reference's NaN in both, nothing to compare
+        assert name == "loss_seed2_many_tiny"
+        return
+    assert torch.allclose(lo_k[ok], lo_t[ok], rtol=1e-5, atol=1e-9), (lo_t, lo_k)
+    fin = torch.isfinite(g_t) & torch.isfinite(g_k)
+    assert bool((torch.isfinite(g_t) == torch.isfinite(g_k)).all())
+    rel = float((g_k[fin] - g_t[fin]).norm() / g_t[fin].norm())
+    assert rel <= 1e-4 and float(g_t[fin].norm()) > 0, rel
