@@ -329,6 +329,10 @@ int prn_copy_multi_f32(const void* recs_dev, const int32_t* work_dev, int32_t n_
  * replayed from a CUDA graph.  Gradients are divided by grad_scale. */
 int prn_adam_multi(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
                    float* state3, float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The same update guarded like torch.cuda.amp.GradScaler.step: *found_inf (device int32) is set to 1 when any gradient element is
+ * inf / NaN, and then neither the parameters, nor the moments, nor the step counter change (loss-scaled f16 training). */
+int prn_adam_multi_checked(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
+                           float* state3, float beta1, float beta2, float eps, float grad_scale, int32_t* found_inf, void* stream);
 
 /* ---- dense parts of PlaneRecNetLoss (models/functions/losses.py), fp32 ------------------------------ */
 

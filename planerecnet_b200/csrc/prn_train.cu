@@ -903,8 +903,9 @@ extern "C" int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, 
 // and bias corrections live in device memory so that the update can be replayed from a CUDA graph.
 namespace prn {
 
-__global__ void adam_advance_kernel(float* state, float beta1, float beta2) {
-  // state = {step, 1 - beta1^step, sqrt(1 - beta2^step)}
+__global__ void adam_advance_kernel(float* state, float beta1, float beta2, const int* __restrict__ found_inf) {
+  // state = {step, 1 - beta1^step, sqrt(1 - beta2^step)}; a step with non-finite gradients is skipped entirely (GradScaler's rule)
+  if (found_inf != nullptr && *found_inf != 0) return;
   const float step = state[0] + 1.f;
   state[0] = step;
   state[1] = 1.f - powf(beta1, step);
@@ -917,7 +918,8 @@ constexpr int kAdamChunk = 1 << 16;
 __global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __restrict__ table, const long long* __restrict__ numel,
                                                        const float* __restrict__ lr, const int* __restrict__ chunks,
                                                        const float* __restrict__ state, float beta1, float beta2, float eps,
-                                                       float inv_grad_scale) {
+                                                       float inv_grad_scale, const int* __restrict__ found_inf) {
+  if (found_inf != nullptr && *found_inf != 0) return;
   const int t = chunks[2 * blockIdx.x], ck = chunks[2 * blockIdx.x + 1];
   float* p = reinterpret_cast<float*>(table[5 * t]);
   const float* g = reinterpret_cast<const float*>(table[5 * t + 1]);
@@ -939,16 +941,50 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __rest
   }
 }
 
+// *found_inf = 1 if any gradient element of the table is inf / NaN (the flag is cleared by a memset before this kernel)
+__global__ void __launch_bounds__(256) grads_nonfinite_kernel(const long long* __restrict__ table, const long long* __restrict__ numel,
+                                                            const int* __restrict__ chunks, int* __restrict__ found_inf) {
+  const int t = chunks[2 * blockIdx.x], ck = chunks[2 * blockIdx.x + 1];
+  const float* g = reinterpret_cast<const float*>(table[5 * t + 1]);
+  const long long gs = table[5 * t + 4];
+  const long long n = numel[t];
+  const long long lo = static_cast<long long>(ck) * kAdamChunk;
+  const long long hi = lo + kAdamChunk < n ? lo + kAdamChunk : n;
+  bool bad = false;
+  for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float v = g[i * gs];
+    bad = bad || !(fabsf(v) <= 3.4028234e38f);            // false for inf and NaN
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) *found_inf = 1;
+}
+
 }  // namespace prn
+
+extern "C" int prn_adam_multi_checked(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks,
+                                      int32_t n_chunks, float* state3, float beta1, float beta2, float eps, float grad_scale,
+                                      int32_t* found_inf, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(table && numel && lr && chunks && state3 && found_inf && n_chunks > 0 && grad_scale > 0.f, "adam_multi_checked: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PRN_CUDA(cudaMemsetAsync(found_inf, 0, sizeof(int32_t), st));
+  grads_nonfinite_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const long long*>(table), reinterpret_cast<const long long*>(numel),
+                                                   chunks, found_inf);
+  adam_advance_kernel<<<1, 1, 0, st>>>(state3, beta1, beta2, found_inf);
+  adam_multi_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const long long*>(table), reinterpret_cast<const long long*>(numel), lr,
+                                              chunks, state3, beta1, beta2, eps, 1.0f / grad_scale, found_inf);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(PRN_ERR_CUDA, "adam_multi_checked launch: %s", cudaGetErrorString(e));
+  return PRN_OK;
+}
 
 extern "C" int prn_adam_multi(const int64_t* table, const int64_t* numel, const float* lr, const int32_t* chunks, int32_t n_chunks,
                               float* state3, float beta1, float beta2, float eps, float grad_scale, void* stream) {
   using namespace prn;
   PRN_REQUIRE(table && numel && lr && chunks && state3 && n_chunks > 0 && grad_scale > 0.f, "adam_multi: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  adam_advance_kernel<<<1, 1, 0, st>>>(state3, beta1, beta2);
+  adam_advance_kernel<<<1, 1, 0, st>>>(state3, beta1, beta2, nullptr);
   adam_multi_kernel<<<n_chunks, 256, 0, st>>>(reinterpret_cast<const long long*>(table), reinterpret_cast<const long long*>(numel), lr,
-                                              chunks, state3, beta1, beta2, eps, 1.0f / grad_scale);
+                                              chunks, state3, beta1, beta2, eps, 1.0f / grad_scale, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(PRN_ERR_CUDA, "adam_multi launch: %s", cudaGetErrorString(e));
   return PRN_OK;

@@ -1,6 +1,14 @@
 """Adam for the training step (train.py:251-256: `optim.Adam` over five parameter groups with their own learning rates):
 one multi-tensor launch of `prn_adam_multi` over every parameter, with the step counter in device memory so that the
-update can be captured into the step's CUDA graphs.  Same update rule and state names as torch.optim.Adam."""
+update can be captured into the step's CUDA graphs.  Same update rule and state names as torch.optim.Adam.
+
+Differences from torch.optim.Adam: ONE step counter for all parameters — every parameter has to receive a gradient in
+every step (true for the PlaneRecNet training step; torch keeps a counter per parameter, so a parameter that skips steps would get a
+different bias correction there); `skip_nonfinite` (default: on when `grad_scale != 1`, i.e. loss-scaled f16 training) checks all
+gradients first and skips the whole update — parameters, moments and the step counter — when one is inf / NaN, like
+torch.cuda.amp.GradScaler.step; `found_inf` (device int32 tensor) tells the caller to lower its scale.  The pointer tables are
+rebuilt (a few host-to-device copies) whenever a gradient tensor moves: keep gradients in persistent buffers on the hot path
+(`GraphedStep.optimizer_step()` does: the flat gradient buffer never moves)."""
 import ctypes as C
 
 import torch
@@ -11,12 +19,14 @@ _CHUNK = 1 << 16
 
 
 class FusedAdam:
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0, skip_nonfinite=None):
         groups = list(params)
         if groups and not isinstance(groups[0], dict):
             groups = [{"params": groups}]
         self.param_groups = [{"params": list(g["params"]), "lr": g.get("lr", lr)} for g in groups]
         self.betas, self.eps, self.grad_scale = betas, eps, grad_scale
+        self.skip_nonfinite = (grad_scale != 1.0) if skip_nonfinite is None else bool(skip_nonfinite)
+        self.found_inf = None            # device int32 [1]: 1 after a skipped step (skip_nonfinite)
         self.state = {}
         self._state3 = None
         self._key = None
@@ -58,6 +68,8 @@ class FusedAdam:
                       torch.tensor(chunks, dtype=torch.int32, device=dev).contiguous(), len(chunks), [g for _, _, g in items])
         if self._state3 is None:
             self._state3 = torch.zeros(3, dtype=torch.float32, device=dev)
+        if self.found_inf is None:
+            self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)
         self._key = key
 
     def prepare(self, grads):
@@ -70,10 +82,17 @@ class FusedAdam:
             grads = {id(p): p.grad for p, _ in self._params()}
         self._build(grads)
         table, numel, lrs, chunks, n_chunks, _keep = self._tabs
-        L.check(L.lib().prn_adam_multi(C.c_void_p(table.data_ptr()), C.c_void_p(numel.data_ptr()), C.c_void_p(lrs.data_ptr()),
-                                       C.c_void_p(chunks.data_ptr()), n_chunks, C.c_void_p(self._state3.data_ptr()),
-                                       C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                                       C.c_float(self.grad_scale), L.current_stream()), "prn_adam_multi")
+        if self.skip_nonfinite:
+            L.check(L.lib().prn_adam_multi_checked(C.c_void_p(table.data_ptr()), C.c_void_p(numel.data_ptr()), C.c_void_p(lrs.data_ptr()),
+                                                   C.c_void_p(chunks.data_ptr()), n_chunks, C.c_void_p(self._state3.data_ptr()),
+                                                   C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                                   C.c_float(self.grad_scale), C.c_void_p(self.found_inf.data_ptr()),
+                                                   L.current_stream()), "prn_adam_multi_checked")
+        else:
+            L.check(L.lib().prn_adam_multi(C.c_void_p(table.data_ptr()), C.c_void_p(numel.data_ptr()), C.c_void_p(lrs.data_ptr()),
+                                           C.c_void_p(chunks.data_ptr()), n_chunks, C.c_void_p(self._state3.data_ptr()),
+                                           C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                           C.c_float(self.grad_scale), L.current_stream()), "prn_adam_multi")
         for p, _ in self._params():       # raw-pointer update: bump the version counters the weight caches key on
             torch.autograd.graph.increment_version(p)
 

@@ -374,3 +374,36 @@ def test_flat_gradient_buffer_of_the_graphed_step_and_autograd_handover(cuda_lib
         assert torch.equal(p.grad, st.flat_views[id(p)]), p.shape
         n_checked += 1
     assert n_checked == len(params)
+
+
+@pytest.mark.gpu
+def test_fused_adam_skips_a_step_with_nonfinite_gradients(cuda_lib):
+    """FusedAdam(skip_nonfinite=True) (prn_adam_multi_checked): a step whose gradients contain one inf (or NaN) changes neither the
+    parameters, nor the moments, nor the step counter and raises found_inf; the next clean step equals torch.optim.Adam's first."""
+    from planerecnet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(70000,), (33, 5, 3, 3), (9,)]
+    ref_p = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=1e-2)
+    ours = FusedAdam(our_p, lr=1e-2, skip_nonfinite=True)
+    grads = [torch.randn(s, generator=g).cuda() for s in shapes]
+    for bad in (float("inf"), float("nan")):
+        poisoned = [gr.clone() for gr in grads]
+        poisoned[0][65536 + 11] = bad                       # in the second chunk of the first tensor
+        before = [p.detach().clone() for p in our_p]
+        ours.step({id(p): gr for p, gr in zip(our_p, poisoned)})
+        torch.cuda.synchronize()
+        assert int(ours.found_inf) == 1 and float(ours._state3[0]) == 0.0
+        for p, b in zip(our_p, before):
+            assert torch.equal(p.detach(), b)
+        for p in our_p:
+            assert float(ours.state[id(p)]["exp_avg"].abs().max()) == 0.0
+    for p, gr in zip(ref_p, grads):
+        p.grad = gr.clone()
+    ref.step()
+    ours.step({id(p): gr for p, gr in zip(our_p, grads)})
+    torch.cuda.synchronize()
+    assert int(ours.found_inf) == 0 and float(ours._state3[0]) == 1.0
+    for a, b in zip(our_p, ref_p):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), float((a - b).abs().max())
