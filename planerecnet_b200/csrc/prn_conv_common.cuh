@@ -77,9 +77,19 @@ __device__ __forceinline__ void act_apply(float* x, int act, float param, int co
       for (int j = 0; j < W; ++j) x[j] = fmaxf(x[j], 0.f);
       break;
     case PRN_ACT_SIGMOID:
-    case PRN_ACT_SIGMOID_AVG4:
 #pragma unroll
       for (int j = 0; j < W; ++j) x[j] = __fdividef(1.f, 1.f + __expf(-x[j]));
+      break;
+    case PRN_ACT_SIGMOID_AVG4:
+      // sigmoid(x) = 0.5 + 0.5 tanh(x / 2): ONE special-function op (MUFU.TANH) instead of two (EX2 + RCP) — this epilogue is
+      // MUFU-bound (plane-prior attention: 143 M sigmoids per batch of 8).  tanh.approx.f32 has a relative error of 2^-11, i.e.
+      // <= 2.4e-4 absolute on the sigmoid: the size of the f16 rounding of the stored average
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x[j]));
+        x[j] = fmaf(0.5f, t, 0.5f);
+      }
       break;
     case PRN_ACT_SOFTPLUS:
 #pragma unroll
