@@ -115,10 +115,13 @@ __global__ void maxpool3s2_kernel(const T* __restrict__ in, T* __restrict__ out,
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(tu_) - b * Ho;
     float best[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) best[j] = -INFINITY;
@@ -146,10 +149,13 @@ __global__ void avgpool2_kernel(const T* __restrict__ in, T* __restrict__ out, i
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(tu_) - b * Ho;
     const T* p = in + ((static_cast<long long>(b) * H + 2 * ho) * W + 2 * wo) * C + c;
     float a[8], q[8], r[8], s[8], o[8];
     load8(p, a);
@@ -183,10 +189,13 @@ __global__ void resize_bilinear_kernel(const T* __restrict__ in, T* __restrict__
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(tu_) - b * Ho;
     int y0, y1, x0, x1;
     float ly, lx;
     src_index(ho, sh, H, &y0, &y1, &ly);
@@ -227,8 +236,9 @@ __global__ void append_coord_kernel(const T* __restrict__ in, T* __restrict__ ou
   const long long total = static_cast<long long>(B) * H * W * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);      // 32-bit decode (see pw_grid)
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
     float o[8];
     if (c < C) {
       load8(in + m * C + c, o);
@@ -236,7 +246,8 @@ __global__ void append_coord_kernel(const T* __restrict__ in, T* __restrict__ ou
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = 0.f;
       if (c == C) {
-        const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
+        const unsigned tq_ = mu_ / static_cast<unsigned>(W);
+        const int x = static_cast<int>(mu_ - tq_ * static_cast<unsigned>(W)), y = static_cast<int>(tq_ % static_cast<unsigned>(H));
         o[0] = W > 1 ? -1.f + 2.f * x / static_cast<float>(W - 1) : -1.f;
         o[1] = H > 1 ? -1.f + 2.f * y / static_cast<float>(H - 1) : -1.f;
       }
@@ -257,9 +268,10 @@ __global__ void gn_apply_kernel(const T* __restrict__ in, T* __restrict__ out, c
   const long long total = static_cast<long long>(B) * HW * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int b = static_cast<int>(m / HW);
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);      // 32-bit decode (see pw_grid)
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const int b = static_cast<int>(mu_ / static_cast<unsigned>(HW));
     float f[8];
     load8(in + m * C + c, f);
 #pragma unroll
@@ -286,10 +298,13 @@ __global__ void upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out,
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(tu_) - b * Ho;
     int y0, y1, x0, x1;
     float ly, lx;
     src_index(ho, 0.5f, H, &y0, &y1, &ly);
@@ -337,8 +352,9 @@ __global__ void ppa_gather_kernel(const T* __restrict__ in, T* __restrict__ out,
   const long long total = static_cast<long long>(B) * Hb * Wb * 4 * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);      // 32-bit decode (see pw_grid)
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
     const int pos = static_cast<int>(m & 3);
     const long long blk = m >> 2;
     const int bx = static_cast<int>(blk % Wb), by = static_cast<int>((blk / Wb) % Hb);

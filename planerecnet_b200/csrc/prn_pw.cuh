@@ -9,6 +9,12 @@ namespace prn {
 constexpr int kPwThreads = 256;
 
 static inline int pw_grid(long long work_items) {
+  // the passes decode their element index with 32-bit arithmetic: refuse anything larger (grid 0 = launch error, reported by
+  // PRN_LAUNCH_CHECK); the path's largest tensor has 2e7 16-byte groups
+  if (work_items >= (1LL << 31)) {
+    set_error(PRN_ERR_UNSUPPORTED, "pointwise pass over %lld work items (>= 2^31) is not supported", work_items);
+    return 0;
+  }
   long long b = (work_items + kPwThreads - 1) / kPwThreads;
   const long long cap = static_cast<long long>(sm_count()) * 16;  // grid-stride beyond 16 CTAs/SM
   if (b > cap) b = cap;

@@ -280,10 +280,13 @@ __global__ void add_strided_kernel(T* __restrict__ dst, const T* __restrict__ sr
   const int H = h * s, W = w * s;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int x = static_cast<int>(m % w), y = static_cast<int>((m / w) % h);
-    const int b = static_cast<int>(m / (static_cast<long long>(w) * h));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(w);
+    const int x = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(w)), b = static_cast<int>(tu_ / static_cast<unsigned>(h));
+    const int y = static_cast<int>(tu_) - b * h;
     T* dp = dst + ((static_cast<long long>(b) * H + y * s) * W + x * s) * C + c;
     float a[8], q[8];
     load8(src + m * C + c, a);
@@ -339,10 +342,13 @@ __global__ void __launch_bounds__(kPwThreads) maxpool3s2_bwd_kernel(const T* __r
   const long long total = static_cast<long long>(B) * Hb * Wb * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int l = static_cast<int>(m % Wb), k = static_cast<int>((m / Wb) % Hb);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wb) * Hb));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wb);
+    const int l = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wb)), b = static_cast<int>(tu_ / static_cast<unsigned>(Hb));
+    const int k = static_cast<int>(tu_) - b * Hb;
     const T* img = in + static_cast<long long>(b) * H * W * C + c;
     float best[2][2][8];
     int arg[2][2][8];
@@ -441,11 +447,15 @@ __global__ void dcn_im2col_kernel(const T* __restrict__ x, const float* __restri
   const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * 9 * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const int tap = static_cast<int>((i / cv) % 9);
-    const long long m = i / (9 * cv);
-    const int wo = static_cast<int>(m % g.Wo), ho = static_cast<int>((m / g.Wo) % g.Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): six 64-bit divisions per 16 bytes made this pass compute-bound
+    const unsigned iu_ = static_cast<unsigned>(i), t1_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - t1_ * static_cast<unsigned>(cv)) * 8;
+    const unsigned mu_ = t1_ / 9u;
+    const int tap = static_cast<int>(t1_ - mu_ * 9u);
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(g.Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(g.Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(g.Ho));
+    const int ho = static_cast<int>(tu_) - b * g.Ho;
     float mk, ly, lx;
     bool inside;
     int y0, x0;
@@ -485,8 +495,9 @@ __global__ void dcn_col2im_bwd_kernel(const T* __restrict__ x, const float* __re
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const long long M = static_cast<long long>(g.B) * g.Ho * g.Wo;
   for (long long m = warp_g; m < M; m += nwarps) {
-    const int wo = static_cast<int>(m % g.Wo), ho = static_cast<int>((m / g.Wo) % g.Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(g.Wo) * g.Ho));
+    const unsigned mu_ = static_cast<unsigned>(m), tu_ = mu_ / static_cast<unsigned>(g.Wo);      // m < 2^24 pixels
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(g.Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(g.Ho));
+    const int ho = static_cast<int>(tu_) - b * g.Ho;
     const float* om = offmask + m * 32;
     float v0 = 0.f, v1 = 0.f;   // the two dpre columns (2*lane, 2*lane+1) this lane writes
     for (int tap = 0; tap < 9; ++tap) {

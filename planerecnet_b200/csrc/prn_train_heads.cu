@@ -147,10 +147,13 @@ __global__ void avgpool2_bwd_kernel(const T* __restrict__ dout, T* __restrict__ 
   const long long total = static_cast<long long>(B) * H * W * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
-    const int b = static_cast<int>(m / (static_cast<long long>(W) * H));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(W);
+    const int x = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(W)), b = static_cast<int>(tu_ / static_cast<unsigned>(H));
+    const int y = static_cast<int>(tu_) - b * H;
     float g[8];
     load8(dout + ((static_cast<long long>(b) * Ho + (y >> 1)) * Wo + (x >> 1)) * C + c, g);
     if (accumulate) {
@@ -173,10 +176,13 @@ __global__ void upsample2x_bwd_kernel(const T* __restrict__ dout, T* __restrict_
   const long long total = static_cast<long long>(B) * H * W * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H);
-    const int b = static_cast<int>(m / (static_cast<long long>(W) * H));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(W);
+    const int x = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(W)), b = static_cast<int>(tu_ / static_cast<unsigned>(H));
+    const int y = static_cast<int>(tu_) - b * H;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -213,10 +219,13 @@ __global__ void resize_bilinear_bwd_kernel(const T* __restrict__ dout, float* __
   const long long total = static_cast<long long>(B) * Ho * Wo * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(Wo) * Ho));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(Wo);
+    const int wo = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(Wo)), b = static_cast<int>(tu_ / static_cast<unsigned>(Ho));
+    const int ho = static_cast<int>(tu_) - b * Ho;
     int y0, y1, x0, x1;
     float ly, lx;
     bil_index(ho, sh, H, &y0, &y1, &ly);
@@ -246,10 +255,13 @@ __global__ void reflect_fold_kernel(const T* __restrict__ dpad, T* __restrict__ 
   const long long total = static_cast<long long>(B) * h * w * cv;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv) * 8;
-    const long long m = i / cv;
-    const int x = static_cast<int>(m % w), y = static_cast<int>((m / w) % h);
-    const int b = static_cast<int>(m / (static_cast<long long>(w) * h));
+    // 32-bit index decode (pw_grid refuses >= 2^31 work items): the 64-bit divisions cost more than the pass's arithmetic
+    const unsigned iu_ = static_cast<unsigned>(i), mu_ = iu_ / static_cast<unsigned>(cv);
+    const int c = static_cast<int>(iu_ - mu_ * static_cast<unsigned>(cv)) * 8;
+    const long long m = mu_;
+    const unsigned tu_ = mu_ / static_cast<unsigned>(w);
+    const int x = static_cast<int>(mu_ - tu_ * static_cast<unsigned>(w)), b = static_cast<int>(tu_ / static_cast<unsigned>(h));
+    const int y = static_cast<int>(tu_) - b * h;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
