@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(kPwThreads) bn_apply_kernel(const T* __restric
                                                             long long rows, int C, int relu) {
   const int cv = C / 8;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
-  const int c = static_cast<int>(gtid % cv) * 8;
+  const long long rstep = (gridDim.x * blockDim.x) / static_cast<unsigned>(cv);      // 32-bit: grids stay far below 2^31 threads
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kPwThreads) bn_apply_kernel(const T* __restric
   const float lo = relu ? 0.f : -INFINITY;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   // two rows per iteration, all loads issued before the first use (latency-bound otherwise)
-  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < rows; m += 2 * rstep) {
     const long long m2 = m + rstep;
     const bool two = m2 < rows;
     const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kPwThreads) bn_finalize_apply_kernel(const T* 
                                                                      const T* __restrict__ res, long long rows, int C, int relu) {
   const int cv = C / 8;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
-  const int c = static_cast<int>(gtid % cv) * 8;
+  const long long rstep = (gridDim.x * blockDim.x) / static_cast<unsigned>(cv);      // 32-bit: grids stay far below 2^31 threads
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
   const bool writer = gtid < cv;
   float sc[8], sh[8];
 #pragma unroll
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(kPwThreads) bn_finalize_apply_kernel(const T* 
   }
   const float lo = relu ? 0.f : -INFINITY;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
-  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < rows; m += 2 * rstep) {
     const long long m2 = m + rstep;
     const bool two = m2 < rows;
     const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(x + m * C + c));
@@ -137,15 +137,15 @@ __global__ void __launch_bounds__(kPwThreads) chan_reduce_kernel(const T* __rest
   const int cv = C / 8;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-  const int c = static_cast<int>(gtid % cv) * 8;
-  const long long rstep = tthreads / cv;
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
+  const long long rstep = static_cast<unsigned>(tthreads) / static_cast<unsigned>(cv);
   // s2 accumulates sum g * x; the normalisation is applied once at the end: sum g*xhat = inv * (s2 - mean * s1)
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   // two rows per iteration, all loads issued before the first use (the pass is latency-bound otherwise)
-  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < rows; m += 2 * rstep) {
     const long long m2 = m + rstep;
     const bool two = m2 < rows;
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(dz + m * C + c));
@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(kPwThreads) bn_bwd_apply_kernel(const T* __res
                                                                 float inv_count) {
   const int cv = C / 8;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
-  const int c = static_cast<int>(gtid % cv) * 8;
+  const long long rstep = (gridDim.x * blockDim.x) / static_cast<unsigned>(cv);      // 32-bit: grids stay far below 2^31 threads
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
   // dx = a * g + b * x + k  with  a = gamma*invstd,  b = -a*invstd*sgx,  k = -a*sg - b*mean
   float ka[8], kb[8], kk[8];
 #pragma unroll
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kPwThreads) bn_bwd_apply_kernel(const T* __res
   }
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
   // two rows per iteration, all loads issued before the first use (latency-bound otherwise: most launches move < 30 MB)
-  for (long long m = gtid / cv; m < rows; m += 2 * rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < rows; m += 2 * rstep) {
     const long long m2 = m + rstep;
     const bool two = m2 < rows;
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(dz + m * C + c));

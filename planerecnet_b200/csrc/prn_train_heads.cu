@@ -30,8 +30,8 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restri
   const int b = blockIdx.y;
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long tthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-  const int c = static_cast<int>(gtid % cv) * 8;
-  const long long rstep = tthreads / cv;
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
+  const long long rstep = static_cast<unsigned>(tthreads) / static_cast<unsigned>(cv);
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
   float mean[8], rstd[8], s1[8], s2[8];
 #pragma unroll
@@ -45,7 +45,7 @@ __global__ void gn_bwd_reduce_kernel(const T* __restrict__ dz, const T* __restri
     s2[j] = 0.f;
   }
   const long long img = static_cast<long long>(b) * HW;
-  for (long long m = gtid / cv; m < HW; m += rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < HW; m += rstep) {
     float g[8], o[8], xv[8];
     load8(dz + (img + m) * C + c, g);
     load8(out + (img + m) * C + c, o);
@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(kPwThreads) gn_bwd_apply_kernel(const T* __res
   const int b = blockIdx.y;
   const float inv_cnt = 1.f / (static_cast<float>(HW) * cg);
   const long long gtid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long rstep = (static_cast<long long>(gridDim.x) * blockDim.x) / cv;
-  const int c = static_cast<int>(gtid % cv) * 8;
+  const long long rstep = (gridDim.x * blockDim.x) / static_cast<unsigned>(cv);      // 32-bit: grids stay far below 2^31 threads
+  const int c = static_cast<int>(static_cast<unsigned>(gtid) % static_cast<unsigned>(cv)) * 8;
   // per-group sums of gamma * {a, bq}: one warp per group, lanes over the group's channels (a per-thread loop over the
   // group's channels was a 2 * cg-deep chain of L2 round trips in every thread: ~30 us of a 38 us launch)
   __shared__ float gsum[2 * 512];
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kPwThreads) gn_bwd_apply_kernel(const T* __res
     kk[j] = -rstd * ga * inv_cnt - kb[j] * m1;
   }
   const long long img = static_cast<long long>(b) * HW;
-  for (long long m = gtid / cv; m < HW; m += rstep) {
+  for (long long m = static_cast<unsigned>(gtid) / static_cast<unsigned>(cv); m < HW; m += rstep) {
     float g[8], o[8], xv[8];
     load8(dz + (img + m) * C + c, g);
     load8(out + (img + m) * C + c, o);
