@@ -51,6 +51,7 @@ class TrainEngine(Engine):
         self._nbt = []
         self._marks, self._pf_done = [], 0
         self._pack_recs, self._pack_tab = {}, None
+        self._big, self._big_off, self._big_hi, self._big_need = None, 0, 0, 0
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
@@ -97,6 +98,17 @@ class TrainEngine(Engine):
         n = 1
         for d in shape:
             n *= d
+        if dtype == torch.float32 and n > self._ARENA_MAX_ITEM and self._arena is not None:
+            # large fp32 accumulators (the weight-gradient buffers: ~160 per step, 240 MB in total): a second arena, sized by what
+            # the first step asked for, cleared by one memset instead of one fill kernel per buffer
+            n_al = (n + 31) // 32 * 32
+            if self._big is not None and self._big_off + n_al <= self._big.numel():
+                t = self._big[self._big_off:self._big_off + n].view(*shape)
+                self._big_off += n_al
+                self._big_hi = max(self._big_hi, self._big_off)
+                return t
+            self._big_need += n_al
+            return torch.zeros(*shape, dtype=dtype, device="cuda")
         if dtype != torch.float32 or n > self._ARENA_MAX_ITEM or self._arena is None:
             return torch.zeros(*shape, dtype=dtype, device="cuda")
         n_al = (n + 31) // 32 * 32
@@ -876,6 +888,16 @@ class TrainEngine(Engine):
         elif self._arena_hi > 0:
             self._arena[:self._arena_hi].zero_()
         self._arena_off = 0
+        if self._big is None:
+            # allocated once the first step has shown how much is needed — never inside a graph capture (the buffer must outlive
+            # every graph that carves from it)
+            if self._big_need > 0 and not torch.cuda.is_current_stream_capturing():
+                self._big = torch.zeros(self._big_need, dtype=torch.float32, device="cuda")
+                self._big_hi = self._big_need     # sized by one step's needs: every later step clears all of it (a capture that
+                                                  # starts right after the allocation must record that memset too)
+        elif self._big_hi > 0:
+            self._big[:self._big_hi].zero_()
+        self._big_off, self._big_need = 0, 0
 
     def seed_output_grads(self, d_mask, d_cates, d_kerns, d_depth):
         """Cotangents of the training outputs (NCHW fp32 or None) -> NHWC 16-bit gradients of the dense tensors."""
@@ -1033,6 +1055,7 @@ class GraphedStep:
                     b.copy_(sv)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        eng.reset()                                      # allocates the large accumulator arena the warm-up sized (never inside a capture)
         if pack_in_graph:
             eng.repack_all(invalidate_others=False)      # uploads the pack tables (not allowed inside a capture); same values
             torch.cuda.synchronize()
