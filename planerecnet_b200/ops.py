@@ -159,6 +159,8 @@ def unpack_wgrad(dw, weight_shape, c_splits=None):
         c_splits = [(cin, round_up(cin, 64))]
     cpad = sum(p for _, p in c_splits)
     v = dw[:cout].view(cout, kh, kw, cpad)
+    if len(c_splits) == 1:                            # one source: a single strided copy (torch.cat of one part is a copy of its own)
+        return v[..., :c_splits[0][0]].permute(0, 3, 1, 2).contiguous()
     parts, off = [], 0
     for real, padded in c_splits:
         parts.append(v[..., off:off + real])

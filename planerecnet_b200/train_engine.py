@@ -156,7 +156,7 @@ class TrainEngine(Engine):
         if not recs:
             return False
         import struct
-        sig = tuple((r["w"].data_ptr(), r["out"].data_ptr()) for r in recs.values())
+        sig = tuple((r["w"].data_ptr(), r["out"].data_ptr()) + tuple(q.data_ptr() for pb in r["vec"] for q in pb) for r in recs.values())
         if self._pack_tab is None or self._pack_tab[0] != sig:
             assert not torch.cuda.is_current_stream_capturing(), "call repack_all() once outside the capture (it uploads its tables)"
             blob, work, smem = b"", [], 0
@@ -167,18 +167,24 @@ class TrainEngine(Engine):
                     smem = max(smem, r["cin"] * r["kk"] * 4)
             rec_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
             work_t = torch.tensor(work, dtype=torch.int32).cuda().contiguous()
-            self._pack_tab = (sig, rec_t, work_t, len(work), smem)
-        _, rec_t, work_t, nblk, smem = self._pack_tab
+            # the padded bias vectors: one prn_copy_multi_f32 launch (torch._foreach_copy_ issued one cudaMemcpy per vector: ~200)
+            dst, src = [], []
+            for r in recs.values():
+                for param, buf in r["vec"]:
+                    dst.append(buf[:param.numel()])
+                    src.append(param.detach())
+            vec = None
+            if dst:
+                vec = ops.CopyMulti(dst)
+                vec.set_sources(src)
+            self._pack_tab = (sig, rec_t, work_t, len(work), smem, vec)
+        _, rec_t, work_t, nblk, smem, vec = self._pack_tab
         L.check(self.lib.prn_pack_multi(C.c_void_p(rec_t.data_ptr()), C.c_void_p(work_t.data_ptr()), nblk, smem, self.dt, self._st()),
                 "prn_pack_multi")
         self.launches += 1
-        dst, src = [], []
-        for r in recs.values():
-            for param, buf in r["vec"]:
-                dst.append(buf[:param.numel()])
-                src.append(param.detach())
-        if dst:
-            torch._foreach_copy_(dst, src)
+        if vec is not None:
+            vec.run()
+            self.launches += 1
         if invalidate_others:
             for k in [k for k in self._packed if k not in recs]:
                 del self._packed[k]
