@@ -312,8 +312,9 @@ int prn_pack_dgrad_weight(const float* w, void* out16, int32_t cout, int32_t cin
                           int32_t rows_pad, int32_t cout_pad, int32_t dtype, void* stream);
 /* Every packed operand of a training step in one launch.  recs_dev: device array of 64-byte records
  * {const float* w; void* out; int32 kind (0 = prn_pack_conv_weight, 1 = prn_pack_dgrad_weight), cout, cin, k*k,
- *  then 7 int32: kind 0: cpad_tot, nsplit, lo0, real0, pad0, lo1, real1;  kind 1: lo, hi - lo, cout_pad, rows_pad, 0...};
- * work_dev: int32 pairs {record, output row (kind 1: first of 8 rows)}, one per thread block; smem_bytes = max over records of
+ *  then 7 int32: kind 0: cpad_tot, nsplit, lo0, real0, pad0, lo1, real1;  kind 1: lo, hi - lo, cout_pad, rows_pad, 0...; then int32
+ *  rows = output rows of the operand};
+ * work_dev: int32 pairs {record, first of 8 consecutive output rows}, one per thread block; smem_bytes = max over records of
  * cin*k*k*4. */
 int prn_pack_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, int32_t dtype, void* stream);
 /* Many fp32 vectors gathered in one launch (the parameter gradients of a training step into one flat buffer: the operand of the

@@ -161,8 +161,8 @@ class TrainEngine(Engine):
             assert not torch.cuda.is_current_stream_capturing(), "call repack_all() once outside the capture (it uploads its tables)"
             blob, work, smem = b"", [], 0
             for i, r in enumerate(recs.values()):
-                blob += struct.pack("<QQ11i4x", r["w"].data_ptr(), r["out"].data_ptr(), r["kind"], r["cout"], r["cin"], r["kk"], *r["f"])
-                work += [(i, n) for n in range(0, r["rows"], 8 if r["kind"] == 1 else 1)]   # dgrad blocks take 8 rows
+                blob += struct.pack("<QQ12i", r["w"].data_ptr(), r["out"].data_ptr(), r["kind"], r["cout"], r["cin"], r["kk"], *r["f"], r["rows"])
+                work += [(i, n) for n in range(0, r["rows"], 8)]          # a block takes 8 consecutive rows (kPackRows)
                 if r["kind"] == 0:
                     smem = max(smem, r["cin"] * r["kk"] * 4)
             rec_t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
