@@ -322,6 +322,11 @@ int prn_pack_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_bloc
  * {const float* src; float* dst; int64 n; int32 src_stride (elements); int32 pad}: dst[i] = scale * src[i * src_stride], i < n;
  * work_dev: int32 pairs {record, chunk}, one per thread block, chunk c covering elements [2048 c, 2048 (c + 1)). */
 int prn_copy_multi_f32(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, float scale, void* stream);
+/* Weight gradients of many convs from the accumulator layout of prn_conv2d_wgrad ([cout rows][k*k][cpad], fp32) to the parameter
+ * layout [cout][cin][k*k] in one launch (autograd's nn.Conv2d.weight.grad).  recs_dev: 40-byte records {const float* src; float* dst;
+ * int32 cout, cin, k*k, cpad, ld (floats per accumulator row), pad}; work_dev: int32 pairs {record, first of 8 output channels};
+ * smem_bytes = max over records of k*k*(cpad+1)*4. */
+int prn_unpack_wgrad_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, void* stream);
 
 /* torch.optim.Adam over all parameters in one launch (train.py:251-256: betas (0.9, 0.999), eps 1e-8, no weight decay, one
  * learning rate per parameter group).  table int64 [n][5] = {param, grad, exp_avg, exp_avg_sq device pointers (fp32), grad

@@ -101,7 +101,7 @@ EXPORTS = [
     "prn_conv2d_wgrad", "prn_conv2d_wgrad_plan", "prn_bn_finalize", "prn_bn_apply", "prn_bn_finalize_apply", "prn_chan_reduce", "prn_bn_bwd_apply",
     "prn_relu_bwd", "prn_add_strided", "prn_add_f32", "prn_add16", "prn_maxpool3x3s2_bwd", "prn_dcn_im2col",
     "prn_dcn_col2im_bwd", "prn_gn_bwd_reduce", "prn_gn_bwd_apply", "prn_avgpool2x2_bwd", "prn_upsample2x_bilinear_bwd",
-    "prn_resize_bilinear_bwd", "prn_reflect_fold", "prn_softplus_bwd_pad", "prn_pack_conv_weight", "prn_pack_dgrad_weight", "prn_pack_multi", "prn_copy_multi_f32", "prn_adam_multi", "prn_adam_multi_checked",
+    "prn_resize_bilinear_bwd", "prn_reflect_fold", "prn_softplus_bwd_pad", "prn_pack_conv_weight", "prn_pack_dgrad_weight", "prn_pack_multi", "prn_copy_multi_f32", "prn_unpack_wgrad_multi", "prn_adam_multi", "prn_adam_multi_checked",
     "prn_focal_loss", "prn_depth_rmselog_fwd", "prn_depth_rmselog_bwd", "prn_dice_lava_rows", "prn_dice_lava_bwd",
     "prn_lava_weights", "prn_vnl_triplets_fwd", "prn_vnl_triplets_bwd",
 ]

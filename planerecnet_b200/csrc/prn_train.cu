@@ -861,7 +861,49 @@ __global__ void __launch_bounds__(256) copy_multi_kernel(const CopyRec* __restri
   }
 }
 
+// ---- weight gradients: accumulator layout [cout rows][kh*kw][cpad] (the packed operand's layout) -> parameter layout
+//      [cout][cin][kh*kw], many convs in one launch (a torch permute + contiguous per conv before: ~140 launches per step).
+//      A block takes kUnpackRows output channels: each row goes through a padded shared-memory tile so that both the read of the
+//      accumulator row and the write of the parameter row are coalesced.
+struct UnpackRec {
+  const float* src;
+  float* dst;
+  int cout, cin, kk, cpad, ld, pad_;
+};
+static_assert(sizeof(UnpackRec) == 40, "UnpackRec is a 40-byte record (ops.UnpackMulti packs it)");
+constexpr int kUnpackRows = 8;
+
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const UnpackRec* __restrict__ recs, const int2* __restrict__ work) {
+  extern __shared__ float tile[];          // [kk][cpad + 1]
+  const int2 wk = work[blockIdx.x];
+  const UnpackRec r = recs[wk.x];
+  const int pitch = r.cpad + 1;
+  const int n_end = min(wk.y + kUnpackRows, r.cout);
+  for (int n = wk.y; n < n_end; ++n) {
+    const float* src = r.src + static_cast<long long>(n) * r.ld;
+    __syncthreads();
+    for (int i = threadIdx.x; i < r.kk * r.cpad; i += blockDim.x) {
+      const int tap = i / r.cpad, c = i - tap * r.cpad;
+      tile[tap * pitch + c] = __ldg(src + i);
+    }
+    __syncthreads();
+    float* dst = r.dst + static_cast<long long>(n) * r.cin * r.kk;
+    for (int i = threadIdx.x; i < r.cin * r.kk; i += blockDim.x) {
+      const int c = i / r.kk, tap = i - c * r.kk;
+      dst[i] = tile[tap * pitch + c];
+    }
+  }
+}
+
 }  // namespace prn
+
+extern "C" int prn_unpack_wgrad_multi(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, int32_t smem_bytes, void* stream) {
+  using namespace prn;
+  PRN_REQUIRE(recs_dev && work_dev && n_blocks > 0 && smem_bytes > 0 && smem_bytes <= 48 * 1024, "unpack_wgrad_multi: bad arguments");
+  unpack_wgrad_multi_kernel<<<n_blocks, 256, smem_bytes, static_cast<cudaStream_t>(stream)>>>(static_cast<const UnpackRec*>(recs_dev),
+                                                                                             reinterpret_cast<const int2*>(work_dev));
+  PRN_LAUNCH_CHECK();
+}
 
 extern "C" int prn_copy_multi_f32(const void* recs_dev, const int32_t* work_dev, int32_t n_blocks, float scale, void* stream) {
   using namespace prn;

@@ -342,3 +342,43 @@ class CopyMulti:
     def run(self, scale=1.0):
         L.check(L.lib().prn_copy_multi_f32(_vp(self.recs), _vp(self.work), self.n_blocks, C.c_float(scale), L.current_stream()),
                 "prn_copy_multi_f32")
+
+
+class UnpackMulti:
+    """Weight gradients of many convs, accumulator layout -> parameter layout, with ONE launch (prn_unpack_wgrad_multi) instead of a
+    permute + contiguous per conv.  Built for CUDA-graph capture: the device tables are allocated up front, add() / run() are
+    called while the backward is being captured (pointers and the grid size are known then), flush() uploads the table contents
+    after the capture has ended (the launch reads them at replay time)."""
+    ROWS = 8
+
+    def __init__(self, max_recs=1024, max_work=1 << 17):
+        self.recs = torch.zeros(40 * max_recs, dtype=torch.uint8, device="cuda")
+        self.work = torch.zeros(max_work, 2, dtype=torch.int32, device="cuda")
+        self.max_recs, self.max_work = max_recs, max_work
+        self.items, self.keep, self.ran = [], [], False
+
+    def add(self, dw, dst, weight_shape, cpad):
+        cout, cin, kh, kw = weight_shape
+        assert dw.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous() and dw.stride(1) == 1
+        assert dw.shape[0] >= cout and dw.shape[1] >= kh * kw * cpad and cin <= cpad and dst.numel() == cout * cin * kh * kw
+        self.items.append((dw.data_ptr(), dst.data_ptr(), cout, cin, kh * kw, cpad, dw.stride(0)))
+        self.keep += [dw, dst]
+
+    def run(self):
+        assert not self.ran and self.items and len(self.items) <= self.max_recs
+        self.n_blocks = sum((it[2] + self.ROWS - 1) // self.ROWS for it in self.items)
+        assert self.n_blocks <= self.max_work
+        self.smem = max(it[4] * (it[5] + 1) * 4 for it in self.items)
+        L.check(L.lib().prn_unpack_wgrad_multi(_vp(self.recs), _vp(self.work), self.n_blocks, self.smem, L.current_stream()),
+                "prn_unpack_wgrad_multi")
+        self.ran = True
+
+    def flush(self):
+        import struct
+        assert not torch.cuda.is_current_stream_capturing()
+        blob, work = b"", []
+        for i, (src, dst, cout, cin, kk, cpad, ld) in enumerate(self.items):
+            blob += struct.pack("<QQ6i", src, dst, cout, cin, kk, cpad, ld, 0)          # = sizeof(UnpackRec) = 40
+            work += [(i, n) for n in range(0, cout, self.ROWS)]
+        self.recs[:len(blob)].copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        self.work[:len(work)].copy_(torch.tensor(work, dtype=torch.int32))

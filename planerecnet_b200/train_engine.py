@@ -52,6 +52,8 @@ class TrainEngine(Engine):
         self._marks, self._pf_done = [], 0
         self._pack_recs, self._pack_tab = {}, None
         self._big, self._big_off, self._big_hi, self._big_need = None, 0, 0, 0
+        self._defer = None
+        self._fin_single = set()
 
     # ------------------------------------------------------------------ gradient bookkeeping
     def _take(self, t):
@@ -87,7 +89,27 @@ class TrainEngine(Engine):
         if cur is None:
             self.pgrads[id(p)] = g                      # may be a view of an accumulator: copied only if joined
         else:
+            assert self._defer is None or id(p) not in self._defer["dst_ids"], "a deferred weight gradient cannot be joined"
             self.pgrads[id(p)] = cur + g
+
+    def _fin_wgrad(self, p, dw, shape, c_splits):
+        """Weight gradient of a conv from its accumulator (layout of the packed operand) to the parameter layout.  While a graphed
+        step captures its backward (`self._defer`, set by GraphedStep) single-source convs are only RECORDED: one
+        prn_unpack_wgrad_multi launch at the end of the backward writes all of them — straight into the flat gradient buffer when
+        there is one — instead of a permute + contiguous per conv."""
+        if p is None or not p.requires_grad:
+            return
+        d = self._defer
+        if len(c_splits) == 1 and self.pgrads.get(id(p)) is None:
+            self._fin_single.add(id(p))                 # (what a later capture of the same step may defer)
+        if d is not None and id(p) in d["ids"] and len(c_splits) == 1 and self.pgrads.get(id(p)) is None:
+            views = d["views"]
+            dst = views[id(p)] if (views is not None and id(p) in views) else torch.empty(shape, dtype=torch.float32, device="cuda")
+            d["um"].add(dw, dst, shape, c_splits[0][1])
+            d["dst_ids"].add(id(p))
+            self.pgrads[id(p)] = dst
+            return
+        self._padd(p, ops.unpack_wgrad(dw, shape, c_splits))
 
     _ARENA_FLOATS = 4 << 20      # 16 MB of fp32 for the many small zero-initialised accumulators of one step
     _ARENA_MAX_ITEM = 1 << 16
@@ -316,7 +338,7 @@ class TrainEngine(Engine):
             self.wbufs[key] = dw
 
             def fin():
-                self._padd(conv.weight, ops.unpack_wgrad(dw, tuple(conv.weight.shape), c_splits))
+                self._fin_wgrad(conv.weight, dw, tuple(conv.weight.shape), c_splits)
 
             self.pfinal.append(fin)
         return dw
@@ -533,7 +555,7 @@ class TrainEngine(Engine):
                 self._padd(reg.bias, sums[:N, 0])
             dw = self._zeros(ops.round_up(N, 4), 9 * Cc)
             self._wgrad("wgrad_dcn", flops, col, dy, dw, batch=B, h_in=Ho, w_in=Wo, n=N, ksize=1, dtype=self.dt)
-            self.pfinal.append(lambda: self._padd(reg.weight, ops.unpack_wgrad(dw, tuple(reg.weight.shape), [(reg.in_channels, Cc)])))
+            self.pfinal.append(lambda: self._fin_wgrad(reg.weight, dw, tuple(reg.weight.shape), [(reg.in_channels, Cc)]))
             dcol = self._empty(B, Ho, Wo, 9 * Cc)
             with self._timed("dgrad_dcn", flops):
                 ops.conv2d(dy, wreg_t, batch=B, h_in=Ho, w_in=Wo, ksize=1, c0=N, out16=dcol, dtype=self.dt)
@@ -854,7 +876,7 @@ class TrainEngine(Engine):
             dw = self._zeros(4, 9 * Cx)
             self._wgrad("wgrad3x3", 2.0 * Bx * Hx * Wx * Cx * 9, xin, dpre, dw, batch=Bx, h_in=Hx, w_in=Wx, n=1, ksize=3, stride=1,
                         pad=1, pad_mode=L.PAD_REFLECT, dtype=self.dt)
-            self.pfinal.append(lambda: self._padd(dconv.weight, ops.unpack_wgrad(dw, tuple(dconv.weight.shape), [(Cx, Cx)])))
+            self.pfinal.append(lambda: self._fin_wgrad(dconv.weight, dw, tuple(dconv.weight.shape), [(Cx, Cx)]))
             self.launches += 3
             self._dgrad(xin, dconv, dpre, 0, Cx, Cx, 3, 1, 1, L.PAD_REFLECT, 1, (Bx, Hx, Wx), 2.0 * Bx * Hx * Wx * Cx * 9)
 
@@ -944,6 +966,9 @@ class TrainEngine(Engine):
         self._join_wgrad()
         for fn in self.pfinal[self._pf_done:]:
             fn()
+        if self._defer is not None and self._defer["um"].items:
+            self._defer["um"].run()                     # every recorded weight gradient, accumulator -> parameter layout, one launch
+            self.launches += 1
         grads = self.pgrads
         self.tape, self.grads, self.wbufs, self.pfinal, self._keep = [], {}, {}, [], []
         self._marks, self._pf_done = [], 0
@@ -1055,7 +1080,9 @@ class GraphedStep:
             outs = eng.forward_train(net, self.sx)
             eng.seed_output_grads(torch.zeros_like(outs[0]), [torch.zeros_like(c) for c in outs[1]],
                                   [torch.zeros_like(k) for k in outs[2]], torch.zeros_like(outs[3]))
+            eng._fin_single = set()
             warm_ids = set(eng.backward().keys())
+            defer_ids = set(eng._fin_single)          # conv weights whose gradient is one accumulator -> one deferred unpack
             with torch.no_grad():
                 for b, sv in zip(bn_bufs, bn_saved):
                     b.copy_(sv)
@@ -1091,17 +1118,27 @@ class GraphedStep:
                     off += p.numel()
                 self.flat_views, self.bucket_slices = views, [(0, off)]
                 self.flat_params = params
-                gather = ops.CopyMulti([views[id(p)] for p in params])
+                # deferred weight gradients are unpacked straight into their flat views: the gather only moves the others
+                rest = [p for p in params if id(p) not in defer_ids]
+                gather = ops.CopyMulti([views[id(p)] for p in rest]) if rest else None
+            um = ops.UnpackMulti()
             self.g_bwd = torch.cuda.CUDAGraph()
             n0 = eng.launches
             with _no_gc(), torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
                 eng.seed_output_grads(*self.cots)
-                self.grads = eng.backward()
-                if use_flat:
-                    srcs = gather.normalise([self.grads[id(p)].reshape(p.shape) for p in params])
+                eng._defer = dict(ids=defer_ids, views=views if use_flat else None, um=um, dst_ids=set())
+                try:
+                    self.grads = eng.backward()
+                finally:
+                    eng._defer = None
+                if use_flat and gather is not None:
+                    srcs = gather.normalise([self.grads[id(p)].reshape(p.shape) for p in rest])
                     gather.run()
                     eng.launches += 1
-            if use_flat:
+            if um.ran:
+                um.flush()                            # table contents of the deferred unpack: read by the launch at replay time
+            self._unpack = um
+            if use_flat and gather is not None:
                 gather.set_sources(srcs)              # table contents: read by the launch at replay time
                 self._gather = gather
             self.bwd_launches = eng.launches - n0
