@@ -731,6 +731,10 @@ class PlaneRecNetLoss(torch.nn.Module):
         dev = gt_instances[0]["masks"].device
         if background is None:
             background = dev.type == "cuda"
+        if self._prep is not None:
+            # an earlier preparation that was never consumed: let its threads end before a new sampler touches numpy's stream
+            self._drain(self._prep)
+            self._prep = None
         prep = dict(key=tuple(id(g["masks"]) for g in gt_instances), keep=[g["masks"] for g in gt_instances], feat_hw=feat_hw,
                     targets=None, vnl=None, thread=None, error=None, done=None)
 
@@ -765,6 +769,17 @@ class PlaneRecNetLoss(torch.nn.Module):
         return prep
 
     @staticmethod
+    def _drain(prep):
+        """Wait for every thread of a preparation (its worker and the plane term's sampler) without consuming it."""
+        if prep.get("thread") is not None:
+            prep["thread"].join()
+            prep["thread"] = None
+        vnl = prep.get("vnl")
+        if vnl is not None and vnl.get("thread") is not None:
+            vnl["thread"].join()
+            vnl["thread"] = None
+
+    @staticmethod
     def _finish(prep, dev):
         """Join a background preparation and order the consumer's stream after it."""
         if prep["thread"] is not None:
@@ -787,6 +802,7 @@ class PlaneRecNetLoss(torch.nn.Module):
                 elif isinstance(o, (list, tuple)):
                     for v in o:
                         rec(v)
+                    rec(getattr(o, "dense", None))          # targets.TargetsBatch: the batch-layout tensors
 
             rec(prep["targets"])
             rec(prep["vnl"])
@@ -800,7 +816,7 @@ class PlaneRecNetLoss(torch.nn.Module):
         fh, fw = mask_preds.shape[-2:]
         prep, self._prep = self._prep, None
         if prep is not None and (prep["key"] != tuple(id(g["masks"]) for g in gt_instances) or prep["feat_hw"] != (fh, fw)):
-            self._finish(prep, mask_preds.device)                        # a stale preparation: let it end, then ignore it
+            self._drain(prep)                                            # a stale preparation: let its threads end, then ignore it
             prep = None
         if prep is None:
             prep = self.prepare(gt_instances, (fh, fw), background=False)

@@ -122,3 +122,34 @@ def test_batched_assignment_equals_per_image_assignment(name):
         for (ri, rc, rd, ro), (gi, gc, gd, go) in zip(rb, gb):
             assert go == ro and torch.equal(gc, rc) and torch.equal(gd, rd)
             assert gi.shape == ri.shape and gi.dtype == ri.dtype and torch.equal(gi, ri)
+
+
+def test_unconsumed_preparation_is_drained_before_the_next_one():
+    """PlaneRecNetLoss.prepare(A) followed by prepare(B) without a forward in between: A's sampler thread has finished (and has
+    advanced numpy's global stream by exactly its draws) before B's starts, so B's loss equals the one of a run that drew A's
+    triplets and then B's, in order."""
+    import numpy as np
+    from loss_emulation import EmuBackend
+    from planerecnet_b200 import losses as PL
+    from planerecnet_b200.config import cfg, set_cfg
+    set_cfg("PlaneRecNet_101_config")
+    names = list(LC.CASES)
+    a = LC.synth(**LC.CASES[names[0]])
+    b = LC.synth(**LC.CASES[names[1]])
+
+    def loss_b(crit):
+        mask, cate, kern, depth, gts, gt_depth = b
+        return crit(None, mask, cate, kern, depth, gts, gt_depth)["pln"].detach().double()
+
+    np.random.seed(3)
+    crit = PL.PlaneRecNetLoss(cfg, backend=EmuBackend())
+    crit.prepare(a[4])                     # never consumed
+    crit.prepare(b[4])
+    got = loss_b(crit)
+    np.random.seed(3)
+    ref_crit = PL.PlaneRecNetLoss(cfg, backend=EmuBackend())
+    pa = ref_crit.vnl_batched.prepare(a[4])
+    if pa["thread"] is not None:
+        pa["thread"].join()
+    ref = loss_b(ref_crit)
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref)), (got, ref)
