@@ -11,8 +11,10 @@ all-reduce (mean) over NCCL.
   value   : images/s of that step with inputs resident in HBM, backward driven by fixed seeded cotangents of the 10
             output tensors (config 4 (i), the kernel-only step the 808.2 GF/image figure describes), CUDA-graph replay,
             device-timed (CUDA events), max over ranks.
-  e2e     : images/s of the step a user runs through the public API (config 4 (ii)): pinned HOST images + ground truth ->
-            H2D -> `net(x)` -> `PlaneRecNetLoss` -> `loss.backward()` (+ all-reduce) -> D2H of the five loss terms.
+  e2e     : images/s of the loop a user runs through the public API (config 4 (ii)), with one batch of look-ahead like a
+            prefetching DataLoader: pinned HOST images + ground truth -> H2D (copy stream) -> `crit.prepare(gts)` -> `net(x)` ->
+            `PlaneRecNetLoss` -> `loss.backward()` (+ all-reduce) -> D2H of the five loss terms + stream sync, every step;
+            `no_lookahead` and `device_sampling` variants beside it.
   inference: the eval-mode dense forward (configs 2 / 3; north_star's >= 70 % tensor-pipe target is quoted on it) with its
             own value / e2e (`net.infer_pipelined`) and the per-kind conv roofline.
   gpu_reference: the UNMODIFIED reference (baseline/_ref) on the same B200 through cuDNN + torchvision deform_conv2d:
