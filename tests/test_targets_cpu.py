@@ -153,3 +153,29 @@ def test_unconsumed_preparation_is_drained_before_the_next_one():
         pa["thread"].join()
     ref = loss_b(ref_crit)
     assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ref)), (got, ref)
+
+
+@pytest.mark.parametrize("name", list(LC.CASES))
+def test_dense_batch_layout_matches_the_per_level_lists(name):
+    """TargetsBatch.dense (what losses._InsLava gathers from in one shot) against the per-(image, level) results it replaces: row r
+    of image b is the r-th positive cell in level order, gidx = level offset + cell, tgt row = that cell's target mask, valid marks
+    exactly the n_b real rows, cate = the level-concatenated label maps, padding rows are zero."""
+    _, _, _, _, gts, _ = LC.synth(**LC.CASES[name])
+    grids = LO.CFG["grids"]
+    tb = T.assign_targets_batch(gts, (120, 160), grids, LO.CFG["scale_ranges"], LO.CFG["num_classes"], LO.CFG["sigma"])
+    d = tb.dense
+    offs = [sum(S * S for S in grids[:l]) for l in range(len(grids))]
+    assert d["level_off"] == offs and d["n"] % 16 == 0 and d["tgt"].shape == (len(gts), d["n"], 120 * 160)
+    for b, per_level in enumerate(tb):
+        rows_idx, rows_tgt = [], []
+        for l, (ins, cate, ind, order) in enumerate(per_level):
+            rows_idx += [offs[l] + c for c in order]
+            rows_tgt.append(ins.reshape(len(order), -1))
+            assert torch.equal(d["cate"][b, offs[l]:offs[l] + grids[l] ** 2].view(grids[l], grids[l]), cate)
+        n_b = len(rows_idx)
+        assert d["n_b"][b] == n_b
+        assert d["gidx"][b, :n_b].tolist() == rows_idx
+        assert bool(d["valid"][b, :n_b].all()) and not bool(d["valid"][b, n_b:].any())
+        if n_b:
+            assert torch.equal(d["tgt"][b, :n_b], torch.cat(rows_tgt))
+        assert int(d["tgt"][b, n_b:].sum()) == 0
