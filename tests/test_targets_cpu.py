@@ -170,7 +170,7 @@ def test_dense_batch_layout_matches_the_per_level_lists(name):
         rows_idx, rows_tgt = [], []
         for l, (ins, cate, ind, order) in enumerate(per_level):
             rows_idx += [offs[l] + c for c in order]
-            rows_tgt.append(ins.reshape(len(order), -1))
+            rows_tgt.append(ins.reshape(len(order), 120 * 160))
             assert torch.equal(d["cate"][b, offs[l]:offs[l] + grids[l] ** 2].view(grids[l], grids[l]), cate)
         n_b = len(rows_idx)
         assert d["n_b"][b] == n_b
