@@ -90,3 +90,48 @@ def test_numpy_py_sampling_gives_the_same_loss_as_the_c_sampler():
     _, got_c, _, _ = _both("loss_seed0", sampling="numpy")
     _, got_py, _, _ = _both("loss_seed0", sampling="numpy_py")
     assert torch.equal(torch.nan_to_num(got_c), torch.nan_to_num(got_py))
+
+
+def test_c_sampler_property_random_region_lists():
+    """Property test (hypothesis) of prn_numpy_choice_shuffle: arbitrary region sizes (incl. powers of two and their neighbours,
+    where the rejection mask changes), arbitrary draw counts k <= n, arbitrary stream positions — indices and the stream afterwards
+    equal numpy's for every example."""
+    import ctypes as C
+    from hypothesis import given, settings, strategies as st
+    from planerecnet_b200 import _lib as L
+
+    sizes = st.one_of(st.integers(1, 5000), st.sampled_from([1, 2, 3, 4, 5, 7, 8, 9, 255, 256, 257, 1023, 1024, 1025, 4095, 4096, 4097]))
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.tuples(sizes, st.floats(0.0, 1.0)), min_size=1, max_size=6), st.integers(0, 2 ** 31 - 1), st.integers(0, 700),
+           st.integers(1, 3))
+    def check(regions, seed, burn, repeats):
+        ns = [n for n, _ in regions]
+        ks = [int(n * f) for n, f in regions]
+        T = sum(ks)
+        np.random.seed(seed)
+        np.random.random_sample(burn)
+        ref = np.full((repeats, T + 1), -1, dtype=np.int32)
+        off = 0
+        for n, k in zip(ns, ks):
+            if k:
+                for j in range(repeats):
+                    p = np.random.choice(n, k, replace=True)
+                    np.random.shuffle(p)
+                    ref[j, off:off + k] = p
+            off += k
+        ref_state = np.random.get_state()
+        np.random.seed(seed)
+        np.random.random_sample(burn)
+        s0 = np.random.get_state()
+        key = np.ascontiguousarray(s0[1], dtype=np.uint32).copy()
+        pos = C.c_int32(int(s0[2]))
+        out = np.full((repeats, T + 1), -1, dtype=np.int32)
+        n_arr, k_arr = np.asarray(ns, dtype=np.int64), np.asarray(ks, dtype=np.int64)
+        L.check(L.lib().prn_numpy_choice_shuffle(key.ctypes.data_as(C.c_void_p), C.byref(pos), n_arr.ctypes.data_as(C.c_void_p),
+                                                 k_arr.ctypes.data_as(C.c_void_p), len(ns), repeats, out.ctypes.data_as(C.c_void_p),
+                                                 out.strides[0] // 4), "prn_numpy_choice_shuffle")
+        assert np.array_equal(out, ref)
+        assert pos.value == ref_state[2] and np.array_equal(key, ref_state[1])
+
+    check()
