@@ -36,6 +36,17 @@ sys.path.insert(0, ROOT)
 # copy / forward / bookkeeping streams of the serving loop); streams that alias onto one queue serialise falsely
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
+# stdout carries exactly ONE line, the JSON: everything else that writes to file descriptor 1 (NCCL's version banner under torchrun,
+# library chatter) is sent to stderr, and the line itself goes to a duplicate of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 METRIC = "images/sec 480x640 ResNet101-DCN fwd+bwd"
 H_IMG, W_IMG = 480, 640
 # algorithmic GFLOP per image of the conv-like contractions as the reference executes them
@@ -179,7 +190,7 @@ def main():
                                        f"1 image per step (bounded sample of bs={a.batch})"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- the reference on the same B200 (own process, first:
@@ -582,7 +593,7 @@ def main():
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "train_step": train_detail, "inference": inference,
                 "gpu_reference": gpu_ref}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
